@@ -1,0 +1,202 @@
+/* slam_b200.h — C ABI of the B200 (sm_100a) scan-registration engine.
+ *
+ * This is the drop-in boundary for the data-parallel front end of kaushik884/LiDAR-SLAM-from-scratch.  The
+ * reference has no FFI: its hot path is the header-only C++ API in namespace slam (slam_viz/include/slam_viz/core/)
+ * called from slam_viz/src/ros/slam_node.cpp.  Every entry point below names the reference interface it replaces
+ * (paths relative to the reference root).  The C++17 header mirror that keeps the reference's class and function
+ * names on top of this ABI lives in lidar-slam-from-scratch_b200/host/slam_viz/core/.
+ *
+ * Conventions
+ *   - extern "C", POD only, no exceptions cross the ABI.  Every function returns an sb_status (0 = SB_OK);
+ *     sb_last_error(ctx) gives the message of the last failure on that context.
+ *   - Point clouds are row-major contiguous fp64 xyz (exactly PointCloud::Matrix::data(), types.hpp:17).
+ *   - Functions without a _dev suffix take HOST pointers and return to HOST buffers owned by the caller (value
+ *     semantics like the reference).  *_dev functions take DEVICE pointers on the context's device and enqueue on the
+ *     context's stream without synchronising unless stated.
+ *   - A context (one per host thread and device) owns the stream, the workspace arena and all index/database
+ *     objects created from it.  There is NO CPU fallback: if no sm_100-class device is usable, sb_ctx_create fails.
+ */
+#ifndef SLAM_B200_H
+#define SLAM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum sb_status {
+    SB_OK = 0,
+    SB_ERR_INVALID_ARG = 1,   /* null pointer, negative size, k out of range ...                                  */
+    SB_ERR_EMPTY = 2,         /* empty cloud where the reference would be undefined behaviour (kdtree.hpp:25,119) */
+    SB_ERR_CUDA = 3,          /* a CUDA runtime call failed; message in sb_last_error                              */
+    SB_ERR_NO_DEVICE = 4,     /* no usable CUDA device                                                             */
+    SB_ERR_RANGE = 5,         /* voxel keys of one call span more than 2^63 packed cells, or non-finite input      */
+    SB_ERR_CAPACITY = 6       /* caller-provided output capacity too small                                         */
+} sb_status;
+
+typedef struct sb_ctx sb_ctx;
+typedef struct sb_index sb_index;   /* replaces slam::KDTree / NearestNeighborSearch (kdtree.hpp:18-221)          */
+typedef struct sb_loop sb_loop;     /* replaces slam::LoopClosureDetector (loop_closure.hpp:41-149)               */
+
+#define SB_SC_RINGS 20              /* scan_context.hpp:27 */
+#define SB_SC_SECTORS 60            /* scan_context.hpp:28 */
+#define SB_SC_SIZE 1200
+#define SB_MAX_K 32                 /* largest k of sb_index_knn / sb_estimate_normals                            */
+#define SB_MAX_ICP_ITERATIONS 128   /* largest ICPConfig::max_iterations; history holds max_iterations + 1 values */
+
+/* slam::ICPConfig (types.hpp:143-148) + the normals k that icp.hpp:170 hard-codes to 20. */
+typedef struct sb_icp_config {
+    int32_t max_iterations;       /* 50   */
+    int32_t normals_k;            /* 20   */
+    double tolerance;             /* 1e-6 */
+    double min_error;             /* 1e-9 */
+    double initial_transform[16]; /* row-major 4x4, identity */
+} sb_icp_config;
+
+/* slam::ICPResult (types.hpp:155-164). */
+typedef struct sb_icp_result {
+    double transformation[16];    /* row-major 4x4 */
+    double final_error;
+    int32_t converged;
+    int32_t num_iterations;       /* = history_len - 1 (icp.hpp:255) */
+    int32_t history_len;
+    int32_t status;               /* per-pair sb_status in batch calls */
+    double error_history[SB_MAX_ICP_ITERATIONS + 1];
+} sb_icp_result;
+
+/* slam::LoopClosureConfig (loop_closure.hpp:14-19) + the constants loop_closure.hpp:105-107 / icp.hpp:170 hard-code. */
+typedef struct sb_loop_config {
+    int32_t frame_gap;              /* 50   */
+    int32_t max_candidates;         /* 3    */
+    double sc_distance_threshold;   /* 0.25 */
+    double icp_fitness_threshold;   /* 0.3  */
+    int32_t icp_max_iterations;     /* 30   */
+    int32_t normals_k;              /* 20   */
+    double icp_tolerance;           /* 1e-6 */
+    int32_t verify_chunk;           /* candidates ICP-verified concurrently per round (0 -> max_candidates)      */
+    int32_t reserved;
+} sb_loop_config;
+
+/* slam::LoopClosureResult (loop_closure.hpp:25-31). */
+typedef struct sb_loop_result {
+    int32_t query_frame;
+    int32_t match_frame;
+    double transform[16];
+    double scan_context_distance;
+    double icp_fitness;
+} sb_loop_result;
+
+/* ---------------------------------------------------------------- context ---------------------------------- */
+const char* sb_version(void);
+/* stream: a cudaStream_t to enqueue on (e.g. torch's current stream) or NULL to let the context create its own. */
+int sb_ctx_create(int device, void* stream, sb_ctx** out);
+void sb_ctx_destroy(sb_ctx* ctx);
+const char* sb_last_error(const sb_ctx* ctx);
+int sb_ctx_synchronize(sb_ctx* ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+int64_t sb_ctx_launch_count(const sb_ctx* ctx);
+void sb_default_icp_config(sb_icp_config* cfg);
+void sb_default_loop_config(sb_loop_config* cfg);
+
+/* ---------------------------------------------------------------- voxel grid ------------------------------- */
+/* Replaces slam::voxel_downsample (file_utils.hpp:41-44, file_utils.cpp:148-196).
+ * key = (long long)floor(coord / voxel) per axis with true IEEE division; centroid = sum over the voxel's points
+ * in ascending input index, divided by the count.  Output rows are in ascending (kx,ky,kz) order (the reference's
+ * unordered_map order is unspecified).  voxel <= 0 returns the input unchanged (file_utils.cpp:152).
+ * out_xyz must hold n*3 doubles; out_keys (optional) n*3 int64. */
+int sb_voxel_downsample(sb_ctx* ctx, const double* xyz, int64_t n, double voxel, double* out_xyz, int64_t* out_m,
+                        int64_t* out_keys);
+/* Batch of clouds in CSR form: cloud c is rows [offsets[c], offsets[c+1]).  out_offsets has n_clouds+1 entries. */
+int sb_voxel_downsample_batch(sb_ctx* ctx, const double* xyz, const int64_t* offsets, int32_t n_clouds, double voxel,
+                              double* out_xyz, int64_t* out_offsets, int64_t* out_keys);
+/* Device variant: d_xyz / d_out_xyz / d_out_keys are device pointers (d_out_* sized for the INPUT row count),
+ * offsets are host arrays.  Synchronises once to learn the output sizes. */
+int sb_voxel_downsample_batch_dev(sb_ctx* ctx, const double* d_xyz, const int64_t* offsets, int32_t n_clouds,
+                                  double voxel, double* d_out_xyz, int64_t* out_offsets, int64_t* d_out_keys);
+
+/* ---------------------------------------------------------------- spatial index ---------------------------- */
+/* Replaces slam::KDTree::KDTree (kdtree.hpp:20-26): copies the points to the device and builds the index. */
+int sb_index_build(sb_ctx* ctx, const double* xyz, int64_t n, sb_index** out);
+void sb_index_free(sb_index* index);
+int64_t sb_index_size(const sb_index* index);
+/* Replaces KDTree::nearest / nearest_batch (kdtree.hpp:32-59): exact 1-NN, squared distance
+ * (dx*dx + dy*dy) + dz*dz in fp64 without FMA, smallest index among exact ties.  out_d2 may be NULL.
+ * An empty index yields index -1 and DBL_MAX like kdtree.hpp:33-36. */
+int sb_index_nearest_batch(sb_index* index, const double* queries, int64_t nq, int32_t* out_idx, double* out_d2);
+/* Replaces KDTree::k_nearest (kdtree.hpp:65-78) for nq queries: row q holds min(k, size) indices ascending by
+ * (d2, index), padded with -1 (and DBL_MAX in out_d2, optional).  1 <= k <= SB_MAX_K. */
+int sb_index_knn(sb_index* index, const double* queries, int64_t nq, int32_t k, int32_t* out_idx, double* out_d2);
+/* Replaces NearestNeighborSearch::find_correspondences (kdtree.hpp:198-214): matched target rows and sqrt(d2). */
+int sb_index_find_correspondences(sb_index* index, const double* source, int64_t ns, double* matched_xyz,
+                                  double* distances);
+/* Replaces slam::estimate_normals(points, tree, k) (icp.hpp:23-67) for points == the indexed cloud.
+ * out_normals: size*3 doubles, row i for input row i.  out_evals (optional): the 3 eigenvalues ascending per point. */
+int sb_estimate_normals(sb_index* index, int32_t k, double* out_normals, double* out_evals);
+
+/* ---------------------------------------------------------------- ICP -------------------------------------- */
+/* Replaces slam::solve_point_to_plane (icp.hpp:89-144): one Gauss-Newton step from given correspondences. */
+int sb_solve_point_to_plane(sb_ctx* ctx, const double* source, const double* target, const double* normals,
+                            int64_t n, double* out_T16);
+/* Replaces slam::icp_point_to_plane(source, target, config) (icp.hpp:157-258). */
+int sb_icp_point_to_plane(sb_ctx* ctx, const double* source, int64_t ns, const double* target, int64_t nt,
+                          const sb_icp_config* cfg, sb_icp_result* out);
+/* Batched registration of independent pairs over a set of clouds (CSR).  pair p registers source cloud
+ * pair_src[p] onto target cloud pair_tgt[p]; every cloud used as a target gets ONE index + normals.
+ * voxel > 0 first applies sb_voxel_downsample to every cloud (slam_node.cpp:122).  sc_desc (optional) receives
+ * the Scan Context of every (downsampled) cloud, n_clouds*1200 doubles (loop_closure.hpp:53-59). */
+int sb_register_batch(sb_ctx* ctx, const double* xyz, const int64_t* offsets, int32_t n_clouds, double voxel,
+                      const int32_t* pair_src, const int32_t* pair_tgt, int32_t n_pairs, const sb_icp_config* cfg,
+                      sb_icp_result* results, double* sc_desc);
+/* Same with the clouds already in device memory; results/sc_desc are host buffers (one D2H copy at the end). */
+int sb_register_batch_dev(sb_ctx* ctx, const double* d_xyz, const int64_t* offsets, int32_t n_clouds, double voxel,
+                          const int32_t* pair_src, const int32_t* pair_tgt, int32_t n_pairs,
+                          const sb_icp_config* cfg, sb_icp_result* results, double* sc_desc);
+
+/* ---------------------------------------------------------------- Scan Context ----------------------------- */
+/* Replaces slam::ScanContext::compute (scan_context.hpp:44-82).  desc: 1200 doubles, COLUMN-major 20x60 like
+ * Eigen::MatrixXd::data(): element (ring i, sector j) at desc[j*20 + i]. */
+int sb_sc_compute(sb_ctx* ctx, const double* xyz, int64_t n, double* desc);
+/* Replaces ScanContext::distance (scan_context.hpp:90-102,121-142): min over the 60 column shifts of b. */
+int sb_sc_distance(sb_ctx* ctx, const double* desc_a, const double* desc_b, double* out);
+/* One query against n_db database descriptors (contiguous, 1200 doubles each): out_dist[n_db]. */
+int sb_sc_distance_batch(sb_ctx* ctx, const double* query, const double* db, int32_t n_db, double* out_dist);
+/* ScanContext::ring_key / sector_key (scan_context.hpp:107-118): row means (20) / column means (60). */
+int sb_sc_keys(sb_ctx* ctx, const double* desc, double* ring_key20, double* sector_key60);
+
+/* ---------------------------------------------------------------- loop closure ----------------------------- */
+/* Replaces slam::LoopClosureDetector (loop_closure.hpp:41-149).  The descriptor database and the cloud copies live
+ * in device memory.  rank/world shard the database by entry id (entry i is owned by rank i % world): every rank
+ * adds every frame, keeps the descriptors and clouds it owns, and sb_loop_candidates_local returns the local
+ * part of the candidate list; the caller gathers (NCCL) and passes the merged list to sb_loop_verify. */
+int sb_loop_create(sb_ctx* ctx, const sb_loop_config* cfg, int32_t rank, int32_t world, sb_loop** out);
+void sb_loop_free(sb_loop* loop);
+int sb_loop_add_frame(sb_loop* loop, const double* xyz, int64_t n, int32_t frame_idx);      /* addFrame, :53-59  */
+/* Adds a frame whose Scan Context is already known (database bulk load; the cloud is still copied). */
+int sb_loop_add_frame_desc(sb_loop* loop, const double* xyz, int64_t n, int32_t frame_idx, const double* desc);
+int64_t sb_loop_size(const sb_loop* loop);                                                    /* size(), :131      */
+int sb_loop_clear(sb_loop* loop);                                                             /* clear(), :136-141 */
+/* detect() (loop_closure.hpp:66-126) on a single rank (world == 1). */
+int sb_loop_detect(sb_loop* loop, sb_loop_result* results, int32_t capacity, int32_t* count);
+/* Stage 1 of detect(): candidates with frame gap >= frame_gap and distance < threshold among the entries this
+ * rank owns, ascending by (distance, entry id) (loop_closure.hpp:75-92); at most `capacity` are returned,
+ * *count is the number found. */
+int sb_loop_candidates_local(sb_loop* loop, double* dist, int32_t* entry, int32_t capacity, int32_t* count);
+/* Stage 2 for the listed entries (this rank must own them): ICP(query cloud -> entry cloud) for each,
+ * loop_closure.hpp:99-109.  Fills results[i] for every listed entry (icp_fitness = final_error) and converged[i]. */
+int sb_loop_verify_entries(sb_loop* loop, const int32_t* entry, const double* dist, int32_t n, sb_loop_result* results,
+                           int32_t* converged);
+
+/* ---------------------------------------------------------------- bench/test input generator --------------- */
+/* Synthetic 64/128-beam raycast straight into device memory (synth/lidar_synth.h).  boxes: host, n_boxes*6 floats;
+ * poses: host, n_scans*3 doubles (x, y, yaw); d_xyz: device, n_scans*beams*azimuth_steps*3 doubles capacity;
+ * out_offsets: host, n_scans+1.  Not part of the reference's API. */
+int sb_synth_scans_dev(sb_ctx* ctx, int32_t beams, int32_t azimuth_steps, float elev_top_deg, float elev_bot_deg,
+                       float max_range, float noise_sigma, float sensor_height, const float* boxes, int32_t n_boxes,
+                       const double* poses, int32_t n_scans, uint64_t noise_seed, double* d_xyz,
+                       int64_t* out_offsets);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLAM_B200_H */
