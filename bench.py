@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark: ICP scan-pairs/s on the KITTI-shaped synthetic odometry sequence
+(BASELINE.json configs[1]: 1000 frame pairs, 64-beam ~120k-point scans, voxel 0.5 m, normals k=20, ICP 50 it / 1e-6,
+Scan Context of every frame).
+
+A step = one pass of the whole front end over the sequence: voxel grid -> Scan Context -> index build -> normals ->
+batched point-to-plane ICP of the F consecutive pairs -> results on the host.
+  value : pairs/s with the raw scans already resident in HBM (sb_register_batch_dev), CUDA-event timed.
+  e2e   : the same through sb_register_batch with HOST (pinned) scans: H2D of every scan + D2H of results inside the
+          timed region.
+  N > 1 : one process per GPU, every rank registers its own sequence (weak scaling), results all-gathered over NCCL.
+--impl reference times the CPU oracle (the reference's algorithm restated: it cannot be compiled here) on all host
+cores over a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "lidar-slam-from-scratch_b200", "python"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+SENSOR = dict(beams=64, azimuth_steps=1875, elev_top_deg=2.0, elev_bot_deg=-24.8, max_range=120.0, noise_sigma=0.02,
+              sensor_height=1.73)
+VOXEL = 0.5
+LOOP_LEN_M = 1200.0
+RADIUS = LOOP_LEN_M / (2.0 * np.pi)
+
+
+def make_world(synth):
+    """Box city around a 1.2 km circular loop."""
+    half = RADIUS + 100.0
+    n_boxes = int(400 * (2 * half) ** 2 / 180.0 ** 2)
+    return synth.scene(11, n_boxes=n_boxes, half_extent=half, path_kind=1, radius=RADIUS, corridor_half=6.0)
+
+
+def make_poses(synth, n_scans, step_m=1.0):
+    return np.stack([synth.pose(1, RADIUS, i * step_m) for i in range(n_scans)])
+
+
+class ClockSampler:
+    def __init__(self, device):
+        self.device = device
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                out = subprocess.check_output(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
+                                               str(self.device)], timeout=5).decode().strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for n, v in zip(names, out[2:]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def start(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=10)
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def cpu_pair(orc, raw_src, raw_tgt):
+    """The reference's per-frame front end on the CPU oracle: voxel_downsample of the new frame + icp_point_to_plane
+    (slam_node.cpp:122,132-138) + Scan Context (loop_closure.hpp:55), with the reference's doubled NN search."""
+    ds, _ = orc.voxel_downsample(raw_src, VOXEL)
+    dt, _ = orc.voxel_downsample(raw_tgt, VOXEL)  # (the reference keeps the previous frame's downsampled cloud; see below)
+    orc.sc_compute(ds)
+    return orc.icp_point_to_plane(ds, dt, faithful_cost=1)
+
+
+def run_reference(args):
+    """--impl reference: CPU oracle on all host cores over a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle_lib
+    from concurrent.futures import ThreadPoolExecutor
+    orc, syn = oracle_lib.Oracle(), oracle_lib.Synth()
+    cores = os.cpu_count() or 1
+    world = make_world(syn)
+    n_pairs = max(cores, min(2 * cores, 64))
+    poses = make_poses(syn, n_pairs + 1)
+    scans = [syn.scan(SENSOR, world, poses[i], 1000 + i, threads=cores) for i in range(n_pairs + 1)]
+    ds = [None] * (n_pairs + 1)
+
+    def one(i):  # ctypes releases the GIL: real parallelism over independent pairs
+        d, _ = orc.voxel_downsample(scans[i + 1], VOXEL)
+        orc.sc_compute(d)
+        t, _ = orc.voxel_downsample(scans[i], VOXEL)
+        return orc.icp_point_to_plane(d, t, faithful_cost=1)["num_iterations"]
+
+    def step():
+        with ThreadPoolExecutor(cores) as ex:
+            return list(ex.map(one, range(n_pairs)))
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    value = n_pairs / dt
+    sample = f"{n_pairs} consecutive pairs of the sequence per step, {cores} threads, one pair per task"
+    print(json.dumps({
+        "impl": "reference", "metric": "ICP scan-pairs/s", "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(n_pairs, note="bounded sample"),
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(frames, note=None):
+    c = {"workload": f"C2: {frames}-pair frame-to-frame odometry on a KITTI-shaped synthetic sequence "
+                     "(64 beams x 1875 az, ~119k pts/scan, 1 m/frame on a 1.2 km loop)",
+         "voxel_m": VOXEL, "normals_k": 20, "icp_max_iterations": 50, "icp_tolerance": 1e-6,
+         "stages": "voxel_downsample + ScanContext + index + normals + point-to-plane ICP",
+         "l2": "inputs (GBs of raw scans) are larger than the 126 MB L2"}
+    if note:
+        c["note"] = note
+    return c
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=1000, help="pairs per step (1000 = the full C2 sequence)")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import oracle_lib
+    import slam_b200
+
+    rank = int(os.environ.get("RANK", "0"))
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world_size > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    stream = torch.cuda.Stream()
+    F = args.frames
+    with torch.cuda.stream(stream):
+        eng = slam_b200.Engine(local_rank, stream=stream.cuda_stream)
+        syn = oracle_lib.Synth()
+        world = make_world(syn)
+        poses = make_poses(syn, F + 1)
+        rays = SENSOR["beams"] * SENSOR["azimuth_steps"]
+        d_raw = torch.empty((F + 1) * rays * 3, dtype=torch.float64, device="cuda")
+        off = eng.synth_scans_dev(SENSOR, world, poses, 1000 + 7919 * rank, d_raw.data_ptr())  # input generation
+        n_raw = int(off[-1])
+        pair_src = np.arange(1, F + 1, dtype=np.int32)   # source = current frame (slam_node.cpp:132-138)
+        pair_tgt = np.arange(0, F, dtype=np.int32)       # target = previous frame
+        cfg = eng.icp_config()
+
+        def step_dev():
+            res, sc = eng.register_batch(None, off, pair_src, pair_tgt, voxel=VOXEL, cfg=cfg, want_sc=True,
+                                         device_ptr=d_raw.data_ptr())
+            return res, sc
+
+        gathered = None
+
+        def gather(res):
+            if world_size == 1:
+                return
+            rec = np.array([np.r_[r.transformation.reshape(16), r.final_error, r.num_iterations, r.converged, r.status]
+                            for r in res])
+            t = torch.from_numpy(rec).cuda()
+            out = [torch.empty_like(t) for _ in range(world_size)]
+            dist.all_gather(out, t)  # NCCL: the only exchange of the sharded path
+            return out
+
+        def barrier():
+            if world_size > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        # ---- warm-up
+        for _ in range(max(args.warmup, 3)):
+            res, sc = step_dev()
+            gather(res)
+        # ---- timed: device-resident inputs
+        eng.set_profiling(True)
+        sampler = ClockSampler(local_rank)
+        barrier()
+        sampler.start()
+        l0 = eng.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        stage_acc = {}
+        e0.record(stream)
+        for _ in range(args.steps):
+            res, sc = step_dev()
+            gathered = gather(res)
+            for k, v in eng.stage_ms().items():
+                stage_acc[k] = stage_acc.get(k, 0.0) + v
+        e1.record(stream)
+        barrier()
+        clocks = sampler.stop()
+        launches = eng.launch_count - l0
+        ms = e0.elapsed_time(e1) / args.steps
+        counts = eng.last_counts()
+        eng.set_profiling(False)
+        t_ms = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        if world_size > 1:
+            dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        ms_max = float(t_ms.item())
+        value = world_size * F / (ms_max * 1e-3)
+
+        # ---- e2e: host (pinned) scans through sb_register_batch, H2D + D2H inside the timed region
+        e2e = None
+        if not args.no_e2e:
+            h_raw = torch.empty(n_raw * 3, dtype=torch.float64, pin_memory=True)
+            h_raw.copy_(d_raw[:n_raw * 3])
+            torch.cuda.synchronize()
+            h_np = h_raw.numpy().reshape(-1, 3)
+
+            def step_host():
+                return eng.register_batch(h_np, off, pair_src, pair_tgt, voxel=VOXEL, cfg=cfg, want_sc=True)
+
+            for _ in range(2):
+                r2, s2 = step_host()
+                gather(r2)
+            barrier()
+            t0 = time.perf_counter()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record(stream)
+            for _ in range(args.steps):
+                r2, s2 = step_host()
+                gather(r2)
+            g1.record(stream)
+            barrier()
+            wall = (time.perf_counter() - t0) / args.steps * 1e3
+            ms2 = max(g0.elapsed_time(g1) / args.steps, wall)  # host-side work (staging, result decode) counts
+            t2 = torch.tensor([ms2], device="cuda", dtype=torch.float64)
+            if world_size > 1:
+                dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+            d2h = F * 1184 + (F + 1) * 9600
+            e2e = {"value": world_size * F / (float(t2.item()) * 1e-3), "unit": "pairs/s",
+                   "h2d_bytes_per_step": int(n_raw * 24), "d2h_bytes_per_step": int(d2h),
+                   "ms_per_step": float(t2.item())}
+            assert all(np.array_equal(a.transformation, b.transformation) for a, b in zip(res, r2))
+
+        if rank != 0:
+            if world_size > 1:
+                dist.destroy_process_group()
+            return
+
+        # ---- roofline of the dominant stage (algorithmic bytes: SURVEY.md 8d / DESIGN.md)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+        st = {k: v / args.steps for k, v in stage_acc.items()}
+        N, M, T, Q = counts["raw_rows"], counts["voxel_rows"], counts["target_rows"], counts["nn_queries"]
+        alg = {"voxel": 24 * N + 24 * M, "scan_context": 24 * M + 9600 * (F + 1), "index_build": 52 * T,
+               "normals": 48 * T, "icp_loop": 72 * Q + 224 * F * max(counts["icp_iter_launches"], 1)}
+        kern = {"voxel": "k_sort_scatter/k_sort_hist/k_voxel_* (voxel grid)", "scan_context": "k_sc_compute",
+                "index_build": "k_morton/k_sort_*/k_gather_leaves", "normals": "k_knn<1> (kNN + covariance + Jacobi)",
+                "icp_loop": "k_icp_iter (1-NN + 28 sums) inside the WHILE graph"}
+        dom = max(alg, key=lambda k: st.get(k, 0.0))
+        dom_ms = st[dom]
+        launches_dom = counts["icp_iter_launches"] if dom == "icp_loop" else 1
+        achieved = alg[dom] / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+        roofline = {"bound": "hbm", "kernel": kern[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_step": int(alg[dom]), "launches_per_step": int(launches_dom),
+                    "avg_launch_ms": dom_ms / max(launches_dom, 1),
+                    "stages_ms": st,
+                    "stage_frac_of_peak": {k: (alg[k] / (st[k] * 1e-3) / 1e9 / peak if st.get(k, 0) > 0 else None)
+                                           for k in alg}}
+
+        # ---- cpu_baseline: the oracle, 1 thread (the reference is single-threaded), bounded sample
+        orc = oracle_lib.Oracle()
+        n_probe = 9
+        h = d_raw[:int(off[n_probe]) * 3].cpu().numpy().reshape(-1, 3)
+        scans = [h[int(off[i]):int(off[i + 1])] for i in range(n_probe)]
+        t0 = time.perf_counter()
+        cpu_res = cpu_pair(orc, scans[1], scans[0])
+        t1 = time.perf_counter() - t0
+        n_cpu = int(max(1, min(n_probe - 1, args.cpu_seconds / max(t1, 1e-3))))
+        t0 = time.perf_counter()
+        cpu_out = [cpu_pair(orc, scans[i + 1], scans[i]) for i in range(n_cpu)]
+        cpu_dt = time.perf_counter() - t0
+        # parity spot check on the same pairs
+        max_dt = 0.0
+        for i in range(n_cpu):
+            dT = res[i].transformation @ np.linalg.inv(cpu_out[i]["transformation"])
+            max_dt = max(max_dt, float(np.linalg.norm(dT[:3, 3])))
+        cpu_baseline = {"value": n_cpu / cpu_dt, "unit": "pairs/s", "cores": 1, "kind": "port",
+                        "sample": f"first {n_cpu} pairs of the same sequence, single thread, reference cost model "
+                                  "(NN search twice per iteration); reference binary not buildable (no Eigen)",
+                        "parity_max_translation_diff_m": max_dt}
+
+        iters = np.array([r.num_iterations for r in res])
+        out = {
+            "metric": "ICP scan-pairs/s", "value": value, "unit": "pairs/s", "n_gpus": world_size, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_max, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(F),
+            "ms_per_frame": ms_max / F, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "workload_stats": {"raw_points_per_scan": n_raw / (F + 1), "voxel_points_per_scan": M / (F + 1),
+                               "icp_iterations_mean": float(iters.mean()), "icp_iterations_max": int(iters.max()),
+                               "converged_frac": float(np.mean([r.converged for r in res]))},
+        }
+        print(json.dumps(out))
+        if world_size > 1:
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -96,6 +96,15 @@ const char* sb_last_error(const sb_ctx* ctx);
 int sb_ctx_synchronize(sb_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t sb_ctx_launch_count(const sb_ctx* ctx);
+/* Measurement hooks (not part of the reference API).  With profiling on, sb_register_batch[_dev] brackets its stages
+ * with CUDA events on the context's stream; sb_ctx_stage_ms returns the milliseconds of the last call per stage:
+ * 0 h2d, 1 voxel, 2 scan_context, 3 index_build, 4 normals, 5 icp_loop, 6 d2h (SB_STAGE_COUNT values).
+ * sb_ctx_last_counts: [0] raw rows, [1] rows after the voxel grid, [2] indexed target rows,
+ * [3] sum over pairs of (source rows x nearest-neighbour passes), [4] launches of the ICP iteration kernel. */
+#define SB_STAGE_COUNT 7
+int sb_ctx_set_profiling(sb_ctx* ctx, int enable);
+int sb_ctx_stage_ms(sb_ctx* ctx, double* ms7);
+int sb_ctx_last_counts(sb_ctx* ctx, int64_t* counts5);
 void sb_default_icp_config(sb_icp_config* cfg);
 void sb_default_loop_config(sb_loop_config* cfg);
 

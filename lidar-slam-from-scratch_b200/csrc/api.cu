@@ -1,0 +1,717 @@
+// api.cu — the C ABI of include/slam_b200.h: context management, host<->device staging and the glue that turns
+// each entry point into calls of the device pipelines (voxel.cu, forest.cu, icp.cu, scancontext.cu, loop.cu).
+// There is no CPU implementation of any stage behind these entry points.
+#include <cstdarg>
+#include <algorithm>
+
+#include "common.cuh"
+
+struct sb_index {
+    sb::Ctx* ctx = nullptr;
+    sb::Forest forest;
+};
+
+namespace sb {
+
+int fail(Ctx* ctx, int status, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    return status;
+}
+
+int arena_reset(Ctx* ctx) {
+    Arena& A = ctx->arena;
+    if (!A.overflow.empty()) {
+        cudaStreamSynchronize(ctx->stream);
+        for (void* p : A.overflow) cudaFree(p);
+        A.overflow.clear();
+    }
+    if (A.high > A.cap) {  // regrow the slab to the high-water mark (+25 %)
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(A.base);
+        A.base = nullptr;
+        size_t ncap = A.high + A.high / 4 + (1u << 20);
+        if (cudaMalloc(&A.base, ncap) != cudaSuccess) {
+            cudaGetLastError();
+            A.cap = 0;
+            A.high = 0;
+        } else {
+            A.cap = ncap;
+        }
+    }
+    A.used = 0;
+    A.high = 0;
+    return SB_OK;
+}
+
+int arena_alloc(Ctx* ctx, size_t bytes, void** out) {
+    Arena& A = ctx->arena;
+    size_t sz = (bytes + 255) & ~(size_t)255;
+    if (sz == 0) sz = 256;
+    A.high += sz;
+    if (A.used + sz <= A.cap) {
+        *out = A.base + A.used;
+        A.used += sz;
+        return SB_OK;
+    }
+    void* p = nullptr;
+    SB_CUDA(ctx, cudaMalloc(&p, sz));
+    A.overflow.push_back(p);
+    *out = p;
+    return SB_OK;
+}
+
+void stage_mark(Ctx* ctx, int stage) {
+    if (!ctx->profiling || ctx->n_ev >= 32) return;
+    while (ctx->ev_created <= ctx->n_ev) {
+        if (cudaEventCreate(&ctx->ev[ctx->ev_created]) != cudaSuccess) return;
+        ctx->ev_created++;
+    }
+    cudaEventRecord(ctx->ev[ctx->n_ev], ctx->stream);
+    ctx->ev_stage[ctx->n_ev] = stage;
+    ctx->n_ev++;
+}
+
+int pinned_reserve(Ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->pinned_cap) return SB_OK;
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    ctx->pinned = nullptr;
+    ctx->pinned_cap = 0;
+    size_t cap = bytes + bytes / 2 + 4096;
+    SB_CUDA(ctx, cudaMallocHost(&ctx->pinned, cap));
+    ctx->pinned_cap = cap;
+    return SB_OK;
+}
+
+// RAII entry guard: selects the device and resets the arena
+struct Enter {
+    Ctx* c;
+    explicit Enter(Ctx* ctx) : c(ctx) {
+        cudaSetDevice(c->device);
+        arena_reset(c);
+        c->err.clear();
+        c->n_ev = 0;
+    }
+};
+
+static int upload(Ctx* ctx, const void* h, size_t bytes, void** d) {
+    SB_TRY(arena_alloc(ctx, bytes, d));
+    if (bytes) SB_CUDA(ctx, cudaMemcpyAsync(*d, h, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return SB_OK;
+}
+
+static int download(Ctx* ctx, void* h, const void* d, size_t bytes) {
+    if (bytes) SB_CUDA(ctx, cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return SB_OK;
+}
+
+static std::vector<QueryItem> items_for(i64 nq) {
+    std::vector<QueryItem> items;
+    items.reserve((size_t)((nq + 31) / 32));
+    for (i64 s = 0; s < nq; s += 32) {
+        QueryItem I;
+        I.q_off = s;
+        I.count = (int)(nq - s < 32 ? nq - s : 32);
+        I.tree = 0;
+        items.push_back(I);
+    }
+    return items;
+}
+
+// shared implementation of sb_register_batch / _dev once the clouds are on the device
+static int register_batch_impl(Ctx* ctx, const double* d_xyz, const i64* offsets, int n_clouds, double voxel,
+                               const int32_t* pair_src, const int32_t* pair_tgt, int n_pairs, const sb_icp_config* cfg,
+                               sb_icp_result* results, double* sc_desc) {
+    for (int p = 0; p < n_pairs; ++p)
+        if (pair_src[p] < 0 || pair_src[p] >= n_clouds || pair_tgt[p] < 0 || pair_tgt[p] >= n_clouds)
+            return fail(ctx, SB_ERR_INVALID_ARG, "register_batch: pair %d references a cloud outside [0, %d)", p, n_clouds);
+    if (cfg->normals_k < 1 || cfg->normals_k > SB_MAX_K)
+        return fail(ctx, SB_ERR_INVALID_ARG, "normals_k %d outside [1, %d]", cfg->normals_k, SB_MAX_K);
+    // 1. voxel grid (slam_node.cpp:122)
+    stage_mark(ctx, STAGE_VOXEL);
+    const double* d_pts = d_xyz;
+    std::vector<i64> off(offsets, offsets + n_clouds + 1);
+    if (voxel > 0) {
+        double* d_ds;
+        SB_TRY(arena_get(ctx, (size_t)3 * (offsets[n_clouds] > 0 ? offsets[n_clouds] : 1), &d_ds));
+        SB_TRY(voxel_downsample_dev(ctx, d_xyz, offsets, n_clouds, voxel, d_ds, off.data(), nullptr));
+        d_pts = d_ds;
+    }
+    // 2. Scan Context of every cloud (loop_closure.hpp:53-59)
+    stage_mark(ctx, STAGE_SC);
+    ctx->last_counts[0] = offsets[n_clouds];
+    ctx->last_counts[1] = off[n_clouds];
+    if (sc_desc) {
+        i64* d_off;
+        double* d_desc;
+        SB_TRY(upload(ctx, off.data(), sizeof(i64) * (n_clouds + 1), (void**)&d_off));
+        SB_TRY(arena_get(ctx, (size_t)n_clouds * SB_SC_SIZE, &d_desc));
+        SB_TRY(sc_compute_dev(ctx, d_pts, d_off, n_clouds, d_desc));
+        SB_TRY(download(ctx, sc_desc, d_desc, sizeof(double) * SB_SC_SIZE * n_clouds));
+    }
+    if (n_pairs == 0) {
+        stage_mark(ctx, STAGE_END);
+        SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return SB_OK;
+    }
+    stage_mark(ctx, STAGE_INDEX);
+    // 3. one tree + normals per distinct target cloud (icp.hpp:166-171)
+    std::vector<int> tree_of((size_t)n_clouds, -1), cloud_ids;
+    for (int p = 0; p < n_pairs; ++p) {
+        int t = pair_tgt[p];
+        if (tree_of[t] < 0) {
+            tree_of[t] = (int)cloud_ids.size();
+            cloud_ids.push_back(t);
+        }
+    }
+    Forest F;
+    int s = forest_build(ctx, d_pts, off.data(), cloud_ids.data(), (int)cloud_ids.size(), &F);
+    stage_mark(ctx, STAGE_NORMALS);
+    if (s == SB_OK) s = forest_normals(ctx, &F, cfg->normals_k, nullptr, nullptr);
+    stage_mark(ctx, STAGE_ICP);
+    ctx->last_counts[2] = F.n_points;
+    // 4. the ICP loop for all pairs (icp.hpp:174-255)
+    if (s == SB_OK) {
+        std::vector<PairDesc> pairs((size_t)n_pairs);
+        for (int p = 0; p < n_pairs; ++p) {
+            int c = pair_src[p];
+            pairs[p].src_off = off[c];
+            pairs[p].n_src = (int)(off[c + 1] - off[c]);
+            pairs[p].tree = tree_of[pair_tgt[p]];
+            pairs[p].item_off = 0; pairs[p].n_items = 0; pairs[p].pad = 0;
+        }
+        s = icp_batch(ctx, &F, d_pts, pairs, cfg, results);
+        if (s == SB_OK) {
+            i64 q = 0;
+            for (int p = 0; p < n_pairs; ++p) q += (i64)pairs[p].n_src * results[p].history_len;
+            ctx->last_counts[3] = q;
+        }
+    }
+    stage_mark(ctx, STAGE_END);
+    cudaStreamSynchronize(ctx->stream);
+    forest_free(&F);
+    return s;
+}
+
+}  // namespace sb
+
+using namespace sb;
+
+extern "C" {
+
+const char* sb_version(void) { return "slam_b200 0.1 (sm_100a)"; }
+
+int sb_ctx_create(int device, void* stream, sb_ctx** out) {
+    if (!out) return SB_ERR_INVALID_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) {
+        cudaGetLastError();
+        return SB_ERR_NO_DEVICE;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return SB_ERR_NO_DEVICE;
+    if (prop.major < 10) return SB_ERR_NO_DEVICE;  // kernels are built for sm_100a only
+    if (cudaSetDevice(device) != cudaSuccess) return SB_ERR_NO_DEVICE;
+    sb_ctx* c = new sb_ctx();
+    c->c.device = device;
+    c->c.sm_count = prop.multiProcessorCount;
+    if (stream) {
+        c->c.stream = static_cast<cudaStream_t>(stream);
+    } else {
+        if (cudaStreamCreateWithFlags(&c->c.stream, cudaStreamNonBlocking) != cudaSuccess) {
+            delete c;
+            return SB_ERR_CUDA;
+        }
+        c->c.own_stream = true;
+    }
+    if (cudaMalloc(&c->c.d_flags, sizeof(int)) != cudaSuccess) {
+        delete c;
+        return SB_ERR_CUDA;
+    }
+    *out = c;
+    return SB_OK;
+}
+
+void sb_ctx_destroy(sb_ctx* ctx) {
+    if (!ctx) return;
+    Ctx* c = &ctx->c;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    icp_graph_free(c);
+    for (void* p : c->arena.overflow) cudaFree(p);
+    cudaFree(c->arena.base);
+    cudaFree(c->d_flags);
+    for (int i = 0; i < c->ev_created; ++i) cudaEventDestroy(c->ev[i]);
+    if (c->pinned) cudaFreeHost(c->pinned);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete ctx;
+}
+
+const char* sb_last_error(const sb_ctx* ctx) { return ctx ? ctx->c.err.c_str() : "null context"; }
+
+int sb_ctx_synchronize(sb_ctx* ctx) {
+    if (!ctx) return SB_ERR_INVALID_ARG;
+    SB_CUDA(&ctx->c, cudaStreamSynchronize(ctx->c.stream));
+    return SB_OK;
+}
+
+int64_t sb_ctx_launch_count(const sb_ctx* ctx) { return ctx ? ctx->c.launches : 0; }
+
+int sb_ctx_set_profiling(sb_ctx* ctx, int enable) {
+    if (!ctx) return SB_ERR_INVALID_ARG;
+    ctx->c.profiling = enable != 0;
+    ctx->c.n_ev = 0;
+    return SB_OK;
+}
+
+int sb_ctx_stage_ms(sb_ctx* ctx, double* ms7) {
+    if (!ctx || !ms7) return SB_ERR_INVALID_ARG;
+    Ctx* c = &ctx->c;
+    for (int i = 0; i < STAGE_COUNT; ++i) ms7[i] = 0.0;
+    SB_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (int i = 0; i + 1 < c->n_ev; ++i) {
+        int st = c->ev_stage[i];
+        if (st < 0 || st >= STAGE_COUNT) continue;
+        float ms = 0.f;
+        SB_CUDA(c, cudaEventElapsedTime(&ms, c->ev[i], c->ev[i + 1]));
+        ms7[st] += (double)ms;
+    }
+    return SB_OK;
+}
+
+int sb_ctx_last_counts(sb_ctx* ctx, int64_t* counts5) {
+    if (!ctx || !counts5) return SB_ERR_INVALID_ARG;
+    for (int i = 0; i < 4; ++i) counts5[i] = ctx->c.last_counts[i];
+    counts5[4] = ctx->c.last_icp_iterations;
+    return SB_OK;
+}
+
+void sb_default_icp_config(sb_icp_config* cfg) {  // types.hpp:143-148, icp.hpp:170
+    cfg->max_iterations = 50;
+    cfg->normals_k = 20;
+    cfg->tolerance = 1e-6;
+    cfg->min_error = 1e-9;
+    for (int i = 0; i < 16; ++i) cfg->initial_transform[i] = (i % 5 == 0) ? 1.0 : 0.0;
+}
+
+void sb_default_loop_config(sb_loop_config* cfg) {  // loop_closure.hpp:14-19, 105-107
+    cfg->frame_gap = 50;
+    cfg->max_candidates = 3;
+    cfg->sc_distance_threshold = 0.25;
+    cfg->icp_fitness_threshold = 0.3;
+    cfg->icp_max_iterations = 30;
+    cfg->normals_k = 20;
+    cfg->icp_tolerance = 1e-6;
+    cfg->verify_chunk = 0;
+    cfg->reserved = 0;
+}
+
+// ---------------------------------------------------------------- voxel grid
+int sb_voxel_downsample_batch_dev(sb_ctx* ctx, const double* d_xyz, const int64_t* offsets, int32_t n_clouds,
+                                  double voxel, double* d_out_xyz, int64_t* out_offsets, int64_t* d_out_keys) {
+    if (!ctx || !offsets || !out_offsets || n_clouds < 0) return SB_ERR_INVALID_ARG;
+    Ctx* c = &ctx->c;
+    Enter g(c);
+    for (int i = 0; i < n_clouds; ++i)
+        if (offsets[i + 1] < offsets[i]) return fail(c, SB_ERR_INVALID_ARG, "offsets must be non-decreasing");
+    if (offsets[n_clouds] > 0 && (!d_xyz || !d_out_xyz)) return fail(c, SB_ERR_INVALID_ARG, "null point buffer");
+    return voxel_downsample_dev(c, d_xyz, (const i64*)offsets, n_clouds, voxel, d_out_xyz, (i64*)out_offsets,
+                                (i64*)d_out_keys);
+}
+
+int sb_voxel_downsample_batch(sb_ctx* ctx, const double* xyz, const int64_t* offsets, int32_t n_clouds, double voxel,
+                              double* out_xyz, int64_t* out_offsets, int64_t* out_keys) {
+    if (!ctx || !offsets || !out_offsets || n_clouds < 0) return SB_ERR_INVALID_ARG;
+    Ctx* c = &ctx->c;
+    Enter g(c);
+    for (int i = 0; i < n_clouds; ++i)
+        if (offsets[i + 1] < offsets[i]) return fail(c, SB_ERR_INVALID_ARG, "offsets must be non-decreasing");
+    i64 n = offsets[n_clouds];
+    if (n > 0 && (!xyz || !out_xyz)) return fail(c, SB_ERR_INVALID_ARG, "null point buffer");
+    double *d_in, *d_out;
+    i64* d_keys = nullptr;
+    SB_TRY(upload(c, xyz, sizeof(double) * 3 * n, (void**)&d_in));
+    SB_TRY(arena_get(c, (size_t)3 * (n > 0 ? n : 1), &d_out));
+    if (out_keys) SB_TRY(arena_get(c, (size_t)3 * (n > 0 ? n : 1), &d_keys));
+    SB_TRY(voxel_downsample_dev(c, d_in, (const i64*)offsets, n_clouds, voxel, d_out, (i64*)out_offsets, d_keys));
+    i64 m = out_offsets[n_clouds];
+    SB_TRY(download(c, out_xyz, d_out, sizeof(double) * 3 * m));
+    if (out_keys) SB_TRY(download(c, out_keys, d_keys, sizeof(i64) * 3 * m));
+    SB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return SB_OK;
+}
+
+int sb_voxel_downsample(sb_ctx* ctx, const double* xyz, int64_t n, double voxel, double* out_xyz, int64_t* out_m,
+                        int64_t* out_keys) {
+    if (!ctx || !out_m || n < 0) return SB_ERR_INVALID_ARG;
+    int64_t off[2] = {0, n}, out_off[2] = {0, 0};
+    int s = sb_voxel_downsample_batch(ctx, xyz, off, 1, voxel, out_xyz, out_off, out_keys);
+    *out_m = out_off[1];
+    return s;
+}
+
+// ---------------------------------------------------------------- spatial index
+int sb_index_build(sb_ctx* ctx, const double* xyz, int64_t n, sb_index** out) {
+    if (!ctx || !out || n < 0 || (n > 0 && !xyz)) return SB_ERR_INVALID_ARG;
+    Ctx* c = &ctx->c;
+    Enter g(c);
+    *out = nullptr;
+    if (n > 0x7fffffffLL) return fail(c, SB_ERR_RANGE, "index: more than 2^31-1 points");
+    double* d_xyz;
+    SB_TRY(upload(c, xyz, sizeof(double) * 3 * n, (void**)&d_xyz));
+    sb_index* ix = new sb_index();
+    ix->ctx = c;
+    i64 off[2] = {0, n};
+    int s = forest_build(c, d_xyz, off, nullptr, 1, &ix->forest);
+    if (s == SB_OK && cudaStreamSynchronize(c->stream) != cudaSuccess)
+        s = fail(c, SB_ERR_CUDA, "index build: %s", cudaGetErrorString(cudaGetLastError()));
+    if (s != SB_OK) {
+        forest_free(&ix->forest);
+        delete ix;
+        return s;
+    }
+    *out = ix;
+    return SB_OK;
+}
+
+void sb_index_free(sb_index* index) {
+    if (!index) return;
+    cudaSetDevice(index->ctx->device);
+    cudaStreamSynchronize(index->ctx->stream);
+    forest_free(&index->forest);
+    delete index;
+}
+
+int64_t sb_index_size(const sb_index* index) { return index ? index->forest.n_points : 0; }
+
+int sb_index_nearest_batch(sb_index* index, const double* queries, int64_t nq, int32_t* out_idx, double* out_d2) {
+    if (!index || nq < 0 || (nq > 0 && (!queries || !out_idx))) return SB_ERR_INVALID_ARG;
+    Ctx* c = index->ctx;
+    Enter g(c);
+    if (nq == 0) return SB_OK;
+    double* d_q;
+    int* d_idx;
+    double* d_d2 = nullptr;
+    QueryItem* d_items;
+    SB_TRY(upload(c, queries, sizeof(double) * 3 * nq, (void**)&d_q));
+    SB_TRY(arena_get(c, (size_t)nq, &d_idx));
+    if (out_d2) SB_TRY(arena_get(c, (size_t)nq, &d_d2));
+    std::vector<QueryItem> items = items_for(nq);
+    SB_TRY(make_items_dev(c, items, &d_items));
+    SB_TRY(forest_nearest(c, &index->forest, d_q, d_items, (i64)items.size(), d_idx, d_d2, nullptr));
+    SB_TRY(download(c, out_idx, d_idx, sizeof(int) * nq));
+    if (out_d2) SB_TRY(download(c, out_d2, d_d2, sizeof(double) * nq));
+    SB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return SB_OK;
+}
+
+int sb_index_knn(sb_index* index, const double* queries, int64_t nq, int32_t k, int32_t* out_idx, double* out_d2) {
+    if (!index || nq < 0 || (nq > 0 && (!queries || !out_idx))) return SB_ERR_INVALID_ARG;
+    Ctx* c = index->ctx;
+    Enter g(c);
+    if (k < 1 || k > SB_MAX_K) return fail(c, SB_ERR_INVALID_ARG, "k %d outside [1, %d]", k, SB_MAX_K);
+    if (nq == 0) return SB_OK;
+    double* d_q;
+    int* d_idx;
+    double* d_d2 = nullptr;
+    QueryItem* d_items;
+    SB_TRY(upload(c, queries, sizeof(double) * 3 * nq, (void**)&d_q));
+    SB_TRY(arena_get(c, (size_t)nq * k, &d_idx));
+    if (out_d2) SB_TRY(arena_get(c, (size_t)nq * k, &d_d2));
+    std::vector<QueryItem> items = items_for(nq);
+    SB_TRY(make_items_dev(c, items, &d_items));
+    if (index->forest.n_points == 0) {  // empty tree: every slot is padding
+        SB_CUDA(c, cudaMemsetAsync(d_idx, 0xff, sizeof(int) * nq * k, c->stream));
+        SB_TRY(download(c, out_idx, d_idx, sizeof(int) * nq * k));
+        SB_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (out_d2) for (i64 i = 0; i < nq * k; ++i) out_d2[i] = 1.7976931348623157e308;
+        return SB_OK;
+    }
+    SB_TRY(forest_knn(c, &index->forest, d_q, d_items, (i64)items.size(), k, d_idx, d_d2));
+    SB_TRY(download(c, out_idx, d_idx, sizeof(int) * nq * k));
+    if (out_d2) SB_TRY(download(c, out_d2, d_d2, sizeof(double) * nq * k));
+    SB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return SB_OK;
+}
+
+int sb_index_find_correspondences(sb_index* index, const double* source, int64_t ns, double* matched_xyz,
+                                  double* distances) {
+    if (!index || ns < 0 || (ns > 0 && (!source || !matched_xyz))) return SB_ERR_INVALID_ARG;
+    Ctx* c = index->ctx;
+    if (ns > 0 && index->forest.n_points == 0) {
+        Enter g(c);
+        return fail(c, SB_ERR_EMPTY, "find_correspondences on an empty index (kdtree.hpp:211 is undefined there)");
+    }
+    std::vector<int32_t> idx((size_t)ns);
+    std::vector<double> d2((size_t)ns);
+    SB_TRY(sb_index_nearest_batch(index, source, ns, idx.data(), d2.data()));
+    // matched rows: gather from the device copy of the target (sorted SoA + original index)
+    Enter g(c);
+    const Forest& F = index->forest;
+    i64 n = F.n_points;
+    std::vector<double> sx((size_t)n), sy((size_t)n), sz((size_t)n);
+    std::vector<int> sidx((size_t)n);
+    SB_TRY(download(c, sx.data(), F.sx, sizeof(double) * n));
+    SB_TRY(download(c, sy.data(), F.sy, sizeof(double) * n));
+    SB_TRY(download(c, sz.data(), F.sz, sizeof(double) * n));
+    SB_TRY(download(c, sidx.data(), F.sidx, sizeof(int) * n));
+    SB_CUDA(c, cudaStreamSynchronize(c->stream));
+    std::vector<int> pos_of((size_t)n);
+    for (i64 p = 0; p < n; ++p) pos_of[sidx[p]] = (int)p;
+    for (i64 i = 0; i < ns; ++i) {  // kdtree.hpp:208-212
+        int p = pos_of[idx[i]];
+        matched_xyz[3 * i] = sx[p]; matched_xyz[3 * i + 1] = sy[p]; matched_xyz[3 * i + 2] = sz[p];
+        if (distances) distances[i] = sqrt(d2[i]);
+    }
+    return SB_OK;
+}
+
+int sb_estimate_normals(sb_index* index, int32_t k, double* out_normals, double* out_evals) {
+    if (!index || !out_normals) return SB_ERR_INVALID_ARG;
+    Ctx* c = index->ctx;
+    Enter g(c);
+    if (k < 1 || k > SB_MAX_K) return fail(c, SB_ERR_INVALID_ARG, "k %d outside [1, %d]", k, SB_MAX_K);
+    i64 n = index->forest.n_points;
+    if (n == 0) return SB_OK;
+    double *d_n, *d_e = nullptr;
+    SB_TRY(arena_get(c, (size_t)3 * n, &d_n));
+    if (out_evals) SB_TRY(arena_get(c, (size_t)3 * n, &d_e));
+    SB_TRY(forest_normals(c, &index->forest, k, d_n, d_e));
+    SB_TRY(download(c, out_normals, d_n, sizeof(double) * 3 * n));
+    if (out_evals) SB_TRY(download(c, out_evals, d_e, sizeof(double) * 3 * n));
+    SB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return SB_OK;
+}
+
+// ---------------------------------------------------------------- ICP
+int sb_solve_point_to_plane(sb_ctx* ctx, const double* source, const double* target, const double* normals, int64_t n,
+                            double* out_T16) {
+    if (!ctx || !out_T16 || n < 0 || (n > 0 && (!source || !target || !normals))) return SB_ERR_INVALID_ARG;
+    Ctx* c = &ctx->c;
+    Enter g(c);
+    double *d_s, *d_t, *d_n, *d_T;
+    SB_TRY(upload(c, source, sizeof(double) * 3 * n, (void**)&d_s));
+    SB_TRY(upload(c, target, sizeof(double) * 3 * n, (void**)&d_t));
+    SB_TRY(upload(c, normals, sizeof(double) * 3 * n, (void**)&d_n));
+    SB_TRY(arena_get(c, 16, &d_T));
+    SB_TRY(solve_point_to_plane_dev(c, d_s, d_t, d_n, n, d_T));
+    SB_TRY(download(c, out_T16, d_T, sizeof(double) * 16));
+    SB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return SB_OK;
+}
+
+int sb_register_batch_dev(sb_ctx* ctx, const double* d_xyz, const int64_t* offsets, int32_t n_clouds, double voxel,
+                          const int32_t* pair_src, const int32_t* pair_tgt, int32_t n_pairs, const sb_icp_config* cfg,
+                          sb_icp_result* results, double* sc_desc) {
+    if (!ctx || !offsets || n_clouds < 0 || n_pairs < 0 || !cfg) return SB_ERR_INVALID_ARG;
+    if (n_pairs > 0 && (!pair_src || !pair_tgt || !results)) return SB_ERR_INVALID_ARG;
+    Ctx* c = &ctx->c;
+    Enter g(c);
+    for (int i = 0; i < n_clouds; ++i)
+        if (offsets[i + 1] < offsets[i]) return fail(c, SB_ERR_INVALID_ARG, "offsets must be non-decreasing");
+    return register_batch_impl(c, d_xyz, (const i64*)offsets, n_clouds, voxel, pair_src, pair_tgt, n_pairs, cfg, results,
+                               sc_desc);
+}
+
+int sb_register_batch(sb_ctx* ctx, const double* xyz, const int64_t* offsets, int32_t n_clouds, double voxel,
+                      const int32_t* pair_src, const int32_t* pair_tgt, int32_t n_pairs, const sb_icp_config* cfg,
+                      sb_icp_result* results, double* sc_desc) {
+    if (!ctx || !offsets || n_clouds < 0 || n_pairs < 0 || !cfg) return SB_ERR_INVALID_ARG;
+    if (n_pairs > 0 && (!pair_src || !pair_tgt || !results)) return SB_ERR_INVALID_ARG;
+    Ctx* c = &ctx->c;
+    Enter g(c);
+    for (int i = 0; i < n_clouds; ++i)
+        if (offsets[i + 1] < offsets[i]) return fail(c, SB_ERR_INVALID_ARG, "offsets must be non-decreasing");
+    i64 n = offsets[n_clouds];
+    if (n > 0 && !xyz) return fail(c, SB_ERR_INVALID_ARG, "null point buffer");
+    double* d_xyz;
+    stage_mark(c, STAGE_H2D);
+    SB_TRY(upload(c, xyz, sizeof(double) * 3 * n, (void**)&d_xyz));
+    return register_batch_impl(c, d_xyz, (const i64*)offsets, n_clouds, voxel, pair_src, pair_tgt, n_pairs, cfg, results,
+                               sc_desc);
+}
+
+int sb_icp_point_to_plane(sb_ctx* ctx, const double* source, int64_t ns, const double* target, int64_t nt,
+                          const sb_icp_config* cfg, sb_icp_result* out) {
+    if (!ctx || !cfg || !out || ns < 0 || nt < 0) return SB_ERR_INVALID_ARG;
+    if (ns == 0 || nt == 0) {
+        Enter g(&ctx->c);
+        return fail(&ctx->c, SB_ERR_EMPTY, "icp: empty %s cloud (undefined behaviour in the reference, kdtree.hpp:25,119)",
+                    ns == 0 ? "source" : "target");
+    }
+    std::vector<double> both((size_t)3 * (ns + nt));
+    memcpy(both.data(), source, sizeof(double) * 3 * ns);
+    memcpy(both.data() + 3 * ns, target, sizeof(double) * 3 * nt);
+    int64_t off[3] = {0, ns, ns + nt};
+    int32_t ps = 0, pt = 1;
+    int s = sb_register_batch(ctx, both.data(), off, 2, 0.0, &ps, &pt, 1, cfg, out, nullptr);
+    if (s == SB_OK && out->status != SB_OK) s = out->status;
+    return s;
+}
+
+// ---------------------------------------------------------------- Scan Context
+int sb_sc_compute(sb_ctx* ctx, const double* xyz, int64_t n, double* desc) {
+    if (!ctx || !desc || n < 0 || (n > 0 && !xyz)) return SB_ERR_INVALID_ARG;
+    Ctx* c = &ctx->c;
+    Enter g(c);
+    double *d_xyz, *d_desc;
+    i64* d_off;
+    i64 off[2] = {0, n};
+    SB_TRY(upload(c, xyz, sizeof(double) * 3 * n, (void**)&d_xyz));
+    SB_TRY(upload(c, off, sizeof(off), (void**)&d_off));
+    SB_TRY(arena_get(c, SB_SC_SIZE, &d_desc));
+    SB_TRY(sc_compute_dev(c, d_xyz, d_off, 1, d_desc));
+    SB_TRY(download(c, desc, d_desc, sizeof(double) * SB_SC_SIZE));
+    SB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return SB_OK;
+}
+
+int sb_sc_distance_batch(sb_ctx* ctx, const double* query, const double* db, int32_t n_db, double* out_dist) {
+    if (!ctx || !query || n_db < 0 || (n_db > 0 && (!db || !out_dist))) return SB_ERR_INVALID_ARG;
+    Ctx* c = &ctx->c;
+    Enter g(c);
+    if (n_db == 0) return SB_OK;
+    double *d_q, *d_db, *d_out;
+    SB_TRY(upload(c, query, sizeof(double) * SB_SC_SIZE, (void**)&d_q));
+    SB_TRY(upload(c, db, sizeof(double) * SB_SC_SIZE * n_db, (void**)&d_db));
+    SB_TRY(arena_get(c, (size_t)n_db, &d_out));
+    SB_TRY(sc_distance_dev(c, d_q, d_db, n_db, d_out));
+    SB_TRY(download(c, out_dist, d_out, sizeof(double) * n_db));
+    SB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return SB_OK;
+}
+
+int sb_sc_distance(sb_ctx* ctx, const double* desc_a, const double* desc_b, double* out) {
+    return sb_sc_distance_batch(ctx, desc_a, desc_b, 1, out);
+}
+
+int sb_sc_keys(sb_ctx* ctx, const double* desc, double* ring_key20, double* sector_key60) {
+    if (!ctx || !desc || !ring_key20 || !sector_key60) return SB_ERR_INVALID_ARG;
+    Ctx* c = &ctx->c;
+    Enter g(c);
+    double *d_desc, *d_r, *d_s;
+    SB_TRY(upload(c, desc, sizeof(double) * SB_SC_SIZE, (void**)&d_desc));
+    SB_TRY(arena_get(c, SB_SC_RINGS, &d_r));
+    SB_TRY(arena_get(c, SB_SC_SECTORS, &d_s));
+    SB_TRY(sc_keys_dev(c, d_desc, d_r, d_s));
+    SB_TRY(download(c, ring_key20, d_r, sizeof(double) * SB_SC_RINGS));
+    SB_TRY(download(c, sector_key60, d_s, sizeof(double) * SB_SC_SECTORS));
+    SB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return SB_OK;
+}
+
+// ---------------------------------------------------------------- loop closure
+int sb_loop_create(sb_ctx* ctx, const sb_loop_config* cfg, int32_t rank, int32_t world, sb_loop** out) {
+    if (!ctx || !cfg || !out || world < 1 || rank < 0 || rank >= world) return SB_ERR_INVALID_ARG;
+    if (cfg->normals_k < 1 || cfg->normals_k > SB_MAX_K || cfg->icp_max_iterations < 0 ||
+        cfg->icp_max_iterations > SB_MAX_ICP_ITERATIONS)
+        return fail(&ctx->c, SB_ERR_INVALID_ARG, "loop config out of range");
+    sb_loop* L = new sb_loop();
+    L->ctx = &ctx->c;
+    L->cfg = *cfg;
+    L->rank = rank;
+    L->world = world;
+    *out = L;
+    return SB_OK;
+}
+
+void sb_loop_free(sb_loop* loop) {
+    if (!loop) return;
+    cudaSetDevice(loop->ctx->device);
+    cudaStreamSynchronize(loop->ctx->stream);
+    cudaFree(loop->d_desc);
+    cudaFree(loop->d_clouds);
+    delete loop;
+}
+
+int sb_loop_add_frame_desc(sb_loop* loop, const double* xyz, int64_t n, int32_t frame_idx, const double* desc) {
+    if (!loop || n < 0 || (n > 0 && !xyz)) return SB_ERR_INVALID_ARG;
+    Enter g(loop->ctx);
+    return loop_add(loop, xyz, n, frame_idx, desc);
+}
+
+int sb_loop_add_frame(sb_loop* loop, const double* xyz, int64_t n, int32_t frame_idx) {
+    return sb_loop_add_frame_desc(loop, xyz, n, frame_idx, nullptr);
+}
+
+int64_t sb_loop_size(const sb_loop* loop) { return loop ? loop->n_global : 0; }
+
+int sb_loop_clear(sb_loop* loop) {  // loop_closure.hpp:136-141
+    if (!loop) return SB_ERR_INVALID_ARG;
+    loop->entry_id.clear();
+    loop->frame_idx.clear();
+    loop->cloud_off.clear();
+    loop->n_global = 0;
+    loop->last_is_guest = false;
+    return SB_OK;
+}
+
+int sb_loop_candidates_local(sb_loop* loop, double* dist, int32_t* entry, int32_t capacity, int32_t* count) {
+    if (!loop || !count || capacity < 0 || (capacity > 0 && (!dist || !entry))) return SB_ERR_INVALID_ARG;
+    Enter g(loop->ctx);
+    std::vector<std::pair<double, int>> cand;
+    SB_TRY(loop_candidates(loop, cand));
+    *count = (int32_t)cand.size();
+    for (int i = 0; i < capacity && i < (int)cand.size(); ++i) {
+        dist[i] = cand[i].first;
+        entry[i] = cand[i].second;
+    }
+    return SB_OK;
+}
+
+int sb_loop_verify_entries(sb_loop* loop, const int32_t* entry, const double* dist, int32_t n, sb_loop_result* results,
+                           int32_t* converged) {
+    if (!loop || n < 0 || (n > 0 && (!entry || !results || !converged))) return SB_ERR_INVALID_ARG;
+    Enter g(loop->ctx);
+    return loop_verify(loop, entry, dist, n, results, converged);
+}
+
+int sb_loop_detect(sb_loop* loop, sb_loop_result* results, int32_t capacity, int32_t* count) {
+    if (!loop || !count || capacity < 0 || (capacity > 0 && !results)) return SB_ERR_INVALID_ARG;
+    Ctx* c = loop->ctx;
+    Enter g(c);
+    *count = 0;
+    if (loop->world != 1) return fail(c, SB_ERR_INVALID_ARG, "sb_loop_detect needs world == 1; use candidates_local + verify_entries");
+    std::vector<std::pair<double, int>> cand;
+    SB_TRY(loop_candidates(loop, cand));
+    if (cand.empty()) return SB_OK;  // loop_closure.hpp:91
+    int chunk = loop->cfg.verify_chunk > 0 ? loop->cfg.verify_chunk : loop->cfg.max_candidates;
+    if (chunk < 1) chunk = 1;
+    int verified = 0;  // counts acceptances only (loop_closure.hpp:95-97, 121)
+    for (size_t b = 0; b < cand.size() && verified < loop->cfg.max_candidates; b += (size_t)chunk) {
+        int m = (int)std::min(cand.size() - b, (size_t)chunk);
+        std::vector<int> ent((size_t)m), conv((size_t)m);
+        std::vector<double> dist((size_t)m);
+        std::vector<sb_loop_result> res((size_t)m);
+        for (int i = 0; i < m; ++i) { ent[i] = cand[b + i].second; dist[i] = cand[b + i].first; }
+        arena_reset(c);
+        SB_TRY(loop_verify(loop, ent.data(), dist.data(), m, res.data(), conv.data()));
+        for (int i = 0; i < m && verified < loop->cfg.max_candidates; ++i) {
+            if (conv[i] && res[i].icp_fitness < loop->cfg.icp_fitness_threshold) {  // loop_closure.hpp:112
+                if (*count < capacity) results[*count] = res[i];
+                ++*count;
+                ++verified;
+            }
+        }
+    }
+    return SB_OK;
+}
+
+// ---------------------------------------------------------------- synthetic input generator
+int sb_synth_scans_dev(sb_ctx* ctx, int32_t beams, int32_t azimuth_steps, float elev_top_deg, float elev_bot_deg,
+                       float max_range, float noise_sigma, float sensor_height, const float* boxes, int32_t n_boxes,
+                       const double* poses, int32_t n_scans, uint64_t noise_seed, double* d_xyz, int64_t* out_offsets) {
+    if (!ctx || !poses || !out_offsets || n_scans < 0 || n_boxes < 0 || (n_boxes > 0 && !boxes)) return SB_ERR_INVALID_ARG;
+    Ctx* c = &ctx->c;
+    Enter g(c);
+    return synth_scans_dev(c, beams, azimuth_steps, elev_top_deg, elev_bot_deg, max_range, noise_sigma, sensor_height,
+                           boxes, n_boxes, poses, n_scans, noise_seed, d_xyz, (i64*)out_offsets);
+}
+
+}  // extern "C"

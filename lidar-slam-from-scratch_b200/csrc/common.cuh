@@ -1,0 +1,270 @@
+// common.cuh — shared host/device plumbing of libslam_b200.so (sm_100a only).
+//
+// One sb_ctx per (host thread, device): it owns the stream, a grow-only device workspace arena that is reset at
+// the start of every C-ABI call, a pinned host staging buffer, the launch counter reported to bench.py and the
+// cached ICP while-graph.  Nothing here falls back to the CPU: every failure becomes an sb_status.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/slam_b200.h"
+
+namespace sb {
+
+typedef long long i64;
+typedef unsigned long long u64;
+
+struct Ctx;
+
+// ---------------------------------------------------------------------------------------------------------------
+// error handling: SB_CUDA(ctx, call) records the message and makes the enclosing function return SB_ERR_CUDA
+// ---------------------------------------------------------------------------------------------------------------
+int fail(Ctx* ctx, int status, const char* fmt, ...);
+
+#define SB_CUDA(ctx, call)                                                                                    \
+    do {                                                                                                      \
+        cudaError_t e__ = (call);                                                                             \
+        if (e__ != cudaSuccess)                                                                               \
+            return sb::fail((ctx), SB_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call,                  \
+                            cudaGetErrorString(e__));                                                         \
+    } while (0)
+
+#define SB_TRY(expr)                  \
+    do {                              \
+        int s__ = (expr);             \
+        if (s__ != SB_OK) return s__; \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------------------------
+// Workspace arena: bump allocator over one cudaMalloc'd slab.  If a call needs more than the slab holds the
+// overflow goes to individually cudaMalloc'd blocks that are freed at the next reset, and the slab is regrown to
+// the high-water mark so that steady-state calls allocate nothing.
+// ---------------------------------------------------------------------------------------------------------------
+struct Arena {
+    char* base = nullptr;
+    size_t cap = 0, used = 0, high = 0;
+    std::vector<void*> overflow;
+};
+
+struct Ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    Arena arena;
+    char* pinned = nullptr;  // pinned host staging
+    size_t pinned_cap = 0;
+    i64 launches = 0;
+    std::string err;
+    // device flag word set by kernels on bad input (non-finite coordinates, voxel key overflow)
+    int* d_flags = nullptr;
+    // cached ICP loop graph (icp.cu)
+    void* icp_graph = nullptr;
+    // optional per-stage CUDA-event timing of the last pipeline call (bench.py's roofline figures)
+    bool profiling = false;
+    cudaEvent_t ev[32];
+    int ev_stage[32];
+    int n_ev = 0, ev_created = 0;
+    i64 last_icp_iterations = 0;   // max history length of the last icp_batch (launches of k_icp_iter)
+    i64 last_counts[4] = {0, 0, 0, 0};  // raw rows, downsampled rows, target rows, sum over pairs of n_src * passes
+};
+
+// stage ids for stage_mark / sb_ctx_stage_ms
+enum { STAGE_H2D = 0, STAGE_VOXEL = 1, STAGE_SC = 2, STAGE_INDEX = 3, STAGE_NORMALS = 4, STAGE_ICP = 5, STAGE_D2H = 6,
+       STAGE_COUNT = 7, STAGE_END = -1 };
+void stage_mark(Ctx* ctx, int stage);
+
+int arena_reset(Ctx* ctx);
+int arena_alloc(Ctx* ctx, size_t bytes, void** out);
+int pinned_reserve(Ctx* ctx, size_t bytes);
+
+template <typename T>
+inline int arena_get(Ctx* ctx, size_t count, T** out) {
+    void* p = nullptr;
+    int s = arena_alloc(ctx, count * sizeof(T), &p);
+    *out = static_cast<T*>(p);
+    return s;
+}
+
+inline int ceil_div(i64 a, i64 b) { return (int)((a + b - 1) / b); }
+
+#define SB_LAUNCH(ctx, kernel, grid, block, smem, ...)                            \
+    do {                                                                          \
+        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);          \
+        (ctx)->launches++;                                                        \
+        SB_CUDA((ctx), cudaGetLastError());                                       \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+// d^2 exactly as the oracle defines it: (dx*dx + dy*dy) + dz*dz, round-to-nearest, never contracted to FMA
+// (kdtree.hpp:124 squaredNorm).
+__device__ __forceinline__ double dist2_rn(double px, double py, double pz, double qx, double qy, double qz) {
+    double dx = __dsub_rn(px, qx), dy = __dsub_rn(py, qy), dz = __dsub_rn(pz, qz);
+    return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+}
+
+// order-preserving map double <-> signed 64-bit so that atomicMin/atomicMax work on doubles exactly
+__device__ __forceinline__ long long ordered_from_double(double d) {
+    long long b = __double_as_longlong(d);
+    return b >= 0 ? b : (b ^ 0x7fffffffffffffffLL);
+}
+__device__ __forceinline__ double double_from_ordered(long long b) {
+    return __longlong_as_double(b >= 0 ? b : (b ^ 0x7fffffffffffffffLL));
+}
+
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+__device__ __forceinline__ double shfl_d_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+
+__device__ __forceinline__ unsigned lanemask_lt() {
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+#endif
+
+// error flag bits written to Ctx::d_flags
+enum { FLAG_NONFINITE = 1, FLAG_KEY_RANGE = 2 };
+
+// ---------------------------------------------------------------------------------------------------------------
+// scan_sort.cu
+// ---------------------------------------------------------------------------------------------------------------
+// exclusive prefix sum of n uint32 values (in may equal out); total (optional device pointer) receives the sum
+int exclusive_scan_u32(Ctx* ctx, const uint32_t* d_in, uint32_t* d_out, i64 n, uint32_t* d_total);
+
+// Stable LSD radix sort of (key64, val32) pairs, independently inside each segment [seg_off[s], seg_off[s+1]).
+// h_seg_off: host offsets (n_seg + 1).  Sorts on key bits [0, key_bits).  On return *out_keys / *out_vals point to
+// whichever of the (a, b) buffers holds the sorted result.
+int segmented_sort_pairs(Ctx* ctx, u64* keys_a, u64* keys_b, uint32_t* vals_a, uint32_t* vals_b,
+                         const i64* h_seg_off, int n_seg, int key_bits, u64** out_keys, uint32_t** out_vals);
+
+// ---------------------------------------------------------------------------------------------------------------
+// voxel.cu
+// ---------------------------------------------------------------------------------------------------------------
+// Device-to-device batched voxel grid.  d_out_xyz / d_out_keys (optional) sized for the input row count;
+// h_out_off (host, n_clouds + 1) receives the CSR offsets of the output.  Synchronises the stream.
+int voxel_downsample_dev(Ctx* ctx, const double* d_xyz, const i64* h_off, int n_clouds, double voxel,
+                         double* d_out_xyz, i64* h_out_off, i64* d_out_keys);
+
+// ---------------------------------------------------------------------------------------------------------------
+// forest.cu — the spatial index: one implicit 32-ary bounding-box tree per cloud over Morton-sorted points
+// ---------------------------------------------------------------------------------------------------------------
+#define SB_MAX_LEVELS 7
+
+struct TreeDesc {      // device-resident, one per indexed cloud
+    i64 pt_off;        // first sorted point of this cloud in the forest's SoA arrays
+    int n;             // points
+    int top;           // top level (boxes at that level <= 32)
+    i64 box_off[SB_MAX_LEVELS];  // first box of level l in the forest's box array
+    int box_cnt[SB_MAX_LEVELS];  // boxes at level l
+    int pad;
+};
+
+struct Forest {
+    Ctx* ctx = nullptr;
+    int n_trees = 0;
+    i64 n_points = 0, n_boxes = 0;
+    // device arrays (owned, cudaMalloc)
+    double *sx = nullptr, *sy = nullptr, *sz = nullptr;  // Morton-sorted coordinates
+    int* sidx = nullptr;                                 // original row of each sorted point (local to its cloud)
+    float* boxes = nullptr;                              // 6 floats per box: lo xyz (rounded down), hi xyz (up)
+    double* normals = nullptr;                           // 3 per sorted point (sorted order), filled by normals
+    TreeDesc* d_trees = nullptr;
+    std::vector<TreeDesc> h_trees;
+    int normals_k = 0;
+};
+
+// Builds trees over clouds `cloud_ids[0..n_trees)` of a device CSR point set.  d_xyz rows are row-major fp64.
+int forest_build(Ctx* ctx, const double* d_xyz, const i64* h_off, const int* cloud_ids, int n_trees, Forest* out);
+void forest_free(Forest* f);
+
+// Query work item: 32 consecutive queries of one query set against one tree.
+struct QueryItem {
+    i64 q_off;   // first query row (into the query xyz array)
+    int count;   // 1..32
+    int tree;    // tree id
+};
+
+// kNN over arbitrary query rows.  out_idx/out_d2 (device, optional): k per query, row = query row.
+int forest_knn(Ctx* ctx, const Forest* f, const double* d_q, const QueryItem* d_items, i64 n_items, int k,
+               int* d_out_idx, double* d_out_d2);
+// 1-NN over arbitrary query rows.
+int forest_nearest(Ctx* ctx, const Forest* f, const double* d_q, const QueryItem* d_items, i64 n_items,
+                   int* d_out_idx, double* d_out_d2, int* d_out_pos);
+// Normals of every tree's own points (icp.hpp:23-67) into f->normals (sorted order); optional outputs in the
+// ORIGINAL row order of the clouds as laid out by (h_off, cloud_ids): d_out_normals[3*(pt_off+orig)] etc.
+int forest_normals(Ctx* ctx, Forest* f, int k, double* d_out_normals, double* d_out_evals);
+// host helper: items covering all points of all trees (queries = the trees' own sorted points)
+int make_items_dev(Ctx* ctx, const std::vector<QueryItem>& items, QueryItem** d_items);
+
+// ---------------------------------------------------------------------------------------------------------------
+// icp.cu
+// ---------------------------------------------------------------------------------------------------------------
+struct PairDesc {      // device-resident, one per scan pair
+    i64 src_off;       // first source row in d_src
+    int n_src;
+    int tree;          // target tree id in the forest
+    i64 item_off;      // first 64-query work item of this pair
+    int n_items;
+    int pad;
+};
+
+// Registers n_pairs pairs; d_src rows fp64.  results: host array.
+int icp_batch(Ctx* ctx, const Forest* f, const double* d_src, const std::vector<PairDesc>& pairs,
+              const sb_icp_config* cfg, sb_icp_result* results);
+void icp_graph_free(Ctx* ctx);
+
+// ---------------------------------------------------------------------------------------------------------------
+// scancontext.cu
+// ---------------------------------------------------------------------------------------------------------------
+int sc_compute_dev(Ctx* ctx, const double* d_xyz, const i64* d_off, int n_clouds, double* d_desc);
+// one query descriptor against n_db descriptors (all column-major 20x60, device)
+int sc_distance_dev(Ctx* ctx, const double* d_query_desc, const double* d_db, int n_db, double* d_out);
+int sc_keys_dev(Ctx* ctx, const double* d_desc, double* d_ring, double* d_sector);
+
+// icp.cu
+int solve_point_to_plane_dev(Ctx* ctx, const double* d_src, const double* d_tgt, const double* d_nrm, i64 n,
+                             double* d_out_T);
+// synth.cu
+int synth_scans_dev(Ctx* ctx, int beams, int azimuth_steps, float elev_top_deg, float elev_bot_deg, float max_range,
+                    float noise_sigma, float sensor_height, const float* boxes6, int n_boxes, const double* poses,
+                    int n_scans, uint64_t noise_seed, double* d_xyz, i64* out_offsets);
+
+}  // namespace sb
+
+struct sb_ctx {
+    sb::Ctx c;
+};
+
+// loop.cu — state of one loop-closure database (slam::LoopClosureDetector, loop_closure.hpp:143-148)
+struct sb_loop {
+    sb::Ctx* ctx = nullptr;
+    sb_loop_config cfg;
+    int rank = 0, world = 1;
+    // owned entries (+ possibly the newest one at the end, flagged by last_is_guest)
+    std::vector<int> entry_id;       // global entry id of each local slot
+    std::vector<int> frame_idx;      // loop_closure.hpp:147
+    std::vector<sb::i64> cloud_off;  // CSR into d_clouds (local slots), size = slots + 1
+    int n_global = 0;                // entries added so far (all ranks)
+    int last_frame = 0;
+    bool last_is_guest = false;      // the newest entry sits in the last slot although another rank owns it
+    double* d_desc = nullptr;        // slots x 1200
+    size_t desc_cap = 0;             // in descriptors
+    double* d_clouds = nullptr;      // rows x 3
+    size_t cloud_cap = 0;            // in rows
+};
+
+namespace sb {
+int loop_add(sb_loop* L, const double* xyz, i64 n, int frame_idx, const double* desc);
+int loop_candidates(sb_loop* L, std::vector<std::pair<double, int>>& cand);
+int loop_verify(sb_loop* L, const int* entries, const double* dist, int n, sb_loop_result* results, int* converged);
+}  // namespace sb

@@ -1,0 +1,512 @@
+// forest.cu — spatial index build, k-NN / 1-NN query kernels and surface-normal estimation.
+//
+// Replaces, for a batch of clouds at once:
+//   slam::KDTree::KDTree / build          slam_viz/include/slam_viz/core/kdtree.hpp:20-26, 87-110
+//   KDTree::nearest / nearest_batch       kdtree.hpp:32-59, 112-142
+//   KDTree::k_nearest                     kdtree.hpp:65-78, 144-180
+//   slam::estimate_normals                slam_viz/include/slam_viz/core/icp.hpp:23-67
+// The index is not a KD-tree: see traverse.cuh.  Build = per-cloud bounding box (exact atomic min/max on ordered
+// integers) -> 30-bit Morton codes -> segmented radix sort -> gather into SoA + leaf boxes -> upper box levels.
+#include "traverse.cuh"
+
+namespace sb {
+
+static constexpr int CHUNK = 1024;  // points per build work item (32 leaves)
+
+struct Chunk {
+    int tree;
+    int start;  // cloud-local first point
+    int count;
+    int pad;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// build kernels
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_bbox(const double* __restrict__ xyz, const i64* __restrict__ src_off,
+                                              const Chunk* __restrict__ chunks, long long* __restrict__ bb) {
+    Chunk c = chunks[blockIdx.x];
+    const double* base = xyz + 3 * (src_off[c.tree] + c.start);
+    double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int i = threadIdx.x; i < c.count; i += 256) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            double v = base[3 * i + a];
+            lo[a] = fmin(lo[a], v);
+            hi[a] = fmax(hi[a], v);
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[a] = fmin(lo[a], shfl_d_xor(lo[a], o));
+            hi[a] = fmax(hi[a], shfl_d_xor(hi[a], o));
+        }
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            if (lo[a] <= hi[a]) {
+                atomicMin(&bb[6 * c.tree + a], ordered_from_double(lo[a]));
+                atomicMax(&bb[6 * c.tree + 3 + a], ordered_from_double(hi[a]));
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ unsigned spread10(unsigned v) {  // 10 bits -> every third bit
+    v &= 0x3ffu;
+    v = (v | (v << 16)) & 0x030000ffu;
+    v = (v | (v << 8)) & 0x0300f00fu;
+    v = (v | (v << 4)) & 0x030c30c3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+
+__global__ void __launch_bounds__(256) k_morton(const double* __restrict__ xyz, const i64* __restrict__ src_off,
+                                                const Chunk* __restrict__ chunks, const long long* __restrict__ bb,
+                                                const TreeDesc* __restrict__ trees, u64* __restrict__ keys,
+                                                uint32_t* __restrict__ vals) {
+    Chunk c = chunks[blockIdx.x];
+    double lo[3], ext = 0.0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        lo[a] = double_from_ordered(bb[6 * c.tree + a]);
+        double e = double_from_ordered(bb[6 * c.tree + 3 + a]) - lo[a];
+        ext = fmax(ext, e);
+    }
+    double inv = ext > 0.0 ? 1024.0 / ext : 0.0;
+    if (!(inv < 1.0e300)) inv = 0.0;
+    const double* base = xyz + 3 * (src_off[c.tree] + c.start);
+    i64 dst = trees[c.tree].pt_off + c.start;
+    for (int i = threadIdx.x; i < c.count; i += 256) {
+        unsigned q[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            double f = (base[3 * i + a] - lo[a]) * inv;
+            int v = (f >= 0.0) ? (f < 1023.0 ? (int)f : 1023) : 0;  // NaN -> 0
+            q[a] = (unsigned)v;
+        }
+        keys[dst + i] = (u64)((spread10(q[0]) << 2) | (spread10(q[1]) << 1) | spread10(q[2]));
+        vals[dst + i] = (uint32_t)(c.start + i);
+    }
+}
+
+// gathers the sorted points into SoA and builds the level-0 boxes (one warp per leaf)
+__global__ void __launch_bounds__(256) k_gather_leaves(const double* __restrict__ xyz, const i64* __restrict__ src_off,
+                                                       const Chunk* __restrict__ chunks,
+                                                       const TreeDesc* __restrict__ trees,
+                                                       const uint32_t* __restrict__ sorted_vals,
+                                                       double* __restrict__ sx, double* __restrict__ sy,
+                                                       double* __restrict__ sz, int* __restrict__ sidx,
+                                                       float* __restrict__ boxes) {
+    Chunk c = chunks[blockIdx.x];
+    const TreeDesc& T = trees[c.tree];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double* base = xyz + 3 * src_off[c.tree];
+    for (int l = warp; l * 32 < c.count; l += 8) {
+        int j = c.start + l * 32 + lane;  // cloud-local sorted position
+        bool valid = j < T.n;
+        double x = 0, y = 0, z = 0;
+        if (valid) {
+            int o = (int)sorted_vals[T.pt_off + j];
+            x = base[3 * (i64)o + 0];
+            y = base[3 * (i64)o + 1];
+            z = base[3 * (i64)o + 2];
+            sx[T.pt_off + j] = x;
+            sy[T.pt_off + j] = y;
+            sz[T.pt_off + j] = z;
+            sidx[T.pt_off + j] = o;
+        }
+        double lo[3] = {valid ? x : INFINITY, valid ? y : INFINITY, valid ? z : INFINITY};
+        double hi[3] = {valid ? x : -INFINITY, valid ? y : -INFINITY, valid ? z : -INFINITY};
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                lo[a] = fmin(lo[a], shfl_d_xor(lo[a], o));
+                hi[a] = fmax(hi[a], shfl_d_xor(hi[a], o));
+            }
+        }
+        if (lane == 0) {
+            float* b = boxes + 6 * (T.box_off[0] + (c.start >> 5) + l);
+            b[0] = __double2float_rd(lo[0]);
+            b[1] = __double2float_rd(lo[1]);
+            b[2] = __double2float_rd(lo[2]);
+            b[3] = __double2float_ru(hi[0]);
+            b[4] = __double2float_ru(hi[1]);
+            b[5] = __double2float_ru(hi[2]);
+        }
+    }
+}
+
+// level >= 1: box b bounds the boxes [32b, 32b+32) of the level below.  One block per tree, warps stride over boxes.
+__global__ void __launch_bounds__(256) k_boxes_up(const TreeDesc* __restrict__ trees, int level,
+                                                  float* __restrict__ boxes) {
+    const TreeDesc& T = trees[blockIdx.x];
+    if (level > T.top) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int n_child = T.box_cnt[level - 1];
+    for (int b = warp; b < T.box_cnt[level]; b += 8) {
+        int ci = b * 32 + lane;
+        float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+        if (ci < n_child) {
+            const float* cb = boxes + 6 * (T.box_off[level - 1] + ci);
+            lo[0] = cb[0]; lo[1] = cb[1]; lo[2] = cb[2];
+            hi[0] = cb[3]; hi[1] = cb[4]; hi[2] = cb[5];
+        }
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+                hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+            }
+        }
+        if (lane == 0) {
+            float* ob = boxes + 6 * (T.box_off[level] + b);
+            ob[0] = lo[0]; ob[1] = lo[1]; ob[2] = lo[2];
+            ob[3] = hi[0]; ob[4] = hi[1]; ob[5] = hi[2];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host: build
+// ---------------------------------------------------------------------------------------------------------------
+void forest_free(Forest* f) {
+    if (!f) return;
+    cudaFree(f->sx); cudaFree(f->sy); cudaFree(f->sz); cudaFree(f->sidx); cudaFree(f->boxes);
+    cudaFree(f->normals); cudaFree(f->d_trees);
+    f->sx = f->sy = f->sz = nullptr; f->sidx = nullptr; f->boxes = nullptr; f->normals = nullptr; f->d_trees = nullptr;
+    f->h_trees.clear();
+    f->n_trees = 0; f->n_points = 0; f->n_boxes = 0;
+}
+
+int forest_build(Ctx* ctx, const double* d_xyz, const i64* h_off, const int* cloud_ids, int n_trees, Forest* f) {
+    f->ctx = ctx;
+    f->n_trees = n_trees;
+    f->h_trees.assign((size_t)n_trees, TreeDesc());
+    std::vector<i64> src_off((size_t)n_trees), seg_off((size_t)n_trees + 1);
+    std::vector<Chunk> chunks;
+    i64 np = 0, nb = 0;
+    int max_top = 0;
+    for (int t = 0; t < n_trees; ++t) {
+        int c = cloud_ids ? cloud_ids[t] : t;
+        i64 n64 = h_off[c + 1] - h_off[c];
+        if (n64 < 0 || n64 > 0x7fffffffLL) return fail(ctx, SB_ERR_RANGE, "index: cloud %d has %lld rows", c, n64);
+        TreeDesc& T = f->h_trees[t];
+        memset(&T, 0, sizeof(T));
+        T.pt_off = np;
+        T.n = (int)n64;
+        src_off[t] = h_off[c];
+        seg_off[t] = np;
+        int cnt = (T.n + 31) / 32, lev = 0;
+        while (true) {
+            T.box_off[lev] = nb;
+            T.box_cnt[lev] = cnt;
+            nb += cnt;
+            if (cnt <= 32) break;
+            cnt = (cnt + 31) / 32;
+            ++lev;
+        }
+        T.top = lev;
+        if (lev > max_top) max_top = lev;
+        for (int s = 0; s < T.n; s += CHUNK) {
+            Chunk ch;
+            ch.tree = t; ch.start = s; ch.count = T.n - s < CHUNK ? T.n - s : CHUNK; ch.pad = 0;
+            chunks.push_back(ch);
+        }
+        np += T.n;
+    }
+    seg_off[n_trees] = np;
+    f->n_points = np;
+    f->n_boxes = nb;
+    if (np >= (i64)0xffffffffLL) return fail(ctx, SB_ERR_RANGE, "index: more than 2^32-1 points in one forest");
+    SB_CUDA(ctx, cudaMalloc(&f->d_trees, sizeof(TreeDesc) * (size_t)(n_trees > 0 ? n_trees : 1)));
+    size_t npa = (size_t)(np > 0 ? np : 1), nba = (size_t)(nb > 0 ? nb : 1);
+    SB_CUDA(ctx, cudaMalloc(&f->sx, sizeof(double) * npa));
+    SB_CUDA(ctx, cudaMalloc(&f->sy, sizeof(double) * npa));
+    SB_CUDA(ctx, cudaMalloc(&f->sz, sizeof(double) * npa));
+    SB_CUDA(ctx, cudaMalloc(&f->sidx, sizeof(int) * npa));
+    SB_CUDA(ctx, cudaMalloc(&f->boxes, sizeof(float) * 6 * nba));
+    SB_CUDA(ctx, cudaMemcpyAsync(f->d_trees, f->h_trees.data(), sizeof(TreeDesc) * (size_t)n_trees,
+                                 cudaMemcpyHostToDevice, ctx->stream));
+    if (np == 0) return SB_OK;
+
+    i64* d_src_off;
+    Chunk* d_chunks;
+    long long* d_bb;
+    u64 *ka, *kb, *ks;
+    uint32_t *va, *vb, *vs;
+    SB_TRY(arena_get(ctx, (size_t)n_trees, &d_src_off));
+    SB_TRY(arena_get(ctx, chunks.size(), &d_chunks));
+    SB_TRY(arena_get(ctx, (size_t)6 * n_trees, &d_bb));
+    SB_TRY(arena_get(ctx, (size_t)np, &ka));
+    SB_TRY(arena_get(ctx, (size_t)np, &kb));
+    SB_TRY(arena_get(ctx, (size_t)np, &va));
+    SB_TRY(arena_get(ctx, (size_t)np, &vb));
+    SB_CUDA(ctx, cudaMemcpyAsync(d_src_off, src_off.data(), sizeof(i64) * (size_t)n_trees, cudaMemcpyHostToDevice, ctx->stream));
+    SB_CUDA(ctx, cudaMemcpyAsync(d_chunks, chunks.data(), sizeof(Chunk) * chunks.size(), cudaMemcpyHostToDevice, ctx->stream));
+    {
+        std::vector<long long> init((size_t)6 * n_trees);
+        for (int t = 0; t < n_trees; ++t)
+            for (int a = 0; a < 3; ++a) { init[6 * t + a] = INT64_MAX; init[6 * t + 3 + a] = INT64_MIN; }
+        SB_CUDA(ctx, cudaMemcpyAsync(d_bb, init.data(), sizeof(long long) * init.size(), cudaMemcpyHostToDevice, ctx->stream));
+        SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the host vectors above go out of scope
+    }
+    unsigned nch = (unsigned)chunks.size();
+    SB_LAUNCH(ctx, k_bbox, nch, 256, 0, d_xyz, d_src_off, d_chunks, d_bb);
+    SB_LAUNCH(ctx, k_morton, nch, 256, 0, d_xyz, d_src_off, d_chunks, d_bb, f->d_trees, ka, va);
+    SB_TRY(segmented_sort_pairs(ctx, ka, kb, va, vb, seg_off.data(), n_trees, 30, &ks, &vs));
+    SB_LAUNCH(ctx, k_gather_leaves, nch, 256, 0, d_xyz, d_src_off, d_chunks, f->d_trees, vs, f->sx, f->sy, f->sz,
+              f->sidx, f->boxes);
+    for (int l = 1; l <= max_top; ++l) SB_LAUNCH(ctx, k_boxes_up, (unsigned)n_trees, 256, 0, f->d_trees, l, f->boxes);
+    return SB_OK;
+}
+
+int make_items_dev(Ctx* ctx, const std::vector<QueryItem>& items, QueryItem** d_items) {
+    SB_TRY(arena_get(ctx, items.size() ? items.size() : 1, d_items));
+    if (!items.empty()) {
+        SB_CUDA(ctx, cudaMemcpyAsync(*d_items, items.data(), sizeof(QueryItem) * items.size(), cudaMemcpyHostToDevice,
+                                     ctx->stream));
+        SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return SB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// query kernels: one warp per 32-query item, persistent grid
+// ---------------------------------------------------------------------------------------------------------------
+static constexpr int QWARPS = 8;
+
+__device__ __forceinline__ void load_tree(TreeDesc* dst, const TreeDesc* src, int lane) {
+    const int* s = reinterpret_cast<const int*>(src);
+    int* d = reinterpret_cast<int*>(dst);
+    for (int i = lane; i < (int)(sizeof(TreeDesc) / 4); i += 32) d[i] = s[i];
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(QWARPS * 32) k_nearest(ForestView F, const double* __restrict__ q,
+                                                         const QueryItem* __restrict__ items, i64 n_items,
+                                                         int* __restrict__ out_idx, double* __restrict__ out_d2,
+                                                         int* __restrict__ out_pos) {
+    __shared__ WarpStack stacks[QWARPS];
+    __shared__ TreeDesc s_tree[QWARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpStack& S = stacks[warp];
+    for (i64 it = (i64)blockIdx.x * QWARPS + warp; it < n_items; it += (i64)gridDim.x * QWARPS) {
+        QueryItem I = items[it];
+        __syncwarp();
+        load_tree(&s_tree[warp], &F.trees[I.tree], lane);
+        const TreeDesc& T = s_tree[warp];
+        double mx = 0, my = 0, mz = 0;
+        if (lane < I.count) {
+            const double* p = q + 3 * (I.q_off + lane);
+            mx = p[0]; my = p[1]; mz = p[2];
+        }
+        int r_idx = -1, r_pos = -1;
+        double r_d = 1.7976931348623157e308;
+        for (int j = 0; j < I.count; ++j) {
+            double qx = shfl_d(mx, j), qy = shfl_d(my, j), qz = shfl_d(mz, j);
+            NearestVisitor V(F, T, qx, qy, qz, lane);
+            traverse(F, T, qx, qy, qz, S, V, lane);
+            if (lane == j) { r_idx = V.best_idx; r_pos = V.best_pos; r_d = V.best_d; }
+        }
+        if (lane < I.count) {
+            out_idx[I.q_off + lane] = r_idx;
+            if (out_d2) out_d2[I.q_off + lane] = r_d;
+            if (out_pos) out_pos[I.q_off + lane] = r_pos;
+        }
+    }
+}
+
+// ----- 3x3 symmetric eigen-decomposition: cyclic Jacobi, the oracle's operation order (oracle/slam_oracle.cpp
+// jacobi3; Eigen's SelfAdjointEigenSolver at icp.hpp:55 is an iterative QR — see DESIGN.md "normals").
+// This translation unit is compiled with -fmad=false so every * and + below is a separately rounded IEEE op.
+template <int P, int Q, int K>
+__device__ __forceinline__ void jacobi_rotate(double (&A)[3][3], double (&V)[3][3]) {
+    double apq = A[P][Q];
+    if (apq == 0.0) return;
+    double theta = (A[Q][Q] - A[P][P]) / (2.0 * apq);
+    double t = 1.0 / (fabs(theta) + sqrt(theta * theta + 1.0));
+    if (theta < 0.0) t = -t;
+    double c = 1.0 / sqrt(t * t + 1.0);
+    double s = t * c;
+    double app = A[P][P], aqq = A[Q][Q];
+    A[P][P] = app - t * apq;
+    A[Q][Q] = aqq + t * apq;
+    A[P][Q] = 0.0; A[Q][P] = 0.0;
+    double akp = A[K][P], akq = A[K][Q];
+    A[K][P] = c * akp - s * akq; A[P][K] = A[K][P];
+    A[K][Q] = s * akp + c * akq; A[Q][K] = A[K][Q];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        double vip = V[i][P], viq = V[i][Q];
+        V[i][P] = c * vip - s * viq;
+        V[i][Q] = s * vip + c * viq;
+    }
+}
+
+__device__ __forceinline__ void jacobi3(double (&A)[3][3], double (&w)[3], double (&V)[3][3]) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) V[i][j] = (i == j) ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 12; ++sweep) {
+        double off = fabs(A[0][1]) + fabs(A[0][2]) + fabs(A[1][2]);
+        if (off == 0.0) break;
+        jacobi_rotate<0, 1, 2>(A, V);
+        jacobi_rotate<0, 2, 1>(A, V);
+        jacobi_rotate<1, 2, 0>(A, V);
+    }
+    w[0] = A[0][0]; w[1] = A[1][1]; w[2] = A[2][2];
+}
+
+// MODE 0: k-NN of external queries -> out_idx/out_d2 (row-major nq x k)
+// MODE 1: normals of the trees' own points (queries are the sorted points; item.q_off is cloud-local sorted start)
+template <int MODE>
+__global__ void __launch_bounds__(QWARPS * 32) k_knn(ForestView F, const double* __restrict__ q,
+                                                     const QueryItem* __restrict__ items, i64 n_items, int k,
+                                                     int* __restrict__ out_idx, double* __restrict__ out_d2,
+                                                     double* __restrict__ nrm_sorted, double* __restrict__ nrm_orig,
+                                                     double* __restrict__ evals_orig) {
+    __shared__ WarpStack stacks[QWARPS];
+    __shared__ TreeDesc s_tree[QWARPS];
+    __shared__ int s_nbr[MODE == 1 ? QWARPS : 1][32][33];  // neighbour positions (cloud-local sorted), padded
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpStack& S = stacks[warp];
+    for (i64 it = (i64)blockIdx.x * QWARPS + warp; it < n_items; it += (i64)gridDim.x * QWARPS) {
+        QueryItem I = items[it];
+        __syncwarp();
+        load_tree(&s_tree[warp], &F.trees[I.tree], lane);
+        const TreeDesc& T = s_tree[warp];
+        double mx = 0, my = 0, mz = 0;
+        if (lane < I.count) {
+            if (MODE == 1) {
+                i64 p = T.pt_off + I.q_off + lane;
+                mx = F.sx[p]; my = F.sy[p]; mz = F.sz[p];
+            } else {
+                const double* p = q + 3 * (I.q_off + lane);
+                mx = p[0]; my = p[1]; mz = p[2];
+            }
+        }
+        int my_m = 0;
+        for (int j = 0; j < I.count; ++j) {
+            double qx = shfl_d(mx, j), qy = shfl_d(my, j), qz = shfl_d(mz, j);
+            KnnVisitor V(F, T, qx, qy, qz, lane, k);
+            traverse(F, T, qx, qy, qz, S, V, lane);
+            bool have = lane < k && V.lidx != 0x7fffffff;
+            int m = __popc(__ballot_sync(0xffffffffu, have));
+            if (MODE == 1) {
+                if (lane < k) s_nbr[warp][j][lane] = V.lpos;
+                if (lane == j) my_m = m;
+            } else {
+                if (lane < k) {
+                    i64 o = (I.q_off + j) * k + lane;
+                    out_idx[o] = have ? V.lidx : -1;
+                    if (out_d2) out_d2[o] = have ? V.ld : 1.7976931348623157e308;
+                }
+            }
+        }
+        if (MODE == 1) {
+            __syncwarp();
+            if (lane < I.count) {
+                const int* nb = s_nbr[warp][lane];
+                const int m = my_m;
+                double n0 = 0.0, n1 = 0.0, n2 = 1.0, e0 = 0.0, e1 = 0.0, e2 = 0.0;
+                if (m >= 3) {  // icp.hpp:34-37
+                    double c0 = 0.0, c1 = 0.0, c2 = 0.0;
+                    for (int j = 0; j < m; ++j) {  // icp.hpp:40-44, neighbours ascending by (d2, idx)
+                        i64 p = T.pt_off + nb[j];
+                        c0 += F.sx[p]; c1 += F.sy[p]; c2 += F.sz[p];
+                    }
+                    double md = (double)m;
+                    c0 /= md; c1 /= md; c2 /= md;
+                    double C00 = 0, C01 = 0, C02 = 0, C11 = 0, C12 = 0, C22 = 0;
+                    for (int j = 0; j < m; ++j) {  // icp.hpp:47-52
+                        i64 p = T.pt_off + nb[j];
+                        double d0 = F.sx[p] - c0, d1 = F.sy[p] - c1, d2 = F.sz[p] - c2;
+                        C00 += d0 * d0; C01 += d0 * d1; C02 += d0 * d2;
+                        C11 += d1 * d1; C12 += d1 * d2; C22 += d2 * d2;
+                    }
+                    double A[3][3], w[3], V[3][3];
+                    A[0][0] = C00 / md; A[0][1] = C01 / md; A[0][2] = C02 / md;
+                    A[1][0] = A[0][1];  A[1][1] = C11 / md; A[1][2] = C12 / md;
+                    A[2][0] = A[0][2];  A[2][1] = A[1][2];  A[2][2] = C22 / md;
+                    jacobi3(A, w, V);
+                    // eigenvector of the smallest eigenvalue, first index on ties (icp.hpp:56 col(0))
+                    double v0 = V[0][0], v1 = V[1][0], v2 = V[2][0], ws = w[0];
+                    if (w[1] < ws) { ws = w[1]; v0 = V[0][1]; v1 = V[1][1]; v2 = V[2][1]; }
+                    if (w[2] < ws) { ws = w[2]; v0 = V[0][2]; v1 = V[1][2]; v2 = V[2][2]; }
+                    if (v2 < 0.0) { v0 = -v0; v1 = -v1; v2 = -v2; }  // icp.hpp:59-61
+                    double nn = sqrt((v0 * v0 + v1 * v1) + v2 * v2);  // icp.hpp:63
+                    n0 = v0 / nn; n1 = v1 / nn; n2 = v2 / nn;
+                    // ascending eigenvalues (diagnostic output)
+                    e0 = w[0]; e1 = w[1]; e2 = w[2];
+                    if (e1 < e0) { double t = e0; e0 = e1; e1 = t; }
+                    if (e2 < e1) { double t = e1; e1 = e2; e2 = t; }
+                    if (e1 < e0) { double t = e0; e0 = e1; e1 = t; }
+                }
+                i64 ps = T.pt_off + I.q_off + lane;
+                nrm_sorted[3 * ps + 0] = n0; nrm_sorted[3 * ps + 1] = n1; nrm_sorted[3 * ps + 2] = n2;
+                i64 po = T.pt_off + F.sidx[ps];
+                if (nrm_orig) { nrm_orig[3 * po + 0] = n0; nrm_orig[3 * po + 1] = n1; nrm_orig[3 * po + 2] = n2; }
+                if (evals_orig) { evals_orig[3 * po + 0] = e0; evals_orig[3 * po + 1] = e1; evals_orig[3 * po + 2] = e2; }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+static ForestView view_of(const Forest* f) {
+    ForestView v;
+    v.sx = f->sx; v.sy = f->sy; v.sz = f->sz; v.sidx = f->sidx; v.boxes = f->boxes; v.trees = f->d_trees;
+    return v;
+}
+
+static int query_grid(Ctx* ctx, i64 n_items) {
+    i64 blocks = (n_items + QWARPS - 1) / QWARPS;
+    i64 cap = (i64)ctx->sm_count * 8;  // persistent: 8 resident 256-thread CTAs per SM
+    return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+}
+
+int forest_nearest(Ctx* ctx, const Forest* f, const double* d_q, const QueryItem* d_items, i64 n_items,
+                   int* d_out_idx, double* d_out_d2, int* d_out_pos) {
+    if (n_items <= 0) return SB_OK;
+    SB_LAUNCH(ctx, k_nearest, query_grid(ctx, n_items), QWARPS * 32, 0, view_of(f), d_q, d_items, n_items, d_out_idx,
+              d_out_d2, d_out_pos);
+    return SB_OK;
+}
+
+int forest_knn(Ctx* ctx, const Forest* f, const double* d_q, const QueryItem* d_items, i64 n_items, int k,
+               int* d_out_idx, double* d_out_d2) {
+    if (n_items <= 0) return SB_OK;
+    SB_LAUNCH(ctx, k_knn<0>, query_grid(ctx, n_items), QWARPS * 32, 0, view_of(f), d_q, d_items, n_items, k, d_out_idx,
+              d_out_d2, nullptr, nullptr, nullptr);
+    return SB_OK;
+}
+
+int forest_normals(Ctx* ctx, Forest* f, int k, double* d_out_normals, double* d_out_evals) {
+    if (!f->normals) SB_CUDA(ctx, cudaMalloc(&f->normals, sizeof(double) * 3 * (size_t)(f->n_points > 0 ? f->n_points : 1)));
+    f->normals_k = k;
+    std::vector<QueryItem> items;
+    for (int t = 0; t < f->n_trees; ++t) {
+        const TreeDesc& T = f->h_trees[t];
+        for (int s = 0; s < T.n; s += 32) {
+            QueryItem I;
+            I.q_off = s; I.count = T.n - s < 32 ? T.n - s : 32; I.tree = t;
+            items.push_back(I);
+        }
+    }
+    if (items.empty()) return SB_OK;
+    QueryItem* d_items;
+    SB_TRY(make_items_dev(ctx, items, &d_items));
+    i64 n_items = (i64)items.size();
+    SB_LAUNCH(ctx, k_knn<1>, query_grid(ctx, n_items), QWARPS * 32, 0, view_of(f), nullptr, d_items, n_items, k,
+              nullptr, nullptr, f->normals, d_out_normals, d_out_evals);
+    return SB_OK;
+}
+
+}  // namespace sb

@@ -1,0 +1,586 @@
+// icp.cu — batched point-to-plane ICP; replaces slam::solve_point_to_plane and slam::icp_point_to_plane
+// (slam_viz/include/slam_viz/core/icp.hpp:89-144 and :157-258).
+//
+// The reference runs, per pair and per iteration: a KD-tree 1-NN pass over the source (twice, icp.hpp:185,190),
+// an RMS pass, an n x 6 Jacobian build, J^T J, an LDLT solve, a Rodrigues update and a full rewrite of the
+// source cloud.  Here one iteration of ALL pairs of a batch is two kernels:
+//   k_icp_iter   one warp per 32 source points: cur = T * src (never stored), warp-cooperative exact 1-NN in the
+//                target's tree (traverse.cuh), then lane-parallel residual + the 28 sums (21 of J^T J, 6 of J^T r,
+//                1 of r^2), fixed-order shuffle tree, one 224-byte partial per work item;
+//   k_icp_solve  one warp per pair: adds the pair's partials in item order (run-to-run deterministic), RMS error,
+//                convergence test (icp.hpp:210-217), 6x6 LDL^T, Rodrigues (icp.hpp:127-142), T <- delta * T.
+// The loop is a CUDA-graph WHILE node whose condition k_icp_solve's last block sets from the device-side count of
+// still-active pairs: no host round trip per iteration.  All kernels read their arguments from one device-resident
+// IcpJob, so the instantiated graph is reused by every call on the context.
+#include "traverse.cuh"
+
+#include <cstdlib>
+
+namespace sb {
+
+enum { ST_ACTIVE = 0, ST_CONVERGED = 1, ST_EXHAUSTED = 2, ST_DONE = 3 };
+
+struct PairState {
+    double prev_error;
+    int state;
+    int iter;
+};
+
+struct IcpJob {
+    ForestView F;
+    const double* normals;   // 3 per sorted target point
+    const double* src;       // source rows, fp64 xyz
+    const QueryItem* items;  // tree field = pair id
+    i64 n_items;
+    const PairDesc* pairs;
+    sb_icp_result* results;
+    PairState* state;
+    double* partials;        // n_items x 28
+    double T0[16];
+    double tol, min_err;
+    int n_pairs;
+    int max_it;
+    int n_active;
+    int ticket;
+};
+
+static constexpr int IWARPS = 8;
+static constexpr int NSUM = 28;
+
+// -------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_icp_init(IcpJob* __restrict__ job, cudaGraphConditionalHandle cond,
+                                                  int use_cond) {
+    const int n = job->n_pairs;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+        sb_icp_result& R = job->results[p];
+        PairDesc P = job->pairs[p];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) R.transformation[i] = job->T0[i];
+        R.final_error = 0.0;
+        R.converged = 0;
+        R.num_iterations = 0;
+        R.history_len = 0;
+        bool empty = P.n_src <= 0 || job->F.trees[P.tree].n <= 0;
+        R.status = empty ? SB_ERR_EMPTY : SB_OK;
+        PairState s;
+        s.prev_error = 1.7976931348623157e308;  // icp.hpp:178
+        s.iter = 0;
+        s.state = empty ? ST_DONE : (job->max_it > 0 ? ST_ACTIVE : ST_EXHAUSTED);
+        job->state[p] = s;
+    }
+    if (use_cond && blockIdx.x == 0 && threadIdx.x == 0)
+        cudaGraphSetConditional(cond, (job->n_active > 0 && job->max_it > 0) ? 1u : 0u);
+}
+
+// phase 0: pairs in ST_ACTIVE; phase 1: pairs in ST_EXHAUSTED (final error pass, icp.hpp:235-252)
+__global__ void __launch_bounds__(IWARPS * 32) k_icp_iter(const IcpJob* __restrict__ job, int phase) {
+    __shared__ WarpStack stacks[IWARPS];
+    __shared__ TreeDesc s_tree[IWARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpStack& S = stacks[warp];
+    const ForestView F = job->F;
+    const i64 n_items = job->n_items;
+    const int want = phase == 0 ? ST_ACTIVE : ST_EXHAUSTED;
+    for (i64 it = (i64)blockIdx.x * IWARPS + warp; it < n_items; it += (i64)gridDim.x * IWARPS) {
+        QueryItem I = job->items[it];
+        const int pair = I.tree;
+        if (job->state[pair].state != want) continue;
+        PairDesc P = job->pairs[pair];
+        __syncwarp();
+        {
+            const int* s = reinterpret_cast<const int*>(&F.trees[P.tree]);
+            int* d = reinterpret_cast<int*>(&s_tree[warp]);
+            for (int i = lane; i < (int)(sizeof(TreeDesc) / 4); i += 32) d[i] = s[i];
+            __syncwarp();
+        }
+        const TreeDesc& T = s_tree[warp];
+        const double* Tm = job->results[pair].transformation;
+        // cur = src * R^T + t, the oracle's association (types.hpp:110-115)
+        double cx = 0, cy = 0, cz = 0;
+        if (lane < I.count) {
+            const double* p = job->src + 3 * (I.q_off + lane);
+            double x = p[0], y = p[1], z = p[2];
+            cx = ((x * Tm[0] + y * Tm[1]) + z * Tm[2]) + Tm[3];
+            cy = ((x * Tm[4] + y * Tm[5]) + z * Tm[6]) + Tm[7];
+            cz = ((x * Tm[8] + y * Tm[9]) + z * Tm[10]) + Tm[11];
+        }
+        int my_pos = -1;
+        for (int j = 0; j < I.count; ++j) {
+            double qx = shfl_d(cx, j), qy = shfl_d(cy, j), qz = shfl_d(cz, j);
+            NearestVisitor V(F, T, qx, qy, qz, lane);
+            traverse(F, T, qx, qy, qz, S, V, lane);
+            if (lane == j) my_pos = V.best_pos;
+        }
+        double acc[NSUM];
+#pragma unroll
+        for (int i = 0; i < NSUM; ++i) acc[i] = 0.0;
+        if (lane < I.count && my_pos >= 0) {
+            i64 p = T.pt_off + my_pos;
+            double tx = F.sx[p], ty = F.sy[p], tz = F.sz[p];
+            double nx = job->normals[3 * p], ny = job->normals[3 * p + 1], nz = job->normals[3 * p + 2];
+            double J[6];
+            J[0] = cy * nz - cz * ny;  // p x n, icp.hpp:105
+            J[1] = cz * nx - cx * nz;
+            J[2] = cx * ny - cy * nx;
+            J[3] = nx; J[4] = ny; J[5] = nz;
+            double b = ((tx - cx) * nx + (ty - cy) * ny) + (tz - cz) * nz;  // icp.hpp:116
+            int t = 0;
+#pragma unroll
+            for (int a = 0; a < 6; ++a)
+#pragma unroll
+                for (int c = a; c < 6; ++c) acc[t++] = J[a] * J[c];
+#pragma unroll
+            for (int a = 0; a < 6; ++a) acc[21 + a] = J[a] * b;
+            acc[27] = b * b;
+        }
+        // fixed-order butterfly: every lane ends with every sum
+        double mine = 0.0;
+#pragma unroll
+        for (int i = 0; i < NSUM; ++i) {
+            double v = acc[i];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += shfl_d_xor(v, o);
+            if (lane == i) mine = v;
+        }
+        if (lane < NSUM) job->partials[it * NSUM + lane] = mine;
+    }
+}
+
+// 6x6 SPD solve by LDL^T without pivoting (Eigen: pivoted LDLT, icp.hpp:120; oracle ldlt6_solve)
+__device__ __forceinline__ void ldlt6_solve(const double (&A)[6][6], const double (&b)[6], double (&x)[6]) {
+    double L[6][6], D[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        double d = A[j][j];
+#pragma unroll
+        for (int k = 0; k < 6; ++k)
+            if (k < j) d -= L[j][k] * L[j][k] * D[k];
+        D[j] = d;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            if (i > j) {
+                double s = A[i][j];
+#pragma unroll
+                for (int k = 0; k < 6; ++k)
+                    if (k < j) s -= L[i][k] * L[j][k] * D[k];
+                L[i][j] = s / d;
+            }
+        }
+    }
+    double y[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        double s = b[i];
+#pragma unroll
+        for (int k = 0; k < 6; ++k)
+            if (k < i) s -= L[i][k] * y[k];
+        y[i] = s;
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) y[i] /= D[i];
+#pragma unroll
+    for (int i = 5; i >= 0; --i) {
+        double s = y[i];
+#pragma unroll
+        for (int k = 0; k < 6; ++k)
+            if (k > i) s -= L[k][i] * x[k];
+        x[i] = s;
+    }
+}
+
+// x -> 4x4 row-major delta (icp.hpp:123-144)
+__device__ __forceinline__ void delta_from_x(const double (&x)[6], double (&Dm)[16]) {
+    double angle = sqrt((x[0] * x[0] + x[1] * x[1]) + x[2] * x[2]);  // icp.hpp:127
+    double R[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    if (!(angle < 1e-10)) {
+        double ax = x[0] / angle, ay = x[1] / angle, az = x[2] / angle;
+        double K[3][3] = {{0, -az, ay}, {az, 0, -ax}, {-ay, ax, 0}};
+        double K2[3][3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                double s = 0;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) s += K[i][k] * K[k][j];
+                K2[i][j] = s;
+            }
+        double sn = sin(angle), cs = 1 - cos(angle);
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) R[i][j] = (R[i][j] + sn * K[i][j]) + cs * K2[i][j];
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) Dm[i] = (i % 5 == 0) ? 1.0 : 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) Dm[4 * i + j] = R[i][j];
+        Dm[4 * i + 3] = x[3 + i];
+    }
+}
+
+__device__ __forceinline__ void mat4_mul(const double (&A)[16], const double* B, double (&C)[16]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            double s = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) s += A[4 * i + k] * B[4 * k + j];
+            C[4 * i + j] = s;
+        }
+}
+
+// sums the pair's partials in item order; lane l gets sum l (l < 28)
+__device__ __forceinline__ double sum_partials(const IcpJob* job, const PairDesc& P, int lane) {
+    double s = 0.0;
+    if (lane < NSUM) {
+        const double* base = job->partials + P.item_off * NSUM + lane;
+        for (int i = 0; i < P.n_items; ++i) s += base[(i64)i * NSUM];
+    }
+    return s;
+}
+
+// mode 0: loop body (icp.hpp:181-232); mode 1: final error (icp.hpp:235-255)
+__global__ void __launch_bounds__(256) k_icp_solve(IcpJob* __restrict__ job, int mode, cudaGraphConditionalHandle cond,
+                                                   int use_cond) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    const int n = job->n_pairs;
+    for (int p = blockIdx.x * wpb + (threadIdx.x >> 5); p < n; p += gridDim.x * wpb) {
+        PairState st = job->state[p];
+        sb_icp_result& R = job->results[p];
+        if (mode == 1) {
+            if (st.state == ST_CONVERGED) {
+                if (lane == 0) {  // broke out of the loop: the final pass repeats the last error (Appendix A.5)
+                    double e = R.error_history[R.history_len - 1];
+                    R.final_error = e;
+                    R.error_history[R.history_len] = e;
+                    R.history_len += 1;
+                    R.num_iterations = R.history_len - 1;  // icp.hpp:255
+                    job->state[p].state = ST_DONE;
+                }
+                continue;
+            }
+            if (st.state != ST_EXHAUSTED) continue;
+        } else if (st.state != ST_ACTIVE) {
+            continue;
+        }
+        PairDesc P = job->pairs[p];
+        double s = sum_partials(job, P, lane);
+        double sr2 = shfl_d(s, 27);
+        double e = sqrt(sr2 / (double)P.n_src);  // icp.hpp:198-207
+        if (mode == 1) {
+            if (lane == 0) {
+                R.final_error = e;
+                R.error_history[R.history_len] = e;
+                R.history_len += 1;
+                R.num_iterations = R.history_len - 1;
+                job->state[p].state = ST_DONE;
+            }
+            continue;
+        }
+        double A[6][6], g[6];
+        {
+            int t = 0;
+#pragma unroll
+            for (int a = 0; a < 6; ++a)
+#pragma unroll
+                for (int c = a; c < 6; ++c) {
+                    double v = shfl_d(s, t);
+                    A[a][c] = v;
+                    A[c][a] = v;
+                    ++t;
+                }
+#pragma unroll
+            for (int a = 0; a < 6; ++a) g[a] = shfl_d(s, 21 + a);
+        }
+        if (lane == 0) {
+            int hl = R.history_len;
+            R.error_history[hl] = e;  // icp.hpp:207
+            R.history_len = hl + 1;
+            if (e < job->min_err || fabs(st.prev_error - e) < job->tol) {  // icp.hpp:210-217
+                R.converged = 1;
+                job->state[p].state = ST_CONVERGED;
+                atomicSub(&job->n_active, 1);
+            } else {
+                double x[6], Dm[16], Tn[16];
+                ldlt6_solve(A, g, x);
+                delta_from_x(x, Dm);
+                mat4_mul(Dm, R.transformation, Tn);  // total = delta * total, icp.hpp:229
+#pragma unroll
+                for (int i = 0; i < 16; ++i) R.transformation[i] = Tn[i];
+                PairState ns;
+                ns.prev_error = e;
+                ns.iter = st.iter + 1;
+                ns.state = ST_ACTIVE;
+                if (ns.iter >= job->max_it) {
+                    ns.state = ST_EXHAUSTED;
+                    atomicSub(&job->n_active, 1);
+                }
+                job->state[p] = ns;
+            }
+        }
+    }
+    if (mode == 0) {
+        // last block to finish decides whether the WHILE node runs another iteration
+        __shared__ int s_last;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            int t = atomicAdd(&job->ticket, 1);
+            s_last = (t == (int)gridDim.x - 1);
+        }
+        __syncthreads();
+        if (s_last && threadIdx.x == 0) {
+            __threadfence();
+            int active = atomicAdd(&job->n_active, 0);
+            job->ticket = 0;
+            if (use_cond) cudaGraphSetConditional(cond, active > 0 ? 1u : 0u);
+        }
+    }
+}
+
+// solve_point_to_plane on explicit correspondences (icp.hpp:89-144): one block, fixed-order reduction
+__global__ void __launch_bounds__(256) k_solve_p2p(const double* __restrict__ src, const double* __restrict__ tgt,
+                                                   const double* __restrict__ nrm, i64 n, double* __restrict__ out_T) {
+    __shared__ double sm[8][NSUM];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double acc[NSUM];
+#pragma unroll
+    for (int i = 0; i < NSUM; ++i) acc[i] = 0.0;
+    for (i64 i = threadIdx.x; i < n; i += 256) {
+        double cx = src[3 * i], cy = src[3 * i + 1], cz = src[3 * i + 2];
+        double tx = tgt[3 * i], ty = tgt[3 * i + 1], tz = tgt[3 * i + 2];
+        double nx = nrm[3 * i], ny = nrm[3 * i + 1], nz = nrm[3 * i + 2];
+        double J[6];
+        J[0] = cy * nz - cz * ny; J[1] = cz * nx - cx * nz; J[2] = cx * ny - cy * nx;
+        J[3] = nx; J[4] = ny; J[5] = nz;
+        double b = ((tx - cx) * nx + (ty - cy) * ny) + (tz - cz) * nz;
+        int t = 0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a)
+#pragma unroll
+            for (int c = a; c < 6; ++c) acc[t++] += J[a] * J[c];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) acc[21 + a] += J[a] * b;
+        acc[27] += b * b;
+    }
+#pragma unroll
+    for (int i = 0; i < NSUM; ++i) {
+        double v = acc[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += shfl_d_xor(v, o);
+        if (lane == 0) sm[warp][i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s[NSUM];
+#pragma unroll
+        for (int i = 0; i < NSUM; ++i) {
+            double v = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) v += sm[w][i];
+            s[i] = v;
+        }
+        double A[6][6], g[6], x[6], Dm[16];
+        int t = 0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a)
+#pragma unroll
+            for (int c = a; c < 6; ++c) { A[a][c] = s[t]; A[c][a] = s[t]; ++t; }
+#pragma unroll
+        for (int a = 0; a < 6; ++a) g[a] = s[21 + a];
+        ldlt6_solve(A, g, x);
+        delta_from_x(x, Dm);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) out_T[i] = Dm[i];
+    }
+}
+
+int solve_point_to_plane_dev(Ctx* ctx, const double* d_src, const double* d_tgt, const double* d_nrm, i64 n,
+                             double* d_out_T) {
+    SB_LAUNCH(ctx, k_solve_p2p, 1, 256, 0, d_src, d_tgt, d_nrm, n, d_out_T);
+    return SB_OK;
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// host: graph construction + batch driver
+// -------------------------------------------------------------------------------------------------------------
+struct IcpGraph {
+    IcpJob* d_job = nullptr;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    int iter_grid = 0, solve_grid = 0;
+};
+
+void icp_graph_free(Ctx* ctx) {
+    IcpGraph* G = static_cast<IcpGraph*>(ctx->icp_graph);
+    if (!G) return;
+    if (G->exec) cudaGraphExecDestroy(G->exec);
+    if (G->graph) cudaGraphDestroy(G->graph);
+    cudaFree(G->d_job);
+    delete G;
+    ctx->icp_graph = nullptr;
+}
+
+static int add_kernel(Ctx* ctx, cudaGraph_t g, cudaGraphNode_t* node, const cudaGraphNode_t* dep, void* fn, int grid,
+                      int block, void** args) {
+    cudaKernelNodeParams kp;
+    memset(&kp, 0, sizeof(kp));
+    kp.func = fn;
+    kp.gridDim = dim3((unsigned)grid, 1, 1);
+    kp.blockDim = dim3((unsigned)block, 1, 1);
+    kp.sharedMemBytes = 0;
+    kp.kernelParams = args;
+    kp.extra = nullptr;
+    SB_CUDA(ctx, cudaGraphAddKernelNode(node, g, dep, dep ? 1 : 0, &kp));
+    return SB_OK;
+}
+
+static int icp_graph_get(Ctx* ctx, IcpGraph** out) {
+    if (ctx->icp_graph) {
+        *out = static_cast<IcpGraph*>(ctx->icp_graph);
+        return SB_OK;
+    }
+    IcpGraph* G = new IcpGraph();
+    ctx->icp_graph = G;
+    *out = G;
+    SB_CUDA(ctx, cudaMalloc(&G->d_job, sizeof(IcpJob)));
+    G->iter_grid = ctx->sm_count * 8;
+    G->solve_grid = ctx->sm_count;
+    if (getenv("SB_ICP_NOGRAPH")) return SB_OK;
+    SB_CUDA(ctx, cudaGraphCreate(&G->graph, 0));
+    cudaGraphConditionalHandle cond;
+    SB_CUDA(ctx, cudaGraphConditionalHandleCreate(&cond, G->graph, 1, cudaGraphCondAssignDefault));
+    IcpJob* job = G->d_job;
+    int one = 1, zero = 0;
+    cudaGraphNode_t n_init, n_while, n_iter, n_solve, n_fiter, n_final;
+    {
+        void* args[] = {&job, &cond, &one};
+        SB_TRY(add_kernel(ctx, G->graph, &n_init, nullptr, (void*)k_icp_init, ctx->sm_count, 256, args));
+    }
+    cudaGraphNodeParams wp = {};
+    wp.type = cudaGraphNodeTypeConditional;
+    wp.conditional.handle = cond;
+    wp.conditional.type = cudaGraphCondTypeWhile;
+    wp.conditional.size = 1;
+    SB_CUDA(ctx, cudaGraphAddNode(&n_while, G->graph, &n_init, 1, &wp));
+    cudaGraph_t body = wp.conditional.phGraph_out[0];
+    {
+        void* args[] = {&job, &zero};
+        SB_TRY(add_kernel(ctx, body, &n_iter, nullptr, (void*)k_icp_iter, G->iter_grid, IWARPS * 32, args));
+    }
+    {
+        void* args[] = {&job, &zero, &cond, &one};
+        SB_TRY(add_kernel(ctx, body, &n_solve, &n_iter, (void*)k_icp_solve, G->solve_grid, 256, args));
+    }
+    {
+        void* args[] = {&job, &one};
+        SB_TRY(add_kernel(ctx, G->graph, &n_fiter, &n_while, (void*)k_icp_iter, G->iter_grid, IWARPS * 32, args));
+    }
+    {
+        void* args[] = {&job, &one, &cond, &zero};
+        SB_TRY(add_kernel(ctx, G->graph, &n_final, &n_fiter, (void*)k_icp_solve, G->solve_grid, 256, args));
+    }
+    SB_CUDA(ctx, cudaGraphInstantiate(&G->exec, G->graph, 0));
+    return SB_OK;
+}
+
+int icp_batch(Ctx* ctx, const Forest* f, const double* d_src, const std::vector<PairDesc>& pairs_in,
+              const sb_icp_config* cfg, sb_icp_result* results) {
+    const int n_pairs = (int)pairs_in.size();
+    if (n_pairs == 0) return SB_OK;
+    if (cfg->max_iterations < 0 || cfg->max_iterations > SB_MAX_ICP_ITERATIONS)
+        return fail(ctx, SB_ERR_INVALID_ARG, "icp: max_iterations %d outside [0, %d]", cfg->max_iterations,
+                    SB_MAX_ICP_ITERATIONS);
+    if (!f->normals) return fail(ctx, SB_ERR_INVALID_ARG, "icp: forest has no normals");
+    IcpGraph* G;
+    SB_TRY(icp_graph_get(ctx, &G));
+    std::vector<PairDesc> pairs(pairs_in);
+    std::vector<QueryItem> items;
+    int n_valid = 0;
+    for (int p = 0; p < n_pairs; ++p) {
+        PairDesc& P = pairs[p];
+        P.item_off = (i64)items.size();
+        for (int s = 0; s < P.n_src; s += 32) {
+            QueryItem I;
+            I.q_off = P.src_off + s;
+            I.count = P.n_src - s < 32 ? P.n_src - s : 32;
+            I.tree = p;
+            items.push_back(I);
+        }
+        P.n_items = (int)((i64)items.size() - P.item_off);
+        if (P.n_src > 0 && f->h_trees[P.tree].n > 0) ++n_valid;
+    }
+    PairDesc* d_pairs;
+    QueryItem* d_items;
+    sb_icp_result* d_res;
+    PairState* d_state;
+    double* d_part;
+    SB_TRY(arena_get(ctx, (size_t)n_pairs, &d_pairs));
+    SB_TRY(arena_get(ctx, items.size() ? items.size() : 1, &d_items));
+    SB_TRY(arena_get(ctx, (size_t)n_pairs, &d_res));
+    SB_TRY(arena_get(ctx, (size_t)n_pairs, &d_state));
+    SB_TRY(arena_get(ctx, (items.size() ? items.size() : 1) * NSUM, &d_part));
+    SB_CUDA(ctx, cudaMemcpyAsync(d_pairs, pairs.data(), sizeof(PairDesc) * n_pairs, cudaMemcpyHostToDevice, ctx->stream));
+    if (!items.empty())
+        SB_CUDA(ctx, cudaMemcpyAsync(d_items, items.data(), sizeof(QueryItem) * items.size(), cudaMemcpyHostToDevice, ctx->stream));
+    IcpJob job;
+    memset(&job, 0, sizeof(job));
+    job.F.sx = f->sx; job.F.sy = f->sy; job.F.sz = f->sz; job.F.sidx = f->sidx; job.F.boxes = f->boxes;
+    job.F.trees = f->d_trees;
+    job.normals = f->normals;
+    job.src = d_src;
+    job.items = d_items;
+    job.n_items = (i64)items.size();
+    job.pairs = d_pairs;
+    job.results = d_res;
+    job.state = d_state;
+    job.partials = d_part;
+    memcpy(job.T0, cfg->initial_transform, sizeof(job.T0));
+    job.tol = cfg->tolerance;
+    job.min_err = cfg->min_error;
+    job.n_pairs = n_pairs;
+    job.max_it = cfg->max_iterations;
+    job.n_active = cfg->max_iterations > 0 ? n_valid : 0;
+    job.ticket = 0;
+    SB_CUDA(ctx, cudaMemcpyAsync(G->d_job, &job, sizeof(job), cudaMemcpyHostToDevice, ctx->stream));
+    if (G->exec) {
+        SB_CUDA(ctx, cudaGraphLaunch(G->exec, ctx->stream));
+    } else {  // debugging path (SB_ICP_NOGRAPH=1): same kernels, host-driven loop
+        cudaGraphConditionalHandle none = 0;
+        SB_LAUNCH(ctx, k_icp_init, ctx->sm_count, 256, 0, G->d_job, none, 0);
+        for (int it = 0; it < cfg->max_iterations; ++it) {
+            SB_LAUNCH(ctx, k_icp_iter, G->iter_grid, IWARPS * 32, 0, G->d_job, 0);
+            SB_LAUNCH(ctx, k_icp_solve, G->solve_grid, 256, 0, G->d_job, 0, none, 0);
+            if ((it & 3) == 3) {
+                int active = 0;
+                SB_CUDA(ctx, cudaMemcpyAsync(&active, &G->d_job->n_active, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+                SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                if (active <= 0) break;
+            }
+        }
+        SB_LAUNCH(ctx, k_icp_iter, G->iter_grid, IWARPS * 32, 0, G->d_job, 1);
+        SB_LAUNCH(ctx, k_icp_solve, G->solve_grid, 256, 0, G->d_job, 1, none, 0);
+    }
+    SB_CUDA(ctx, cudaMemcpyAsync(results, d_res, sizeof(sb_icp_result) * n_pairs, cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (G->exec) {
+        int max_hist = 1;
+        for (int p = 0; p < n_pairs; ++p)
+            if (results[p].history_len > max_hist) max_hist = results[p].history_len;
+        ctx->launches += 3 + 2 * (i64)(max_hist - 1);
+    }
+    {
+        int max_hist = 1;
+        for (int p = 0; p < n_pairs; ++p)
+            if (results[p].history_len > max_hist) max_hist = results[p].history_len;
+        ctx->last_icp_iterations = max_hist;
+    }
+    return SB_OK;
+}
+
+}  // namespace sb

@@ -1,0 +1,141 @@
+// loop.cu — device-resident loop-closure database; replaces slam::LoopClosureDetector
+// (slam_viz/include/slam_viz/core/loop_closure.hpp:41-149).
+//
+// The reference keeps a vector of Eigen descriptors plus a full copy of every cloud on the host and scans it
+// linearly (loop_closure.hpp:78-89), then verifies candidates one by one with ICP (:95-122).  Here descriptors
+// and clouds live in two growing device pools; the Scan Context search is one kernel over the whole database and
+// the ICP verifications of a chunk of candidates run as ONE batch (they are independent); acceptance then walks the
+// candidates in the reference's (distance, entry) order so the accepted set is the same as the sequential loop's.
+// With world > 1, entry i is owned by rank i % world; every rank also keeps the newest entry (the query).
+#include "common.cuh"
+
+#include <algorithm>
+
+namespace sb {
+
+static int grow(Ctx* ctx, double** buf, size_t* cap, size_t need, size_t used, size_t unit) {
+    if (need <= *cap) return SB_OK;
+    size_t ncap = *cap ? *cap : 256;
+    while (ncap < need) ncap *= 2;
+    double* nb;
+    SB_CUDA(ctx, cudaMalloc(&nb, ncap * unit * sizeof(double)));
+    if (used) SB_CUDA(ctx, cudaMemcpyAsync(nb, *buf, used * unit * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(*buf);
+    *buf = nb;
+    *cap = ncap;
+    return SB_OK;
+}
+
+int loop_add(sb_loop* L, const double* xyz, i64 n, int frame_idx, const double* desc) {
+    Ctx* ctx = L->ctx;
+    // drop a guest (non-owned former query) before appending
+    if (L->last_is_guest) {
+        L->entry_id.pop_back();
+        L->frame_idx.pop_back();
+        L->cloud_off.pop_back();
+        L->last_is_guest = false;
+    }
+    int id = L->n_global++;
+    size_t slots = L->entry_id.size();
+    i64 rows = L->cloud_off.empty() ? 0 : L->cloud_off.back();
+    if (L->cloud_off.empty()) L->cloud_off.push_back(0);
+    SB_TRY(grow(ctx, &L->d_desc, &L->desc_cap, slots + 1, slots, SB_SC_SIZE));
+    SB_TRY(grow(ctx, &L->d_clouds, &L->cloud_cap, (size_t)(rows + n), (size_t)rows, 3));
+    if (n > 0)
+        SB_CUDA(ctx, cudaMemcpyAsync(L->d_clouds + 3 * rows, xyz, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, ctx->stream));
+    double* d_slot = L->d_desc + slots * SB_SC_SIZE;
+    if (desc) {
+        SB_CUDA(ctx, cudaMemcpyAsync(d_slot, desc, sizeof(double) * SB_SC_SIZE, cudaMemcpyHostToDevice, ctx->stream));
+    } else {  // ScanContext sc(points), loop_closure.hpp:55
+        i64* d_off;
+        SB_TRY(arena_get(ctx, 2, &d_off));
+        i64 h[2] = {rows, rows + n};
+        SB_CUDA(ctx, cudaMemcpyAsync(d_off, h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
+        SB_TRY(sc_compute_dev(ctx, L->d_clouds, d_off, 1, d_slot));
+    }
+    SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    L->entry_id.push_back(id);
+    L->frame_idx.push_back(frame_idx);
+    L->cloud_off.push_back(rows + n);
+    L->last_frame = frame_idx;
+    L->last_is_guest = (id % L->world) != L->rank;
+    return SB_OK;
+}
+
+// loop_closure.hpp:75-92 restricted to the entries this rank owns
+int loop_candidates(sb_loop* L, std::vector<std::pair<double, int>>& cand) {
+    Ctx* ctx = L->ctx;
+    cand.clear();
+    if (L->n_global < 2) return SB_OK;  // loop_closure.hpp:69
+    int slots = (int)L->entry_id.size();
+    int n_db = slots - 1;  // the newest entry (the query) is always the last slot
+    if (n_db <= 0) return SB_OK;
+    double* d_out;
+    SB_TRY(arena_get(ctx, (size_t)n_db, &d_out));
+    SB_TRY(sc_distance_dev(ctx, L->d_desc + (size_t)(slots - 1) * SB_SC_SIZE, L->d_desc, n_db, d_out));
+    std::vector<double> dist((size_t)n_db);
+    SB_CUDA(ctx, cudaMemcpyAsync(dist.data(), d_out, sizeof(double) * n_db, cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < n_db; ++i) {
+        if (L->last_frame - L->frame_idx[i] < L->cfg.frame_gap) continue;            // loop_closure.hpp:79-81
+        if (dist[i] < L->cfg.sc_distance_threshold) cand.push_back({dist[i], L->entry_id[i]});  // :86-88
+    }
+    std::sort(cand.begin(), cand.end());  // loop_closure.hpp:92: (distance, entry) ascending
+    return SB_OK;
+}
+
+static int slot_of(const sb_loop* L, int entry) {
+    // owned entries are stored in ascending id order: entry = rank + slot * world
+    int slot = (entry - L->rank) / L->world;
+    if (entry % L->world != L->rank || slot < 0 || slot >= (int)L->entry_id.size() || L->entry_id[slot] != entry) return -1;
+    return slot;
+}
+
+// loop_closure.hpp:99-109 for a set of entries at once
+int loop_verify(sb_loop* L, const int* entries, const double* dist, int n, sb_loop_result* results, int* converged) {
+    Ctx* ctx = L->ctx;
+    if (n <= 0) return SB_OK;
+    int qslot = (int)L->entry_id.size() - 1;
+    if (qslot < 0) return fail(ctx, SB_ERR_EMPTY, "loop: empty database");
+    std::vector<int> slots((size_t)n);
+    for (int i = 0; i < n; ++i) {
+        slots[i] = slot_of(L, entries[i]);
+        if (slots[i] < 0 || slots[i] == qslot)
+            return fail(ctx, SB_ERR_INVALID_ARG, "loop: entry %d is not owned by rank %d", entries[i], L->rank);
+    }
+    Forest F;
+    int s = forest_build(ctx, L->d_clouds, L->cloud_off.data(), slots.data(), n, &F);
+    if (s == SB_OK) s = forest_normals(ctx, &F, L->cfg.normals_k, nullptr, nullptr);
+    std::vector<sb_icp_result> res((size_t)n);
+    if (s == SB_OK) {
+        sb_icp_config cfg;
+        sb_default_icp_config(&cfg);
+        cfg.max_iterations = L->cfg.icp_max_iterations;  // loop_closure.hpp:106
+        cfg.tolerance = L->cfg.icp_tolerance;            // loop_closure.hpp:107
+        cfg.normals_k = L->cfg.normals_k;
+        std::vector<PairDesc> pairs((size_t)n);
+        for (int i = 0; i < n; ++i) {
+            pairs[i].src_off = L->cloud_off[qslot];  // source = query cloud (loop_closure.hpp:102)
+            pairs[i].n_src = (int)(L->cloud_off[qslot + 1] - L->cloud_off[qslot]);
+            pairs[i].tree = i;                       // target = candidate cloud (loop_closure.hpp:103)
+            pairs[i].item_off = 0; pairs[i].n_items = 0; pairs[i].pad = 0;
+        }
+        s = icp_batch(ctx, &F, L->d_clouds, pairs, &cfg, res.data());
+    }
+    cudaStreamSynchronize(ctx->stream);
+    forest_free(&F);
+    if (s != SB_OK) return s;
+    for (int i = 0; i < n; ++i) {
+        sb_loop_result& R = results[i];
+        R.query_frame = L->last_frame;
+        R.match_frame = L->frame_idx[slots[i]];
+        memcpy(R.transform, res[i].transformation, sizeof(R.transform));
+        R.scan_context_distance = dist ? dist[i] : 0.0;
+        R.icp_fitness = res[i].final_error;
+        converged[i] = res[i].converged && res[i].status == SB_OK;
+    }
+    return SB_OK;
+}
+
+}  // namespace sb

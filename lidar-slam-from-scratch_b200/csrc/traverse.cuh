@@ -1,0 +1,187 @@
+// traverse.cuh — warp-cooperative exact nearest-neighbour traversal of the forest (forest.cu, icp.cu).
+//
+// Replaces the recursive KD-tree searches of the reference (slam_viz/include/slam_viz/core/kdtree.hpp:112-142
+// search_nearest and :144-180 search_k_nearest).  The index of one cloud is an implicit 32-ary tree of axis-aligned
+// boxes over the Morton-sorted points: level-0 box b bounds sorted points [32b, 32b+32), level-l box b bounds the
+// level-(l-1) boxes [32b, 32b+32).  One warp answers one query: the 32 lanes test the 32 children of a node (one
+// coalesced 768-byte load), descend nearest-box-first, and evaluate the 32 points of a leaf with one coalesced
+// load per coordinate.  A subtree is skipped only if a conservative lower bound of its squared distance is
+// strictly greater than the current k-th best, so the result is exact for any density and any radius.
+//
+// Distances are the oracle's (dx*dx + dy*dy) + dz*dz in fp64 without FMA; candidates are ranked by
+// (d2, original index) lexicographically.
+#pragma once
+#include "common.cuh"
+
+namespace sb {
+
+struct WarpStack {                       // shared memory, one per warp
+    float dm[SB_MAX_LEVELS][32];         // lower-bound d^2 of "my" child at each level
+    unsigned mask[SB_MAX_LEVELS];        // children still to visit at each level (warp-uniform)
+    int base[SB_MAX_LEVELS];             // first child index at each level (warp-uniform)
+};
+
+struct ForestView {
+    const double* __restrict__ sx;
+    const double* __restrict__ sy;
+    const double* __restrict__ sz;
+    const int* __restrict__ sidx;
+    const float* __restrict__ boxes;
+    const TreeDesc* __restrict__ trees;
+};
+
+__device__ __forceinline__ bool lex_less(double da, int ia, double db, int ib) {
+    return da < db || (da == db && ia < ib);
+}
+
+// Tests the (up to 32) boxes [first, first+32) of `level` against the query; records the survivors.
+__device__ __forceinline__ void test_children(const ForestView& F, const TreeDesc& T, int level, int first,
+                                              double qx, double qy, double qz, double tau, WarpStack& S, int lane) {
+    int ci = first + lane;
+    bool valid = ci < T.box_cnt[level];
+    float dmf = __int_as_float(0x7f800000);
+    if (valid) {
+        const float2* b = reinterpret_cast<const float2*>(F.boxes + 6 * (T.box_off[level] + ci));
+        float2 b0 = b[0], b1 = b[1], b2 = b[2];  // lo.x lo.y | lo.z hi.x | hi.y hi.z
+        double ex = fmax(fmax((double)b0.x - qx, qx - (double)b1.y), 0.0);
+        double ey = fmax(fmax((double)b0.y - qy, qy - (double)b2.x), 0.0);
+        double ez = fmax(fmax((double)b1.x - qz, qz - (double)b2.y), 0.0);
+        double d = (ex * ex + ey * ey) + ez * ez;
+        // conservative: shave a few ulps, then round towards -inf into a float
+        dmf = __double2float_rd(d * (1.0 - 1.0e-14));
+    }
+    bool pass = valid && !((double)dmf > tau);
+    unsigned m = __ballot_sync(0xffffffffu, pass);
+    S.dm[level][lane] = dmf;
+    S.mask[level] = m;   // every lane writes the same value; each lane only ever reads back what the warp wrote
+    S.base[level] = first;
+}
+
+// Generic nearest-first traversal.  V must provide:
+//   double tau() const            — current pruning bound (k-th best d2; +inf/DBL_MAX while the list is not full)
+//   void leaf(int p0, int cnt)    — visit sorted points [p0, p0+cnt) (absolute indices into the SoA arrays)
+template <class Visitor>
+__device__ __forceinline__ void traverse(const ForestView& F, const TreeDesc& T, double qx, double qy, double qz,
+                                         WarpStack& S, Visitor& V, int lane) {
+    if (T.n <= 0) return;
+    int level = T.top;
+    test_children(F, T, level, 0, qx, qy, qz, V.tau(), S, lane);
+    while (true) {
+        unsigned m = S.mask[level];
+        if (m == 0u) {
+            if (level == T.top) break;
+            ++level;
+            continue;
+        }
+        bool mine = (m >> lane) & 1u;
+        unsigned key = mine ? __float_as_uint(S.dm[level][lane]) : 0xffffffffu;  // non-negative floats order as uints
+        unsigned kmin = __reduce_min_sync(0xffffffffu, key);
+        if ((double)__uint_as_float(kmin) > V.tau()) {  // the nearest remaining child is too far: so are the rest
+            S.mask[level] = 0u;
+            continue;
+        }
+        int c = __ffs(__ballot_sync(0xffffffffu, mine && key == kmin)) - 1;
+        S.mask[level] = m & ~(1u << c);
+        int node = S.base[level] + c;
+        if (level == 0) {
+            int p0 = node * 32;
+            int cnt = T.n - p0;
+            V.leaf(p0, cnt > 32 ? 32 : cnt);
+        } else {
+            --level;
+            test_children(F, T, level, node * 32, qx, qy, qz, V.tau(), S, lane);
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// 1-NN visitor
+// -------------------------------------------------------------------------------------------------------------
+struct NearestVisitor {
+    const ForestView& F;
+    const TreeDesc& T;
+    double qx, qy, qz;
+    int lane;
+    double best_d;   // warp-uniform
+    int best_idx;    // original (cloud-local) row, -1 if none
+    int best_pos;    // cloud-local sorted position
+    __device__ NearestVisitor(const ForestView& f, const TreeDesc& t, double x, double y, double z, int l)
+        : F(f), T(t), qx(x), qy(y), qz(z), lane(l), best_d(1.7976931348623157e308), best_idx(-1), best_pos(-1) {}
+    __device__ __forceinline__ double tau() const { return best_d; }
+    __device__ __forceinline__ void leaf(int p0, int cnt) {
+        bool valid = lane < cnt;
+        unsigned hi = 0xffffffffu, lo = 0xffffffffu;
+        int idx = 0x7fffffff;
+        if (valid) {
+            i64 p = T.pt_off + p0 + lane;
+            double d = dist2_rn(F.sx[p], F.sy[p], F.sz[p], qx, qy, qz);
+            idx = F.sidx[p];
+            if (d == d) {  // NaN never wins (kdtree.hpp:125 strict <)
+                long long b = __double_as_longlong(d);
+                hi = (unsigned)((unsigned long long)b >> 32);
+                lo = (unsigned)b;
+            }
+        }
+        unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+        if (mh == 0xffffffffu) return;
+        unsigned lo2 = hi == mh ? lo : 0xffffffffu;
+        unsigned ml = __reduce_min_sync(0xffffffffu, lo2);
+        bool tie = hi == mh && lo == ml;
+        unsigned mi = __reduce_min_sync(0xffffffffu, tie ? (unsigned)idx : 0xffffffffu);
+        int src = __ffs(__ballot_sync(0xffffffffu, tie && (unsigned)idx == mi)) - 1;
+        double d = __longlong_as_double((long long)(((unsigned long long)mh << 32) | ml));
+        if (d < best_d || (d == best_d && (int)mi < best_idx)) {  // kdtree.hpp:125 + canonical tie rule
+            best_d = d;
+            best_idx = (int)mi;
+            best_pos = p0 + src;
+        }
+    }
+};
+
+// -------------------------------------------------------------------------------------------------------------
+// k-NN visitor (k <= 32): lane j holds the j-th best (d2, idx, pos), ascending
+// -------------------------------------------------------------------------------------------------------------
+struct KnnVisitor {
+    const ForestView& F;
+    const TreeDesc& T;
+    double qx, qy, qz;
+    int lane, k;
+    double ld;       // this lane's entry
+    int lidx, lpos;
+    double tau_d;    // entry k-1 (warp-uniform)
+    int tau_idx;
+    __device__ KnnVisitor(const ForestView& f, const TreeDesc& t, double x, double y, double z, int l, int kk)
+        : F(f), T(t), qx(x), qy(y), qz(z), lane(l), k(kk), ld((double)INFINITY),
+          lidx(0x7fffffff), lpos(-1), tau_d((double)INFINITY), tau_idx(0x7fffffff) {}
+    __device__ __forceinline__ double tau() const { return tau_d; }
+    __device__ __forceinline__ void leaf(int p0, int cnt) {
+        bool valid = lane < cnt;
+        double cd = 0.0;
+        int cidx = 0x7fffffff;
+        if (valid) {
+            i64 p = T.pt_off + p0 + lane;
+            cd = dist2_rn(F.sx[p], F.sy[p], F.sz[p], qx, qy, qz);
+            cidx = F.sidx[p];
+        }
+        bool want = valid && lex_less(cd, cidx, tau_d, tau_idx);  // NaN compares false: never inserted
+        unsigned cm = __ballot_sync(0xffffffffu, want);
+        while (cm) {
+            int b = __ffs(cm) - 1;
+            cm &= cm - 1u;
+            double bd = shfl_d(cd, b);
+            int bi = __shfl_sync(0xffffffffu, cidx, b);
+            if (!lex_less(bd, bi, tau_d, tau_idx)) continue;  // warp-uniform: the bound moved past it
+            int bp = p0 + b;
+            int pos = __popc(__ballot_sync(0xffffffffu, lex_less(ld, lidx, bd, bi)));  // sorted: a prefix
+            double ud = __shfl_up_sync(0xffffffffu, ld, 1);
+            int ui = __shfl_up_sync(0xffffffffu, lidx, 1);
+            int up = __shfl_up_sync(0xffffffffu, lpos, 1);
+            if (lane > pos) { ld = ud; lidx = ui; lpos = up; }
+            else if (lane == pos) { ld = bd; lidx = bi; lpos = bp; }
+            tau_d = shfl_d(ld, k - 1);
+            tau_idx = __shfl_sync(0xffffffffu, lidx, k - 1);
+        }
+    }
+};
+
+}  // namespace sb

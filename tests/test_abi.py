@@ -1,0 +1,81 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads, exports every symbol include/slam_b200.h declares,
+the ctypes mirror has the C layout, and the library refuses to work without a GPU (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+import subprocess
+import tempfile
+
+import pytest
+
+import oracle_lib  # noqa: F401  (sys.path)
+import slam_b200
+
+ROOT = oracle_lib.ROOT
+HEADER = os.path.join(ROOT, "include", "slam_b200.h")
+LIB = os.path.join(ROOT, "lidar-slam-from-scratch_b200", "libslam_b200.so")
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(sb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_built():
+    assert os.path.exists(LIB), "run `make -C lidar-slam-from-scratch_b200` (or __graft_entry__.build())"
+
+
+def test_exports_every_declared_symbol():
+    lib = C.CDLL(LIB)
+    names = declared_symbols()
+    assert len(names) >= 35
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/slam_b200.h but not exported"
+    assert set(names) == set(slam_b200.SYMBOLS), set(names) ^ set(slam_b200.SYMBOLS)
+
+
+def test_ctypes_layout_matches_header():
+    prog = r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "slam_b200.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(sb_icp_config), sizeof(sb_icp_result), sizeof(sb_loop_config),
+         sizeof(sb_loop_result), offsetof(sb_icp_result, error_history), offsetof(sb_loop_config, icp_tolerance),
+         offsetof(sb_loop_result, transform));
+  return 0; }
+'''
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "t.c")
+        open(src, "w").write(prog)
+        exe = os.path.join(d, "t")
+        subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), src, "-o", exe])
+        got = [int(x) for x in subprocess.check_output([exe]).split()]
+    want = [C.sizeof(slam_b200.ICPConfigC), C.sizeof(slam_b200.ICPResultC), C.sizeof(slam_b200.LoopConfigC),
+            C.sizeof(slam_b200.LoopResultC), slam_b200.ICPResultC.error_history.offset,
+            slam_b200.LoopConfigC.icp_tolerance.offset, slam_b200.LoopResultC.transform.offset]
+    assert got == want
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib = slam_b200.load_library()
+    assert lib.sb_version().decode().startswith("slam_b200")
+    with pytest.raises(slam_b200.SlamB200Error) as e:
+        slam_b200.Engine(0)
+    assert e.value.status == 4  # SB_ERR_NO_DEVICE
+
+
+def test_defaults_match_reference():
+    lib = slam_b200.load_library()
+    cfg = slam_b200.ICPConfigC()
+    lib.sb_default_icp_config(C.byref(cfg))
+    assert (cfg.max_iterations, cfg.tolerance, cfg.min_error, cfg.normals_k) == (50, 1e-6, 1e-9, 20)  # types.hpp:143-148
+    assert list(cfg.initial_transform) == [1.0 if i % 5 == 0 else 0.0 for i in range(16)]
+    lc = slam_b200.LoopConfigC()
+    lib.sb_default_loop_config(C.byref(lc))
+    assert (lc.frame_gap, lc.sc_distance_threshold, lc.icp_fitness_threshold, lc.max_candidates) == (50, 0.25, 0.3, 3)
+    assert (lc.icp_max_iterations, lc.icp_tolerance) == (30, 1e-6)  # loop_closure.hpp:106-107

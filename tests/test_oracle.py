@@ -1,0 +1,285 @@
+"""CPU tests of the oracle (oracle/slam_oracle.cpp) against INDEPENDENT implementations.
+
+The reference ships no tests or golden vectors and cannot be built here (Eigen absent), so the oracle is pinned
+against brute force, numpy and scipy, against analytic cases, and against the committed fixtures in tests/golden/
+(produced by tests/golden/make_golden.py, a pure-numpy restatement that shares no code with the C++ oracle).
+"""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+# ------------------------------------------------------------------ voxel grid (file_utils.cpp:148-196)
+def np_voxel(pts, voxel):
+    keys = np.floor(pts / voxel).astype(np.int64)
+    order = np.lexsort((keys[:, 2], keys[:, 1], keys[:, 0]))  # stable: ascending input index inside a voxel
+    ks = keys[order]
+    starts = np.r_[0, np.nonzero(np.any(ks[1:] != ks[:-1], axis=1))[0] + 1, len(ks)]
+    out = np.empty((len(starts) - 1, 3))
+    for v in range(len(starts) - 1):
+        acc = np.zeros(3)
+        for i in order[starts[v]:starts[v + 1]]:
+            acc = acc + pts[i]
+        out[v] = acc / float(starts[v + 1] - starts[v])
+    return out, ks[starts[:-1]]
+
+
+def test_voxel_matches_numpy(oracle):
+    rng = np.random.default_rng(3)
+    pts = np.round(rng.uniform(-20, 20, (3000, 3)).astype(np.float32), 3).astype(np.float64)
+    out, keys = oracle.voxel_downsample(pts, 0.5)
+    ref, rkeys = np_voxel(pts, 0.5)
+    assert np.array_equal(keys, rkeys)
+    assert np.array_equal(out, ref)  # same summation order -> bit-identical
+
+
+def test_voxel_true_division_and_negative(oracle):
+    pts = np.array([[0.6, -0.6, 0.0], [0.6000000000000001, -0.2, 1e-300], [-1e-300, 0.2, -0.0]])
+    _, keys = oracle.voxel_downsample(pts, 0.2)
+    # 0.6/0.2 == 2.9999999999999996 -> 2 (0.6*5.0 would give 3); -1e-300/0.2 floors to -1
+    assert sorted(map(tuple, keys.tolist())) == sorted([(2, -3, 0), (3, -1, 0), (-1, 1, 0)])
+
+
+def test_voxel_nonpositive_returns_input(oracle):
+    pts = np.arange(12, dtype=np.float64).reshape(4, 3)
+    out, _ = oracle.voxel_downsample(pts, 0.0)
+    assert np.array_equal(out, pts)
+    out, _ = oracle.voxel_downsample(pts, -1.0)
+    assert np.array_equal(out, pts)
+
+
+# ------------------------------------------------------------------ KD-tree (kdtree.hpp)
+def cloud(rng, n, kind):
+    if kind == "uniform":
+        return rng.uniform(-10, 10, (n, 3))
+    if kind == "lattice":  # many exact distance ties
+        g = rng.integers(-4, 5, (n, 3)).astype(np.float64)
+        return g * 0.5
+    if kind == "dups":
+        base = rng.uniform(-5, 5, (n // 4 + 1, 3))
+        return base[rng.integers(0, len(base), n)]
+    if kind == "collinear":
+        t = rng.uniform(-10, 10, n)
+        return np.stack([t, 2 * t, np.zeros(n)], axis=1)
+    raise ValueError(kind)
+
+
+@pytest.mark.parametrize("kind", ["uniform", "lattice", "dups", "collinear"])
+def test_kdtree_equals_bruteforce(oracle, kind):
+    rng = np.random.default_rng(11)
+    pts = cloud(rng, 700, kind)
+    q = np.vstack([pts[:100], cloud(rng, 100, kind) + 0.25])
+    tree = oracle.tree(pts)
+    for k in (1, 5, 20):
+        ti, td = tree.k_nearest_batch(q, k)
+        bi, bd = oracle.brute_knn(pts, q, k)
+        assert np.array_equal(ti, bi), f"{kind} k={k}"
+        assert np.array_equal(td, bd)
+    ni, nd = tree.nearest_batch(q)
+    bi, bd = oracle.brute_knn(pts, q, 1)
+    assert np.array_equal(ni, bi[:, 0]) and np.array_equal(nd, bd[:, 0])
+
+
+def test_kdtree_small_and_k_larger_than_n(oracle):
+    pts = np.array([[0, 0, 0], [1, 0, 0.0]])
+    idx, d2 = oracle.tree(pts).k_nearest_batch(np.array([[0.1, 0, 0]]), 5)
+    assert idx.tolist() == [[0, 1, -1, -1, -1]]
+    assert d2[0, 2] == np.finfo(np.float64).max
+
+
+def test_kdtree_vs_scipy(oracle):
+    scipy_spatial = pytest.importorskip("scipy.spatial")
+    rng = np.random.default_rng(5)
+    pts = rng.normal(0, 5, (2000, 3))
+    q = rng.normal(0, 5, (300, 3))
+    d, i = scipy_spatial.cKDTree(pts).query(q, k=10)
+    ti, td = oracle.tree(pts).k_nearest_batch(q, 10)
+    assert np.array_equal(ti, i)  # random data: no ties
+    assert np.allclose(np.sqrt(td), d, rtol=1e-12)
+
+
+# ------------------------------------------------------------------ normals / small solvers
+def test_jacobi_vs_eigh(oracle):
+    rng = np.random.default_rng(2)
+    for _ in range(200):
+        M = rng.normal(size=(3, 3))
+        A = M @ M.T
+        w, V = oracle.jacobi3(A)
+        ew, _ = np.linalg.eigh(A)
+        assert np.allclose(np.sort(w), ew, rtol=1e-12, atol=1e-14)
+        for c in range(3):
+            v = V[:, c]
+            assert np.allclose(A @ v, w[c] * v, atol=1e-12 * max(1.0, abs(ew[-1])))
+
+
+def test_normals_vs_numpy(oracle, small_pair):
+    pts = small_pair["a"]
+    tree = oracle.tree(pts)
+    nrm, ev = tree.estimate_normals(20)
+    idx, _ = tree.k_nearest_batch(pts, 20)
+    rng = np.random.default_rng(0)
+    checked = 0
+    for i in rng.choice(len(pts), 400, replace=False):
+        nb = pts[idx[i]]
+        c = nb.mean(axis=0)
+        Cm = (nb - c).T @ (nb - c) / 20.0
+        w, V = np.linalg.eigh(Cm)
+        assert np.allclose(ev[i], w, rtol=1e-9, atol=1e-12)
+        if (w[1] - w[0]) / max(w[2], 1e-300) < 1e-2:
+            continue  # numerically arbitrary direction
+        v = V[:, 0] * (1.0 if V[2, 0] >= 0 else -1.0)
+        assert np.max(np.abs(v - nrm[i])) < 1e-6
+        checked += 1
+    assert checked > 300
+    assert np.allclose(np.linalg.norm(nrm, axis=1), 1.0, atol=1e-12)
+    assert np.all(nrm[:, 2] >= 0)
+
+
+def test_normals_fewer_than_three_neighbours(oracle):
+    nrm, _ = oracle.tree(np.array([[0, 0, 0], [1, 1, 1.0]])).estimate_normals(20)
+    assert np.array_equal(nrm, np.array([[0, 0, 1], [0, 0, 1.0]]))
+
+
+def test_ldlt_vs_numpy(oracle):
+    rng = np.random.default_rng(9)
+    for _ in range(50):
+        J = rng.normal(size=(40, 6))
+        A, b = J.T @ J, rng.normal(size=6)
+        assert np.allclose(oracle.ldlt6_solve(A, b), np.linalg.solve(A, b), rtol=1e-9, atol=1e-12)
+
+
+def se3(rx, ry, rz, t):
+    cx, sx, cy, sy, cz, sz = np.cos(rx), np.sin(rx), np.cos(ry), np.sin(ry), np.cos(rz), np.sin(rz)
+    Rx = np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]])
+    Ry = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+    Rz = np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]])
+    T = np.eye(4)
+    T[:3, :3] = Rz @ Ry @ Rx
+    T[:3, 3] = t
+    return T
+
+
+def test_solve_point_to_plane_vs_numpy(oracle):
+    rng = np.random.default_rng(4)
+    src = rng.normal(0, 3, (500, 3))
+    nrm = rng.normal(size=(500, 3))
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    T = se3(0.01, -0.02, 0.015, [0.05, -0.03, 0.02])
+    tgt = src @ T[:3, :3].T + T[:3, 3]
+    J = np.hstack([np.cross(src, nrm), nrm])
+    b = np.einsum("ij,ij->i", tgt - src, nrm)
+    x = np.linalg.solve(J.T @ J, J.T @ b)
+    got = oracle.solve_point_to_plane(src, tgt, nrm)
+    assert np.allclose(got[:3, 3], x[3:], atol=1e-12)
+    th = np.linalg.norm(x[:3])
+    K = np.array([[0, -x[2], x[1]], [x[2], 0, -x[0]], [-x[1], x[0], 0]]) / th
+    R = np.eye(3) + np.sin(th) * K + (1 - np.cos(th)) * K @ K
+    assert np.allclose(got[:3, :3], R, atol=1e-12)
+
+
+# ------------------------------------------------------------------ ICP (icp.hpp:157-258)
+def test_icp_recovers_known_transform(oracle, small_pair):
+    tgt = small_pair["a"]
+    T = se3(0.004, -0.003, 0.01, [0.15, -0.08, 0.02])
+    src = (tgt - T[:3, 3]) @ T[:3, :3]  # src = T^-1 tgt, so ICP should return ~T
+    r = oracle.icp_point_to_plane(src, tgt, max_iterations=50, tolerance=1e-12)
+    assert np.allclose(r["transformation"], T, atol=5e-5)
+    assert r["final_error"] < 1e-4
+    assert r["num_iterations"] == len(r["error_history"]) - 1
+
+
+def test_icp_history_semantics(oracle, small_pair):
+    r = oracle.icp_point_to_plane(small_pair["b"], small_pair["a"])
+    assert r["converged"]
+    h = r["error_history"]
+    assert h[-1] == h[-2] == r["final_error"]  # break -> final pass repeats the last error (Appendix A.5)
+    r2 = oracle.icp_point_to_plane(small_pair["b"], small_pair["a"], max_iterations=2)
+    assert not r2["converged"] and r2["num_iterations"] == 2 and len(r2["error_history"]) == 3
+    rf = oracle.icp_point_to_plane(small_pair["b"], small_pair["a"], faithful_cost=1)
+    assert np.array_equal(rf["transformation"], r["transformation"])
+
+
+# ------------------------------------------------------------------ Scan Context (scan_context.hpp)
+def np_sc(pts):
+    d = np.full((20, 60), -np.finfo(np.float64).max)
+    for x, y, z in pts:
+        r = np.sqrt(x * x + y * y)
+        a = np.arctan2(y, x) + np.pi
+        if r > 80.0 or r < 0.1:
+            continue
+        i = min(max(int(r / (80.0 / 20)), 0), 19)
+        j = min(max(int(a / (2.0 * np.pi / 60)), 0), 59)
+        if z > d[i, j]:
+            d[i, j] = z
+    d[d < -1000] = 0.0
+    return d
+
+
+def np_sc_distance(A, B):
+    best = np.finfo(np.float64).max
+    for s in range(60):
+        Bs = np.roll(B, -s, axis=1)
+        n = np.sqrt((A * A).sum()) * np.sqrt((Bs * Bs).sum())
+        dd = 1.0 if n < 1e-10 else 1.0 - (A * Bs).sum() / n
+        best = min(best, dd)
+    return best
+
+
+def test_scan_context_vs_numpy(oracle, small_pair):
+    a, b = small_pair["a"], small_pair["b"]
+    da, db = oracle.sc_compute(a), oracle.sc_compute(b)
+    assert np.array_equal(da.reshape(60, 20).T, np_sc(a))  # column-major storage
+    assert abs(oracle.sc_distance(da, db) - np_sc_distance(np_sc(a), np_sc(b))) < 1e-12
+    assert oracle.sc_distance(da, da) < 1e-12
+    assert oracle.sc_distance(np.zeros(1200), da) == 1.0  # norm < 1e-10 rule
+
+
+def test_scan_context_shift_invariance(oracle, small_pair):
+    a = small_pair["a"]
+    th = 2 * np.pi / 60 * 7  # rotate by exactly 7 sectors
+    R = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1]])
+    d0, d1 = oracle.sc_compute(a), oracle.sc_compute(a @ R.T)
+    assert oracle.sc_distance(d0, d1) < 0.05
+
+
+# ------------------------------------------------------------------ loop closure (loop_closure.hpp)
+def test_loop_detector_semantics(oracle, synth, scene):
+    s = oracle_lib.small_sensor(16, 360)
+    det = oracle.loop(frame_gap=3, sc_thr=0.5, icp_thr=0.5, max_candidates=2)
+    poses = [(0.0, 0, 0), (1.0, 0, 0), (2.0, 0, 0), (3.0, 0, 0), (4.0, 0, 0), (5.0, 0, 0), (0.3, 0.05, 0.0)]
+    clouds = []
+    for i, p in enumerate(poses):
+        c, _ = oracle.voxel_downsample(synth.scan(s, scene, p, 20 + i), 0.5)
+        clouds.append(c)
+        det.add(c, i)
+    dist, idx = det.candidates()
+    assert np.all(np.diff(dist) >= 0)
+    assert set(idx.tolist()) <= {0, 1, 2, 3}  # frame gap 3: entries 4, 5 excluded
+    assert idx[0] == 0  # the revisit of pose 0
+    res = det.detect()
+    assert len(res) <= 2 and res[0]["match_frame"] == 0 and res[0]["query_frame"] == 6
+    assert abs(res[0]["transform"][0, 3] - 0.3) < 0.1
+
+
+# ------------------------------------------------------------------ committed golden fixtures
+def test_golden_fixtures(oracle):
+    g = np.load(os.path.join(GOLDEN, "golden_small.npz"))
+    out, keys = oracle.voxel_downsample(g["raw"], 0.5)
+    assert np.array_equal(keys, g["voxel_keys"]) and np.array_equal(out, g["voxel_xyz"])
+    tree = oracle.tree(g["voxel_xyz"])
+    idx, d2 = tree.k_nearest_batch(g["voxel_xyz"], 10)
+    assert np.array_equal(idx, g["knn_idx"]) and np.array_equal(d2, g["knn_d2"])
+    nrm, ev = tree.estimate_normals(10)
+    ok = g["normal_ok"]
+    assert np.max(np.abs(nrm[ok] - g["normals"][ok])) < 1e-6
+    assert np.array_equal(oracle.sc_compute(g["voxel_xyz"]), g["sc_desc"])
+    assert abs(oracle.sc_distance(g["sc_desc"], g["sc_desc_b"]) - float(g["sc_dist"])) < 1e-12
+    r = oracle.icp_point_to_plane(g["icp_src"], g["voxel_xyz"], max_iterations=int(g["icp_max_it"]))
+    assert np.allclose(r["transformation"], g["icp_T"], atol=1e-9)
+    assert np.allclose(r["error_history"], g["icp_history"], atol=1e-10)
+    assert r["converged"] == bool(g["icp_converged"])
