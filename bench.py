@@ -194,9 +194,7 @@ def main():
         def gather(res):
             if world_size == 1:
                 return
-            rec = np.array([np.r_[r.transformation.reshape(16), r.final_error, r.num_iterations, r.converged, r.status]
-                            for r in res])
-            t = torch.from_numpy(rec).cuda()
+            t = torch.from_numpy(res.records20()).cuda()
             out = [torch.empty_like(t) for _ in range(world_size)]
             dist.all_gather(out, t)  # NCCL: the only exchange of the sharded path
             return out
@@ -217,13 +215,15 @@ def main():
         sampler.start()
         l0 = eng.launch_count
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        stage_acc = {}
+        stage_acc, host_acc = {}, {}
         e0.record(stream)
         for _ in range(args.steps):
             res, sc = step_dev()
             gathered = gather(res)
             for k, v in eng.stage_ms().items():
                 stage_acc[k] = stage_acc.get(k, 0.0) + v
+            for k, v in eng.stage_host_ms().items():
+                host_acc[k] = host_acc.get(k, 0.0) + v
         e1.record(stream)
         barrier()
         clocks = sampler.stop()
@@ -269,7 +269,7 @@ def main():
             e2e = {"value": world_size * F / (float(t2.item()) * 1e-3), "unit": "pairs/s",
                    "h2d_bytes_per_step": int(n_raw * 24), "d2h_bytes_per_step": int(d2h),
                    "ms_per_step": float(t2.item())}
-            assert all(np.array_equal(a.transformation, b.transformation) for a, b in zip(res, r2))
+            assert np.array_equal(res.transformations, r2.transformations)
 
         if rank != 0:
             if world_size > 1:
@@ -299,7 +299,7 @@ def main():
                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                     "algorithmic_bytes_per_step": int(alg[dom]), "launches_per_step": int(launches_dom),
                     "avg_launch_ms": dom_ms / max(launches_dom, 1),
-                    "stages_ms": st,
+                    "stages_ms": st, "stages_host_ms": {k: v / args.steps for k, v in host_acc.items()},
                     "stage_frac_of_peak": {k: (alg[k] / (st[k] * 1e-3) / 1e9 / peak if st.get(k, 0) > 0 else None)
                                            for k in alg}}
 
@@ -325,7 +325,7 @@ def main():
                                   "(NN search twice per iteration); reference binary not buildable (no Eigen)",
                         "parity_max_translation_diff_m": max_dt}
 
-        iters = np.array([r.num_iterations for r in res])
+        iters = res.num_iterations
         out = {
             "metric": "ICP scan-pairs/s", "value": value, "unit": "pairs/s", "n_gpus": world_size, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_max, "higher_is_better": True, "scaling": "weak",
@@ -334,7 +334,7 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "workload_stats": {"raw_points_per_scan": n_raw / (F + 1), "voxel_points_per_scan": M / (F + 1),
                                "icp_iterations_mean": float(iters.mean()), "icp_iterations_max": int(iters.max()),
-                               "converged_frac": float(np.mean([r.converged for r in res]))},
+                               "converged_frac": float(res.converged.mean())},
         }
         print(json.dumps(out))
         if world_size > 1:

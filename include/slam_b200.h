@@ -104,6 +104,8 @@ int64_t sb_ctx_launch_count(const sb_ctx* ctx);
 #define SB_STAGE_COUNT 7
 int sb_ctx_set_profiling(sb_ctx* ctx, int enable);
 int sb_ctx_stage_ms(sb_ctx* ctx, double* ms7);
+/* host wall-clock milliseconds between the same marks (enqueue + host-side bookkeeping of each stage) */
+int sb_ctx_stage_host_ms(sb_ctx* ctx, double* ms7);
 int sb_ctx_last_counts(sb_ctx* ctx, int64_t* counts5);
 void sb_default_icp_config(sb_icp_config* cfg);
 void sb_default_loop_config(sb_loop_config* cfg);

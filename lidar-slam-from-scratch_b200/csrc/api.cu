@@ -1,6 +1,7 @@
 // api.cu — the C ABI of include/slam_b200.h: context management, host<->device staging and the glue that turns
 // each entry point into calls of the device pipelines (voxel.cu, forest.cu, icp.cu, scancontext.cu, loop.cu).
 // There is no CPU implementation of any stage behind these entry points.
+#include <chrono>
 #include <cstdarg>
 #include <algorithm>
 
@@ -72,6 +73,8 @@ void stage_mark(Ctx* ctx, int stage) {
         ctx->ev_created++;
     }
     cudaEventRecord(ctx->ev[ctx->n_ev], ctx->stream);
+    ctx->ev_host[ctx->n_ev] =
+        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
     ctx->ev_stage[ctx->n_ev] = stage;
     ctx->n_ev++;
 }
@@ -170,6 +173,7 @@ static int register_batch_impl(Ctx* ctx, const double* d_xyz, const i64* offsets
         }
     }
     Forest F;
+    F.in_arena = true;
     int s = forest_build(ctx, d_pts, off.data(), cloud_ids.data(), (int)cloud_ids.size(), &F);
     stage_mark(ctx, STAGE_NORMALS);
     if (s == SB_OK) s = forest_normals(ctx, &F, cfg->normals_k, nullptr, nullptr);
@@ -281,6 +285,17 @@ int sb_ctx_stage_ms(sb_ctx* ctx, double* ms7) {
         float ms = 0.f;
         SB_CUDA(c, cudaEventElapsedTime(&ms, c->ev[i], c->ev[i + 1]));
         ms7[st] += (double)ms;
+    }
+    return SB_OK;
+}
+
+int sb_ctx_stage_host_ms(sb_ctx* ctx, double* ms7) {
+    if (!ctx || !ms7) return SB_ERR_INVALID_ARG;
+    Ctx* c = &ctx->c;
+    for (int i = 0; i < STAGE_COUNT; ++i) ms7[i] = 0.0;
+    for (int i = 0; i + 1 < c->n_ev; ++i) {
+        int st = c->ev_stage[i];
+        if (st >= 0 && st < STAGE_COUNT) ms7[st] += c->ev_host[i + 1] - c->ev_host[i];
     }
     return SB_OK;
 }

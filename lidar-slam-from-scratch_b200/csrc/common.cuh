@@ -70,6 +70,7 @@ struct Ctx {
     bool profiling = false;
     cudaEvent_t ev[32];
     int ev_stage[32];
+    double ev_host[32];  // host steady_clock milliseconds at the same marks
     int n_ev = 0, ev_created = 0;
     i64 last_icp_iterations = 0;   // max history length of the last icp_batch (launches of k_icp_iter)
     i64 last_counts[4] = {0, 0, 0, 0};  // raw rows, downsampled rows, target rows, sum over pairs of n_src * passes
@@ -181,6 +182,7 @@ struct Forest {
     TreeDesc* d_trees = nullptr;
     std::vector<TreeDesc> h_trees;
     int normals_k = 0;
+    bool in_arena = false;  // arrays live in the context arena (valid until the next C-ABI call), not cudaMalloc
 };
 
 // Builds trees over clouds `cloud_ids[0..n_trees)` of a device CSR point set.  d_xyz rows are row-major fp64.

@@ -177,6 +177,9 @@ __global__ void __launch_bounds__(256) k_boxes_up(const TreeDesc* __restrict__ t
 // ---------------------------------------------------------------------------------------------------------------
 void forest_free(Forest* f) {
     if (!f) return;
+    if (f->in_arena) {
+        f->sx = f->sy = f->sz = nullptr; f->sidx = nullptr; f->boxes = nullptr; f->normals = nullptr; f->d_trees = nullptr;
+    }
     cudaFree(f->sx); cudaFree(f->sy); cudaFree(f->sz); cudaFree(f->sidx); cudaFree(f->boxes);
     cudaFree(f->normals); cudaFree(f->d_trees);
     f->sx = f->sy = f->sz = nullptr; f->sidx = nullptr; f->boxes = nullptr; f->normals = nullptr; f->d_trees = nullptr;
@@ -224,13 +227,23 @@ int forest_build(Ctx* ctx, const double* d_xyz, const i64* h_off, const int* clo
     f->n_points = np;
     f->n_boxes = nb;
     if (np >= (i64)0xffffffffLL) return fail(ctx, SB_ERR_RANGE, "index: more than 2^32-1 points in one forest");
-    SB_CUDA(ctx, cudaMalloc(&f->d_trees, sizeof(TreeDesc) * (size_t)(n_trees > 0 ? n_trees : 1)));
     size_t npa = (size_t)(np > 0 ? np : 1), nba = (size_t)(nb > 0 ? nb : 1);
-    SB_CUDA(ctx, cudaMalloc(&f->sx, sizeof(double) * npa));
-    SB_CUDA(ctx, cudaMalloc(&f->sy, sizeof(double) * npa));
-    SB_CUDA(ctx, cudaMalloc(&f->sz, sizeof(double) * npa));
-    SB_CUDA(ctx, cudaMalloc(&f->sidx, sizeof(int) * npa));
-    SB_CUDA(ctx, cudaMalloc(&f->boxes, sizeof(float) * 6 * nba));
+    if (f->in_arena) {
+        SB_TRY(arena_get(ctx, (size_t)(n_trees > 0 ? n_trees : 1), &f->d_trees));
+        SB_TRY(arena_get(ctx, npa, &f->sx));
+        SB_TRY(arena_get(ctx, npa, &f->sy));
+        SB_TRY(arena_get(ctx, npa, &f->sz));
+        SB_TRY(arena_get(ctx, npa, &f->sidx));
+        SB_TRY(arena_get(ctx, 6 * nba, &f->boxes));
+        SB_TRY(arena_get(ctx, 3 * npa, &f->normals));
+    } else {
+        SB_CUDA(ctx, cudaMalloc(&f->d_trees, sizeof(TreeDesc) * (size_t)(n_trees > 0 ? n_trees : 1)));
+        SB_CUDA(ctx, cudaMalloc(&f->sx, sizeof(double) * npa));
+        SB_CUDA(ctx, cudaMalloc(&f->sy, sizeof(double) * npa));
+        SB_CUDA(ctx, cudaMalloc(&f->sz, sizeof(double) * npa));
+        SB_CUDA(ctx, cudaMalloc(&f->sidx, sizeof(int) * npa));
+        SB_CUDA(ctx, cudaMalloc(&f->boxes, sizeof(float) * 6 * nba));
+    }
     SB_CUDA(ctx, cudaMemcpyAsync(f->d_trees, f->h_trees.data(), sizeof(TreeDesc) * (size_t)n_trees,
                                  cudaMemcpyHostToDevice, ctx->stream));
     if (np == 0) return SB_OK;
@@ -364,6 +377,16 @@ __device__ __forceinline__ void jacobi3(double (&A)[3][3], double (&w)[3], doubl
     w[0] = A[0][0]; w[1] = A[1][1]; w[2] = A[2][2];
 }
 
+// largest s in [0, n) with off[s] <= x (off ascending, off[0] <= x)
+__device__ __forceinline__ int find_segment(const i64* __restrict__ off, int n, i64 x) {
+    int lo = 0, hi = n;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (off[mid] <= x) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
 // MODE 0: k-NN of external queries -> out_idx/out_d2 (row-major nq x k)
 // MODE 1: normals of the trees' own points (queries are the sorted points; item.q_off is cloud-local sorted start)
 template <int MODE>
@@ -371,14 +394,25 @@ __global__ void __launch_bounds__(QWARPS * 32) k_knn(ForestView F, const double*
                                                      const QueryItem* __restrict__ items, i64 n_items, int k,
                                                      int* __restrict__ out_idx, double* __restrict__ out_d2,
                                                      double* __restrict__ nrm_sorted, double* __restrict__ nrm_orig,
-                                                     double* __restrict__ evals_orig) {
+                                                     double* __restrict__ evals_orig, int n_trees_or_zero) {
     __shared__ WarpStack stacks[QWARPS];
     __shared__ TreeDesc s_tree[QWARPS];
     __shared__ int s_nbr[MODE == 1 ? QWARPS : 1][32][33];  // neighbour positions (cloud-local sorted), padded
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpStack& S = stacks[warp];
     for (i64 it = (i64)blockIdx.x * QWARPS + warp; it < n_items; it += (i64)gridDim.x * QWARPS) {
-        QueryItem I = items[it];
+        QueryItem I;
+        if (MODE == 1) {
+            // implicit items: tree_item_off (passed in `items`' place as i64 prefix sums) -> (tree, 32-point chunk)
+            const i64* tio = reinterpret_cast<const i64*>(items);
+            int t = find_segment(tio, n_trees_or_zero, it);
+            I.tree = t;
+            I.q_off = (it - tio[t]) * 32;
+            int rem = F.trees[t].n - (int)I.q_off;
+            I.count = rem < 32 ? rem : 32;
+        } else {
+            I = items[it];
+        }
         __syncwarp();
         load_tree(&s_tree[warp], &F.trees[I.tree], lane);
         const TreeDesc& T = s_tree[warp];
@@ -393,10 +427,14 @@ __global__ void __launch_bounds__(QWARPS * 32) k_knn(ForestView F, const double*
             }
         }
         int my_m = 0;
+        int prev_pos = -1;  // this lane's entry of the previous query's list: the seed of the next query
+        if (MODE == 1) prev_pos = (int)I.q_off + lane < T.n ? (int)I.q_off + lane : -1;  // own leaf: 32 distinct points
         for (int j = 0; j < I.count; ++j) {
             double qx = shfl_d(mx, j), qy = shfl_d(my, j), qz = shfl_d(mz, j);
             KnnVisitor V(F, T, qx, qy, qz, lane, k);
+            if (MODE == 1 || j > 0) V.seed(prev_pos);
             traverse(F, T, qx, qy, qz, S, V, lane);
+            prev_pos = V.lpos;
             bool have = lane < k && V.lidx != 0x7fffffff;
             int m = __popc(__ballot_sync(0xffffffffu, have));
             if (MODE == 1) {
@@ -484,28 +522,24 @@ int forest_knn(Ctx* ctx, const Forest* f, const double* d_q, const QueryItem* d_
                int* d_out_idx, double* d_out_d2) {
     if (n_items <= 0) return SB_OK;
     SB_LAUNCH(ctx, k_knn<0>, query_grid(ctx, n_items), QWARPS * 32, 0, view_of(f), d_q, d_items, n_items, k, d_out_idx,
-              d_out_d2, nullptr, nullptr, nullptr);
+              d_out_d2, nullptr, nullptr, nullptr, 0);
     return SB_OK;
 }
 
 int forest_normals(Ctx* ctx, Forest* f, int k, double* d_out_normals, double* d_out_evals) {
     if (!f->normals) SB_CUDA(ctx, cudaMalloc(&f->normals, sizeof(double) * 3 * (size_t)(f->n_points > 0 ? f->n_points : 1)));
     f->normals_k = k;
-    std::vector<QueryItem> items;
-    for (int t = 0; t < f->n_trees; ++t) {
-        const TreeDesc& T = f->h_trees[t];
-        for (int s = 0; s < T.n; s += 32) {
-            QueryItem I;
-            I.q_off = s; I.count = T.n - s < 32 ? T.n - s : 32; I.tree = t;
-            items.push_back(I);
-        }
-    }
-    if (items.empty()) return SB_OK;
-    QueryItem* d_items;
-    SB_TRY(make_items_dev(ctx, items, &d_items));
-    i64 n_items = (i64)items.size();
-    SB_LAUNCH(ctx, k_knn<1>, query_grid(ctx, n_items), QWARPS * 32, 0, view_of(f), nullptr, d_items, n_items, k,
-              nullptr, nullptr, f->normals, d_out_normals, d_out_evals);
+    // implicit work items: chunk c of tree t is item tree_item_off[t] + c (no per-item table to build or upload)
+    std::vector<i64> tio((size_t)f->n_trees + 1, 0);
+    for (int t = 0; t < f->n_trees; ++t) tio[t + 1] = tio[t] + (f->h_trees[t].n + 31) / 32;
+    i64 n_items = tio[f->n_trees];
+    if (n_items == 0) return SB_OK;
+    i64* d_tio;
+    SB_TRY(arena_get(ctx, tio.size(), &d_tio));
+    SB_CUDA(ctx, cudaMemcpyAsync(d_tio, tio.data(), sizeof(i64) * tio.size(), cudaMemcpyHostToDevice, ctx->stream));
+    SB_LAUNCH(ctx, k_knn<1>, query_grid(ctx, n_items), QWARPS * 32, 0, view_of(f), nullptr,
+              reinterpret_cast<const QueryItem*>(d_tio), n_items, k, nullptr, nullptr, f->normals, d_out_normals,
+              d_out_evals, f->n_trees);
     return SB_OK;
 }
 

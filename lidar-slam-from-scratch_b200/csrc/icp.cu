@@ -30,7 +30,7 @@ struct IcpJob {
     ForestView F;
     const double* normals;   // 3 per sorted target point
     const double* src;       // source rows, fp64 xyz
-    const QueryItem* items;  // tree field = pair id
+    int* match;              // n_items x ITEM_Q: last correspondence of every source point (seed of the next pass)
     i64 n_items;
     const PairDesc* pairs;
     sb_icp_result* results;
@@ -46,6 +46,7 @@ struct IcpJob {
 
 static constexpr int IWARPS = 8;
 static constexpr int NSUM = 28;
+static constexpr int ITEM_Q = 16;  // source points per warp work item
 
 // -------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_icp_init(IcpJob* __restrict__ job, cudaGraphConditionalHandle cond,
@@ -72,7 +73,18 @@ __global__ void __launch_bounds__(256) k_icp_init(IcpJob* __restrict__ job, cuda
         cudaGraphSetConditional(cond, (job->n_active > 0 && job->max_it > 0) ? 1u : 0u);
 }
 
-// phase 0: pairs in ST_ACTIVE; phase 1: pairs in ST_EXHAUSTED (final error pass, icp.hpp:235-252)
+// largest s in [0, n) with pairs[s].item_off <= x
+__device__ __forceinline__ int find_pair(const PairDesc* __restrict__ pairs, int n, i64 x) {
+    int lo = 0, hi = n;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (pairs[mid].item_off <= x) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// phase 0: pairs in ST_ACTIVE; phase 1: pairs in ST_EXHAUSTED (final error pass, icp.hpp:235-252).
+// Work item `it` = ITEM_Q consecutive source points of one pair (implicit: binary search over pairs[].item_off).
 __global__ void __launch_bounds__(IWARPS * 32) k_icp_iter(const IcpJob* __restrict__ job, int phase) {
     __shared__ WarpStack stacks[IWARPS];
     __shared__ TreeDesc s_tree[IWARPS];
@@ -80,12 +92,14 @@ __global__ void __launch_bounds__(IWARPS * 32) k_icp_iter(const IcpJob* __restri
     WarpStack& S = stacks[warp];
     const ForestView F = job->F;
     const i64 n_items = job->n_items;
+    const int n_pairs = job->n_pairs;
     const int want = phase == 0 ? ST_ACTIVE : ST_EXHAUSTED;
     for (i64 it = (i64)blockIdx.x * IWARPS + warp; it < n_items; it += (i64)gridDim.x * IWARPS) {
-        QueryItem I = job->items[it];
-        const int pair = I.tree;
+        const int pair = find_pair(job->pairs, n_pairs, it);
         if (job->state[pair].state != want) continue;
         PairDesc P = job->pairs[pair];
+        const int s0 = (int)(it - P.item_off) * ITEM_Q;
+        const int count = P.n_src - s0 < ITEM_Q ? P.n_src - s0 : ITEM_Q;
         __syncwarp();
         {
             const int* s = reinterpret_cast<const int*>(&F.trees[P.tree]);
@@ -97,50 +111,67 @@ __global__ void __launch_bounds__(IWARPS * 32) k_icp_iter(const IcpJob* __restri
         const double* Tm = job->results[pair].transformation;
         // cur = src * R^T + t, the oracle's association (types.hpp:110-115)
         double cx = 0, cy = 0, cz = 0;
-        if (lane < I.count) {
-            const double* p = job->src + 3 * (I.q_off + lane);
+        int my_pos = -1;
+        if (lane < count) {
+            const double* p = job->src + 3 * (P.src_off + s0 + lane);
             double x = p[0], y = p[1], z = p[2];
             cx = ((x * Tm[0] + y * Tm[1]) + z * Tm[2]) + Tm[3];
             cy = ((x * Tm[4] + y * Tm[5]) + z * Tm[6]) + Tm[7];
             cz = ((x * Tm[8] + y * Tm[9]) + z * Tm[10]) + Tm[11];
+            my_pos = job->match[it * ITEM_Q + lane];  // last iteration's correspondence (-1 before the first)
         }
-        int my_pos = -1;
-        for (int j = 0; j < I.count; ++j) {
+        int last = -1;
+        for (int j = 0; j < count; ++j) {
             double qx = shfl_d(cx, j), qy = shfl_d(cy, j), qz = shfl_d(cz, j);
+            int sd = __shfl_sync(0xffffffffu, my_pos, j);
             NearestVisitor V(F, T, qx, qy, qz, lane);
+            V.seed(sd >= 0 ? sd : last);  // temporal seed, else the neighbouring query's match
             traverse(F, T, qx, qy, qz, S, V, lane);
+            last = V.best_pos;
             if (lane == j) my_pos = V.best_pos;
         }
-        double acc[NSUM];
-#pragma unroll
-        for (int i = 0; i < NSUM; ++i) acc[i] = 0.0;
-        if (lane < I.count && my_pos >= 0) {
+        double tx = 0, ty = 0, tz = 0, nx = 0, ny = 0, nz = 0;
+        const bool ok = lane < count && my_pos >= 0;
+        if (lane < count) job->match[it * ITEM_Q + lane] = my_pos;
+        if (ok) {
             i64 p = T.pt_off + my_pos;
-            double tx = F.sx[p], ty = F.sy[p], tz = F.sz[p];
-            double nx = job->normals[3 * p], ny = job->normals[3 * p + 1], nz = job->normals[3 * p + 2];
-            double J[6];
-            J[0] = cy * nz - cz * ny;  // p x n, icp.hpp:105
-            J[1] = cz * nx - cx * nz;
-            J[2] = cx * ny - cy * nx;
-            J[3] = nx; J[4] = ny; J[5] = nz;
-            double b = ((tx - cx) * nx + (ty - cy) * ny) + (tz - cz) * nz;  // icp.hpp:116
-            int t = 0;
-#pragma unroll
-            for (int a = 0; a < 6; ++a)
-#pragma unroll
-                for (int c = a; c < 6; ++c) acc[t++] = J[a] * J[c];
-#pragma unroll
-            for (int a = 0; a < 6; ++a) acc[21 + a] = J[a] * b;
-            acc[27] = b * b;
+            tx = F.sx[p]; ty = F.sy[p]; tz = F.sz[p];
+            nx = job->normals[3 * p]; ny = job->normals[3 * p + 1]; nz = job->normals[3 * p + 2];
+        } else {
+            cx = cy = cz = 0.0;
         }
-        // fixed-order butterfly: every lane ends with every sum
+        double J[6];
+        J[0] = cy * nz - cz * ny;  // p x n, icp.hpp:105
+        J[1] = cz * nx - cx * nz;
+        J[2] = cx * ny - cy * nx;
+        J[3] = nx; J[4] = ny; J[5] = nz;
+        const double b = ((tx - cx) * nx + (ty - cy) * ny) + (tz - cz) * nz;  // icp.hpp:116
+        // 28 sums over the item points (idle lanes add zeros): fixed-order butterfly, term i is kept by lane i
         double mine = 0.0;
+        int t = 0;
 #pragma unroll
-        for (int i = 0; i < NSUM; ++i) {
-            double v = acc[i];
+        for (int a = 0; a < 6; ++a) {
+#pragma unroll
+            for (int c = a; c < 6; ++c) {
+                double v = J[a] * J[c];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += shfl_d_xor(v, o);
+                if (lane == t) mine = v;
+                ++t;
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+            double v = J[a] * b;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) v += shfl_d_xor(v, o);
-            if (lane == i) mine = v;
+            if (lane == 21 + a) mine = v;
+        }
+        {
+            double v = b * b;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += shfl_d_xor(v, o);
+            if (lane == 27) mine = v;
         }
         if (lane < NSUM) job->partials[it * NSUM + lane] = mine;
     }
@@ -500,42 +531,36 @@ int icp_batch(Ctx* ctx, const Forest* f, const double* d_src, const std::vector<
     IcpGraph* G;
     SB_TRY(icp_graph_get(ctx, &G));
     std::vector<PairDesc> pairs(pairs_in);
-    std::vector<QueryItem> items;
     int n_valid = 0;
+    i64 n_items = 0;
     for (int p = 0; p < n_pairs; ++p) {
         PairDesc& P = pairs[p];
-        P.item_off = (i64)items.size();
-        for (int s = 0; s < P.n_src; s += 32) {
-            QueryItem I;
-            I.q_off = P.src_off + s;
-            I.count = P.n_src - s < 32 ? P.n_src - s : 32;
-            I.tree = p;
-            items.push_back(I);
-        }
-        P.n_items = (int)((i64)items.size() - P.item_off);
+        P.item_off = n_items;
+        P.n_items = P.n_src > 0 ? (P.n_src + ITEM_Q - 1) / ITEM_Q : 0;
+        n_items += P.n_items;
         if (P.n_src > 0 && f->h_trees[P.tree].n > 0) ++n_valid;
     }
     PairDesc* d_pairs;
-    QueryItem* d_items;
+    int* d_match;
     sb_icp_result* d_res;
     PairState* d_state;
     double* d_part;
+    size_t ni = (size_t)(n_items > 0 ? n_items : 1);
     SB_TRY(arena_get(ctx, (size_t)n_pairs, &d_pairs));
-    SB_TRY(arena_get(ctx, items.size() ? items.size() : 1, &d_items));
+    SB_TRY(arena_get(ctx, ni * ITEM_Q, &d_match));
     SB_TRY(arena_get(ctx, (size_t)n_pairs, &d_res));
     SB_TRY(arena_get(ctx, (size_t)n_pairs, &d_state));
-    SB_TRY(arena_get(ctx, (items.size() ? items.size() : 1) * NSUM, &d_part));
+    SB_TRY(arena_get(ctx, ni * NSUM, &d_part));
     SB_CUDA(ctx, cudaMemcpyAsync(d_pairs, pairs.data(), sizeof(PairDesc) * n_pairs, cudaMemcpyHostToDevice, ctx->stream));
-    if (!items.empty())
-        SB_CUDA(ctx, cudaMemcpyAsync(d_items, items.data(), sizeof(QueryItem) * items.size(), cudaMemcpyHostToDevice, ctx->stream));
+    SB_CUDA(ctx, cudaMemsetAsync(d_match, 0xff, sizeof(int) * ni * ITEM_Q, ctx->stream));  // -1: no correspondence yet
     IcpJob job;
     memset(&job, 0, sizeof(job));
     job.F.sx = f->sx; job.F.sy = f->sy; job.F.sz = f->sz; job.F.sidx = f->sidx; job.F.boxes = f->boxes;
     job.F.trees = f->d_trees;
     job.normals = f->normals;
     job.src = d_src;
-    job.items = d_items;
-    job.n_items = (i64)items.size();
+    job.match = d_match;
+    job.n_items = n_items;
     job.pairs = d_pairs;
     job.results = d_res;
     job.state = d_state;

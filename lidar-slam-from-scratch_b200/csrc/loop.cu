@@ -105,6 +105,7 @@ int loop_verify(sb_loop* L, const int* entries, const double* dist, int n, sb_lo
             return fail(ctx, SB_ERR_INVALID_ARG, "loop: entry %d is not owned by rank %d", entries[i], L->rank);
     }
     Forest F;
+    F.in_arena = true;
     int s = forest_build(ctx, L->d_clouds, L->cloud_off.data(), slots.data(), n, &F);
     if (s == SB_OK) s = forest_normals(ctx, &F, L->cfg.normals_k, nullptr, nullptr);
     std::vector<sb_icp_result> res((size_t)n);

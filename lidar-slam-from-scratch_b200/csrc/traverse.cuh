@@ -108,6 +108,19 @@ struct NearestVisitor {
     __device__ NearestVisitor(const ForestView& f, const TreeDesc& t, double x, double y, double z, int l)
         : F(f), T(t), qx(x), qy(y), qz(z), lane(l), best_d(1.7976931348623157e308), best_idx(-1), best_pos(-1) {}
     __device__ __forceinline__ double tau() const { return best_d; }
+    // Starts the search from a known tree point (cloud-local sorted position): any real point bounds the nearest
+    // distance from above, so the traversal only has to visit boxes inside that ball.  Exactness is unaffected.
+    __device__ __forceinline__ void seed(int pos) {
+        if (pos < 0 || pos >= T.n) return;
+        i64 p = T.pt_off + pos;
+        double d = dist2_rn(F.sx[p], F.sy[p], F.sz[p], qx, qy, qz);
+        int idx = F.sidx[p];
+        if (d < best_d || (d == best_d && idx < best_idx)) {
+            best_d = d;
+            best_idx = idx;
+            best_pos = pos;
+        }
+    }
     __device__ __forceinline__ void leaf(int p0, int cnt) {
         bool valid = lane < cnt;
         unsigned hi = 0xffffffffu, lo = 0xffffffffu;
@@ -154,6 +167,33 @@ struct KnnVisitor {
         : F(f), T(t), qx(x), qy(y), qz(z), lane(l), k(kk), ld((double)INFINITY),
           lidx(0x7fffffff), lpos(-1), tau_d((double)INFINITY), tau_idx(0x7fffffff) {}
     __device__ __forceinline__ double tau() const { return tau_d; }
+    // Seeds the list with up to 32 DISTINCT tree points (this lane's `pos`, cloud-local sorted position, or -1):
+    // distances to the new query are evaluated and the 32 entries are bitonic-sorted by (d2, idx) across the warp.
+    // Any k distinct real points bound the k-th nearest distance from above, so the result stays exact.
+    __device__ __forceinline__ void seed(int pos) {
+        ld = (double)INFINITY; lidx = 0x7fffffff; lpos = -1;
+        if (pos >= 0 && pos < T.n) {
+            i64 p = T.pt_off + pos;
+            double d = dist2_rn(F.sx[p], F.sy[p], F.sz[p], qx, qy, qz);
+            if (d == d) { ld = d; lidx = F.sidx[p]; lpos = pos; }
+        }
+#pragma unroll
+        for (int kk = 2; kk <= 32; kk <<= 1) {
+#pragma unroll
+            for (int j = kk >> 1; j > 0; j >>= 1) {
+                double od = shfl_d_xor(ld, j);
+                int oi = __shfl_xor_sync(0xffffffffu, lidx, j);
+                int op = __shfl_xor_sync(0xffffffffu, lpos, j);
+                bool lower = (lane & j) == 0;            // this lane is the lower index of the pair
+                bool asc = (lane & kk) == 0;             // sort direction of this block
+                bool other_less = lex_less(od, oi, ld, lidx);
+                bool take = (lower == asc) ? other_less : !other_less && !(od == ld && oi == lidx);
+                if (take) { ld = od; lidx = oi; lpos = op; }
+            }
+        }
+        tau_d = shfl_d(ld, k - 1);
+        tau_idx = __shfl_sync(0xffffffffu, lidx, k - 1);
+    }
     __device__ __forceinline__ void leaf(int p0, int cnt) {
         bool valid = lane < cnt;
         double cd = 0.0;
@@ -171,6 +211,7 @@ struct KnnVisitor {
             double bd = shfl_d(cd, b);
             int bi = __shfl_sync(0xffffffffu, cidx, b);
             if (!lex_less(bd, bi, tau_d, tau_idx)) continue;  // warp-uniform: the bound moved past it
+            if (__any_sync(0xffffffffu, lidx == bi)) continue;  // already listed (seeded entries)
             int bp = p0 + b;
             int pos = __popc(__ballot_sync(0xffffffffu, lex_less(ld, lidx, bd, bi)));  // sorted: a prefix
             double ud = __shfl_up_sync(0xffffffffu, ld, 1);

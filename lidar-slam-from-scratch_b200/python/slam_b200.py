@@ -73,6 +73,7 @@ SYMBOLS = {
     "sb_ctx_launch_count": (C.c_int64, [_P]),
     "sb_ctx_set_profiling": (C.c_int, [_P, C.c_int]),
     "sb_ctx_stage_ms": (C.c_int, [_P, _D]),
+    "sb_ctx_stage_host_ms": (C.c_int, [_P, _D]),
     "sb_ctx_last_counts": (C.c_int, [_P, _I64]),
     "sb_default_icp_config": (None, [C.POINTER(ICPConfigC)]),
     "sb_default_loop_config": (None, [C.POINTER(LoopConfigC)]),
@@ -185,6 +186,11 @@ class Engine:
         self._check(self.lib.sb_ctx_stage_ms(self.h, _dp(ms)))
         return dict(zip(self.STAGES, ms.tolist()))
 
+    def stage_host_ms(self):
+        ms = np.zeros(7)
+        self._check(self.lib.sb_ctx_stage_host_ms(self.h, _dp(ms)))
+        return dict(zip(self.STAGES, ms.tolist()))
+
     def last_counts(self):
         c = np.zeros(5, dtype=np.int64)
         self._check(self.lib.sb_ctx_last_counts(self.h, c.ctypes.data_as(_I64)))
@@ -257,19 +263,20 @@ class Engine:
         pt = np.ascontiguousarray(pair_tgt, dtype=np.int32)
         npairs = ps.shape[0]
         cfg = cfg or self.icp_config()
-        res = (ICPResultC * max(npairs, 1))()
+        res = np.zeros(max(npairs, 1), dtype=ICP_DTYPE)
+        rp = res.ctypes.data_as(C.POINTER(ICPResultC))
         sc = np.empty((nc, SB_SC_SIZE)) if want_sc else None
         if device_ptr is None:
             pts = _f64(points, 3)
             s = self.lib.sb_register_batch(self.h, _dp(pts), off.ctypes.data_as(_I64), nc, float(voxel),
-                                           ps.ctypes.data_as(_I32), pt.ctypes.data_as(_I32), npairs, C.byref(cfg), res,
+                                           ps.ctypes.data_as(_I32), pt.ctypes.data_as(_I32), npairs, C.byref(cfg), rp,
                                            _dp(sc) if want_sc else None)
         else:
             s = self.lib.sb_register_batch_dev(self.h, _P(device_ptr), off.ctypes.data_as(_I64), nc, float(voxel),
                                                ps.ctypes.data_as(_I32), pt.ctypes.data_as(_I32), npairs, C.byref(cfg),
-                                               res, _dp(sc) if want_sc else None)
+                                               rp, _dp(sc) if want_sc else None)
         self._check(s)
-        out = [ICPResult(res[i]) for i in range(npairs)]
+        out = ICPResultBatch(res[:npairs])
         return (out, sc) if want_sc else out
 
     # ---- Scan Context (scan_context.hpp)
@@ -310,10 +317,24 @@ class Engine:
         return off
 
 
+ICP_DTYPE = np.dtype([("transformation", "f8", (16,)), ("final_error", "f8"), ("converged", "i4"),
+                      ("num_iterations", "i4"), ("history_len", "i4"), ("status", "i4"),
+                      ("error_history", "f8", (SB_MAX_ICP_ITERATIONS + 1,))])
+assert ICP_DTYPE.itemsize == C.sizeof(ICPResultC)
+
+
 class ICPResult:
     """slam::ICPResult (types.hpp:155-164)."""
 
     def __init__(self, r):
+        if isinstance(r, np.void):  # one record of an ICP_DTYPE array
+            self.transformation = r["transformation"].reshape(4, 4).copy()
+            self.converged = bool(r["converged"])
+            self.num_iterations = int(r["num_iterations"])
+            self.final_error = float(r["final_error"])
+            self.error_history = r["error_history"][:int(r["history_len"])].copy()
+            self.status = int(r["status"])
+            return
         self.transformation = np.array(r.transformation[:]).reshape(4, 4)
         self.converged = bool(r.converged)
         self.num_iterations = int(r.num_iterations)
@@ -323,6 +344,53 @@ class ICPResult:
 
     def success(self):  # types.hpp:162
         return self.converged and self.final_error < 0.1
+
+
+class ICPResultBatch:
+    """The sb_icp_result records of one sb_register_batch call, kept as one structured array (no per-pair Python
+    objects on the hot path); indexing yields an ICPResult."""
+
+    def __init__(self, rec):
+        self.rec = rec
+
+    def __len__(self):
+        return self.rec.shape[0]
+
+    def __getitem__(self, i):
+        return ICPResult(self.rec[i])
+
+    def __iter__(self):
+        return (ICPResult(self.rec[i]) for i in range(len(self)))
+
+    @property
+    def transformations(self):
+        return self.rec["transformation"].reshape(-1, 4, 4)
+
+    @property
+    def num_iterations(self):
+        return self.rec["num_iterations"]
+
+    @property
+    def converged(self):
+        return self.rec["converged"].astype(bool)
+
+    @property
+    def final_errors(self):
+        return self.rec["final_error"]
+
+    @property
+    def status(self):
+        return self.rec["status"]
+
+    def records20(self):
+        """(n, 20) float64: T[16], final_error, num_iterations, converged, status — the NCCL gather payload."""
+        out = np.empty((len(self), 20))
+        out[:, :16] = self.rec["transformation"]
+        out[:, 16] = self.rec["final_error"]
+        out[:, 17] = self.rec["num_iterations"]
+        out[:, 18] = self.rec["converged"]
+        out[:, 19] = self.rec["status"]
+        return out
 
 
 class KDTree:
