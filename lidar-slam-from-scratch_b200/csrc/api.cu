@@ -470,18 +470,14 @@ int sb_index_find_correspondences(sb_index* index, const double* source, int64_t
     Enter g(c);
     const Forest& F = index->forest;
     i64 n = F.n_points;
-    std::vector<double> sx((size_t)n), sy((size_t)n), sz((size_t)n);
-    std::vector<int> sidx((size_t)n);
-    SB_TRY(download(c, sx.data(), F.sx, sizeof(double) * n));
-    SB_TRY(download(c, sy.data(), F.sy, sizeof(double) * n));
-    SB_TRY(download(c, sz.data(), F.sz, sizeof(double) * n));
-    SB_TRY(download(c, sidx.data(), F.sidx, sizeof(int) * n));
+    std::vector<TreePoint> pts((size_t)n);
+    SB_TRY(download(c, pts.data(), F.pts, sizeof(TreePoint) * n));
     SB_CUDA(c, cudaStreamSynchronize(c->stream));
     std::vector<int> pos_of((size_t)n);
-    for (i64 p = 0; p < n; ++p) pos_of[sidx[p]] = (int)p;
+    for (i64 p = 0; p < n; ++p) pos_of[pts[p].idx] = (int)p;
     for (i64 i = 0; i < ns; ++i) {  // kdtree.hpp:208-212
-        int p = pos_of[idx[i]];
-        matched_xyz[3 * i] = sx[p]; matched_xyz[3 * i + 1] = sy[p]; matched_xyz[3 * i + 2] = sz[p];
+        const TreePoint& P = pts[pos_of[idx[i]]];
+        matched_xyz[3 * i] = P.x; matched_xyz[3 * i + 1] = P.y; matched_xyz[3 * i + 2] = P.z;
         if (distances) distances[i] = sqrt(d2[i]);
     }
     return SB_OK;

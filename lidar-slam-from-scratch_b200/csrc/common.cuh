@@ -170,15 +170,36 @@ struct TreeDesc {      // device-resident, one per indexed cloud
     int pad;
 };
 
+// One Morton-sorted point: exactly one 32-byte sector, so that a gathered candidate costs one sector and a leaf
+// (32 consecutive points) is one coalesced 1 KB load.
+struct alignas(32) TreePoint {
+    double x, y, z;
+    int idx;   // original row of the point, local to its cloud
+    int pad;
+};
+// Unit normal of a sorted point (icp.hpp:23-67), padded to one sector.
+struct alignas(32) TreeNormal {
+    double x, y, z;
+    double pad;
+};
+// Entry j of a point's k-nearest-neighbour list (ascending by (d2, index), the point itself included): the
+// neighbour's cloud-local sorted position and a LOWER bound of its distance to the point.  Every point that is
+// not among the first j entries is at least r_j away from the point — the certificate icp.cu's per-thread
+// correspondence search rests on.
+struct NbrEntry {
+    int pos;   // -1: the cloud has fewer than k points
+    float r;   // sqrt(d2) rounded down and shrunk by 1e-6 (+inf for padding)
+};
+
 struct Forest {
     Ctx* ctx = nullptr;
     int n_trees = 0;
     i64 n_points = 0, n_boxes = 0;
     // device arrays (owned, cudaMalloc)
-    double *sx = nullptr, *sy = nullptr, *sz = nullptr;  // Morton-sorted coordinates
-    int* sidx = nullptr;                                 // original row of each sorted point (local to its cloud)
-    float* boxes = nullptr;                              // 6 floats per box: lo xyz (rounded down), hi xyz (up)
-    double* normals = nullptr;                           // 3 per sorted point (sorted order), filled by normals
+    TreePoint* pts = nullptr;      // Morton-sorted points
+    float* boxes = nullptr;        // 6 floats per box: lo xyz (rounded down), hi xyz (up)
+    TreeNormal* normals = nullptr; // per sorted point, filled by forest_normals
+    NbrEntry* nbr = nullptr;       // normals_k entries per sorted point, filled by forest_normals
     TreeDesc* d_trees = nullptr;
     std::vector<TreeDesc> h_trees;
     int normals_k = 0;

@@ -98,9 +98,7 @@ __global__ void __launch_bounds__(256) k_gather_leaves(const double* __restrict_
                                                        const Chunk* __restrict__ chunks,
                                                        const TreeDesc* __restrict__ trees,
                                                        const uint32_t* __restrict__ sorted_vals,
-                                                       double* __restrict__ sx, double* __restrict__ sy,
-                                                       double* __restrict__ sz, int* __restrict__ sidx,
-                                                       float* __restrict__ boxes) {
+                                                       TreePoint* __restrict__ pts, float* __restrict__ boxes) {
     Chunk c = chunks[blockIdx.x];
     const TreeDesc& T = trees[c.tree];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -114,10 +112,9 @@ __global__ void __launch_bounds__(256) k_gather_leaves(const double* __restrict_
             x = base[3 * (i64)o + 0];
             y = base[3 * (i64)o + 1];
             z = base[3 * (i64)o + 2];
-            sx[T.pt_off + j] = x;
-            sy[T.pt_off + j] = y;
-            sz[T.pt_off + j] = z;
-            sidx[T.pt_off + j] = o;
+            TreePoint P;
+            P.x = x; P.y = y; P.z = z; P.idx = o; P.pad = 0;
+            pts[T.pt_off + j] = P;
         }
         double lo[3] = {valid ? x : INFINITY, valid ? y : INFINITY, valid ? z : INFINITY};
         double hi[3] = {valid ? x : -INFINITY, valid ? y : -INFINITY, valid ? z : -INFINITY};
@@ -177,12 +174,10 @@ __global__ void __launch_bounds__(256) k_boxes_up(const TreeDesc* __restrict__ t
 // ---------------------------------------------------------------------------------------------------------------
 void forest_free(Forest* f) {
     if (!f) return;
-    if (f->in_arena) {
-        f->sx = f->sy = f->sz = nullptr; f->sidx = nullptr; f->boxes = nullptr; f->normals = nullptr; f->d_trees = nullptr;
+    if (!f->in_arena) {
+        cudaFree(f->pts); cudaFree(f->boxes); cudaFree(f->normals); cudaFree(f->nbr); cudaFree(f->d_trees);
     }
-    cudaFree(f->sx); cudaFree(f->sy); cudaFree(f->sz); cudaFree(f->sidx); cudaFree(f->boxes);
-    cudaFree(f->normals); cudaFree(f->d_trees);
-    f->sx = f->sy = f->sz = nullptr; f->sidx = nullptr; f->boxes = nullptr; f->normals = nullptr; f->d_trees = nullptr;
+    f->pts = nullptr; f->boxes = nullptr; f->normals = nullptr; f->nbr = nullptr; f->d_trees = nullptr;
     f->h_trees.clear();
     f->n_trees = 0; f->n_points = 0; f->n_boxes = 0;
 }
@@ -230,18 +225,11 @@ int forest_build(Ctx* ctx, const double* d_xyz, const i64* h_off, const int* clo
     size_t npa = (size_t)(np > 0 ? np : 1), nba = (size_t)(nb > 0 ? nb : 1);
     if (f->in_arena) {
         SB_TRY(arena_get(ctx, (size_t)(n_trees > 0 ? n_trees : 1), &f->d_trees));
-        SB_TRY(arena_get(ctx, npa, &f->sx));
-        SB_TRY(arena_get(ctx, npa, &f->sy));
-        SB_TRY(arena_get(ctx, npa, &f->sz));
-        SB_TRY(arena_get(ctx, npa, &f->sidx));
+        SB_TRY(arena_get(ctx, npa, &f->pts));
         SB_TRY(arena_get(ctx, 6 * nba, &f->boxes));
-        SB_TRY(arena_get(ctx, 3 * npa, &f->normals));
     } else {
         SB_CUDA(ctx, cudaMalloc(&f->d_trees, sizeof(TreeDesc) * (size_t)(n_trees > 0 ? n_trees : 1)));
-        SB_CUDA(ctx, cudaMalloc(&f->sx, sizeof(double) * npa));
-        SB_CUDA(ctx, cudaMalloc(&f->sy, sizeof(double) * npa));
-        SB_CUDA(ctx, cudaMalloc(&f->sz, sizeof(double) * npa));
-        SB_CUDA(ctx, cudaMalloc(&f->sidx, sizeof(int) * npa));
+        SB_CUDA(ctx, cudaMalloc(&f->pts, sizeof(TreePoint) * npa));
         SB_CUDA(ctx, cudaMalloc(&f->boxes, sizeof(float) * 6 * nba));
     }
     SB_CUDA(ctx, cudaMemcpyAsync(f->d_trees, f->h_trees.data(), sizeof(TreeDesc) * (size_t)n_trees,
@@ -273,8 +261,7 @@ int forest_build(Ctx* ctx, const double* d_xyz, const i64* h_off, const int* clo
     SB_LAUNCH(ctx, k_bbox, nch, 256, 0, d_xyz, d_src_off, d_chunks, d_bb);
     SB_LAUNCH(ctx, k_morton, nch, 256, 0, d_xyz, d_src_off, d_chunks, d_bb, f->d_trees, ka, va);
     SB_TRY(segmented_sort_pairs(ctx, ka, kb, va, vb, seg_off.data(), n_trees, 30, &ks, &vs));
-    SB_LAUNCH(ctx, k_gather_leaves, nch, 256, 0, d_xyz, d_src_off, d_chunks, f->d_trees, vs, f->sx, f->sy, f->sz,
-              f->sidx, f->boxes);
+    SB_LAUNCH(ctx, k_gather_leaves, nch, 256, 0, d_xyz, d_src_off, d_chunks, f->d_trees, vs, f->pts, f->boxes);
     for (int l = 1; l <= max_top; ++l) SB_LAUNCH(ctx, k_boxes_up, (unsigned)n_trees, 256, 0, f->d_trees, l, f->boxes);
     return SB_OK;
 }
@@ -393,7 +380,8 @@ template <int MODE>
 __global__ void __launch_bounds__(QWARPS * 32) k_knn(ForestView F, const double* __restrict__ q,
                                                      const QueryItem* __restrict__ items, i64 n_items, int k,
                                                      int* __restrict__ out_idx, double* __restrict__ out_d2,
-                                                     double* __restrict__ nrm_sorted, double* __restrict__ nrm_orig,
+                                                     TreeNormal* __restrict__ nrm_sorted,
+                                                     NbrEntry* __restrict__ nbr_sorted, double* __restrict__ nrm_orig,
                                                      double* __restrict__ evals_orig, int n_trees_or_zero) {
     __shared__ WarpStack stacks[QWARPS];
     __shared__ TreeDesc s_tree[QWARPS];
@@ -419,8 +407,8 @@ __global__ void __launch_bounds__(QWARPS * 32) k_knn(ForestView F, const double*
         double mx = 0, my = 0, mz = 0;
         if (lane < I.count) {
             if (MODE == 1) {
-                i64 p = T.pt_off + I.q_off + lane;
-                mx = F.sx[p]; my = F.sy[p]; mz = F.sz[p];
+                TreePoint P = load_point(F.pts + T.pt_off + I.q_off + lane);
+                mx = P.x; my = P.y; mz = P.z;
             } else {
                 const double* p = q + 3 * (I.q_off + lane);
                 mx = p[0]; my = p[1]; mz = p[2];
@@ -438,7 +426,14 @@ __global__ void __launch_bounds__(QWARPS * 32) k_knn(ForestView F, const double*
             bool have = lane < k && V.lidx != 0x7fffffff;
             int m = __popc(__ballot_sync(0xffffffffu, have));
             if (MODE == 1) {
-                if (lane < k) s_nbr[warp][j][lane] = V.lpos;
+                if (lane < k) {
+                    s_nbr[warp][j][lane] = V.lpos;
+                    // the neighbour graph of icp.cu: position + a lower bound of the distance (padding: -1, +inf)
+                    NbrEntry e;
+                    e.pos = have ? V.lpos : -1;
+                    e.r = have ? __fmul_rd(__fsqrt_rd(__double2float_rd(V.ld)), 0.999999f) : __int_as_float(0x7f800000);
+                    nbr_sorted[(T.pt_off + I.q_off + j) * k + lane] = e;
+                }
                 if (lane == j) my_m = m;
             } else {
                 if (lane < k) {
@@ -457,15 +452,15 @@ __global__ void __launch_bounds__(QWARPS * 32) k_knn(ForestView F, const double*
                 if (m >= 3) {  // icp.hpp:34-37
                     double c0 = 0.0, c1 = 0.0, c2 = 0.0;
                     for (int j = 0; j < m; ++j) {  // icp.hpp:40-44, neighbours ascending by (d2, idx)
-                        i64 p = T.pt_off + nb[j];
-                        c0 += F.sx[p]; c1 += F.sy[p]; c2 += F.sz[p];
+                        TreePoint P = load_point(F.pts + T.pt_off + nb[j]);
+                        c0 += P.x; c1 += P.y; c2 += P.z;
                     }
                     double md = (double)m;
                     c0 /= md; c1 /= md; c2 /= md;
                     double C00 = 0, C01 = 0, C02 = 0, C11 = 0, C12 = 0, C22 = 0;
                     for (int j = 0; j < m; ++j) {  // icp.hpp:47-52
-                        i64 p = T.pt_off + nb[j];
-                        double d0 = F.sx[p] - c0, d1 = F.sy[p] - c1, d2 = F.sz[p] - c2;
+                        TreePoint P = load_point(F.pts + T.pt_off + nb[j]);
+                        double d0 = P.x - c0, d1 = P.y - c1, d2 = P.z - c2;
                         C00 += d0 * d0; C01 += d0 * d1; C02 += d0 * d2;
                         C11 += d1 * d1; C12 += d1 * d2; C22 += d2 * d2;
                     }
@@ -488,8 +483,10 @@ __global__ void __launch_bounds__(QWARPS * 32) k_knn(ForestView F, const double*
                     if (e1 < e0) { double t = e0; e0 = e1; e1 = t; }
                 }
                 i64 ps = T.pt_off + I.q_off + lane;
-                nrm_sorted[3 * ps + 0] = n0; nrm_sorted[3 * ps + 1] = n1; nrm_sorted[3 * ps + 2] = n2;
-                i64 po = T.pt_off + F.sidx[ps];
+                TreeNormal Nn;
+                Nn.x = n0; Nn.y = n1; Nn.z = n2; Nn.pad = 0.0;
+                nrm_sorted[ps] = Nn;
+                i64 po = T.pt_off + F.pts[ps].idx;
                 if (nrm_orig) { nrm_orig[3 * po + 0] = n0; nrm_orig[3 * po + 1] = n1; nrm_orig[3 * po + 2] = n2; }
                 if (evals_orig) { evals_orig[3 * po + 0] = e0; evals_orig[3 * po + 1] = e1; evals_orig[3 * po + 2] = e2; }
             }
@@ -500,7 +497,7 @@ __global__ void __launch_bounds__(QWARPS * 32) k_knn(ForestView F, const double*
 
 static ForestView view_of(const Forest* f) {
     ForestView v;
-    v.sx = f->sx; v.sy = f->sy; v.sz = f->sz; v.sidx = f->sidx; v.boxes = f->boxes; v.trees = f->d_trees;
+    v.pts = f->pts; v.boxes = f->boxes; v.trees = f->d_trees;
     return v;
 }
 
@@ -522,12 +519,24 @@ int forest_knn(Ctx* ctx, const Forest* f, const double* d_q, const QueryItem* d_
                int* d_out_idx, double* d_out_d2) {
     if (n_items <= 0) return SB_OK;
     SB_LAUNCH(ctx, k_knn<0>, query_grid(ctx, n_items), QWARPS * 32, 0, view_of(f), d_q, d_items, n_items, k, d_out_idx,
-              d_out_d2, nullptr, nullptr, nullptr, 0);
+              d_out_d2, nullptr, nullptr, nullptr, nullptr, 0);
     return SB_OK;
 }
 
 int forest_normals(Ctx* ctx, Forest* f, int k, double* d_out_normals, double* d_out_evals) {
-    if (!f->normals) SB_CUDA(ctx, cudaMalloc(&f->normals, sizeof(double) * 3 * (size_t)(f->n_points > 0 ? f->n_points : 1)));
+    const size_t npa = (size_t)(f->n_points > 0 ? f->n_points : 1);
+    if (f->in_arena) {
+        SB_TRY(arena_get(ctx, npa, &f->normals));
+        SB_TRY(arena_get(ctx, npa * (size_t)k, &f->nbr));
+    } else {
+        if (!f->normals) SB_CUDA(ctx, cudaMalloc(&f->normals, sizeof(TreeNormal) * npa));
+        if (f->nbr && f->normals_k != k) {
+            SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            cudaFree(f->nbr);
+            f->nbr = nullptr;
+        }
+        if (!f->nbr) SB_CUDA(ctx, cudaMalloc(&f->nbr, sizeof(NbrEntry) * npa * (size_t)k));
+    }
     f->normals_k = k;
     // implicit work items: chunk c of tree t is item tree_item_off[t] + c (no per-item table to build or upload)
     std::vector<i64> tio((size_t)f->n_trees + 1, 0);
@@ -538,7 +547,7 @@ int forest_normals(Ctx* ctx, Forest* f, int k, double* d_out_normals, double* d_
     SB_TRY(arena_get(ctx, tio.size(), &d_tio));
     SB_CUDA(ctx, cudaMemcpyAsync(d_tio, tio.data(), sizeof(i64) * tio.size(), cudaMemcpyHostToDevice, ctx->stream));
     SB_LAUNCH(ctx, k_knn<1>, query_grid(ctx, n_items), QWARPS * 32, 0, view_of(f), nullptr,
-              reinterpret_cast<const QueryItem*>(d_tio), n_items, k, nullptr, nullptr, f->normals, d_out_normals,
+              reinterpret_cast<const QueryItem*>(d_tio), n_items, k, nullptr, nullptr, f->normals, f->nbr, d_out_normals,
               d_out_evals, f->n_trees);
     return SB_OK;
 }

@@ -28,25 +28,30 @@ struct PairState {
 
 struct IcpJob {
     ForestView F;
-    const double* normals;   // 3 per sorted target point
-    const double* src;       // source rows, fp64 xyz
-    int* match;              // n_items x ITEM_Q: last correspondence of every source point (seed of the next pass)
+    const TreeNormal* normals;  // per sorted target point
+    const NbrEntry* nbr;        // nbr_k entries per sorted target point (forest_normals)
+    const double* src;          // source rows, fp64 xyz
+    int* match;                 // n_items x ITEM_Q: last correspondence of every source point (seed of the next pass)
     i64 n_items;
     const PairDesc* pairs;
     sb_icp_result* results;
     PairState* state;
-    double* partials;        // n_items x 28
+    double* partials;           // n_items x 28
+    unsigned long long* stats;  // optional (SB_ICP_STATS): [0] queries, [1] queries that needed the tree traversal
     double T0[16];
     double tol, min_err;
     int n_pairs;
     int max_it;
     int n_active;
     int ticket;
+    int nbr_k;
+    int pad;
 };
 
 static constexpr int IWARPS = 8;
 static constexpr int NSUM = 28;
-static constexpr int ITEM_Q = 16;  // source points per warp work item
+static constexpr int ITEM_Q = 32;   // source points per warp work item: one per lane
+static constexpr int MAX_HOPS = 6;  // re-centrings of the neighbour-graph walk before the tree takes over
 
 // -------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_icp_init(IcpJob* __restrict__ job, cudaGraphConditionalHandle cond,
@@ -83,8 +88,60 @@ __device__ __forceinline__ int find_pair(const PairDesc* __restrict__ pairs, int
     return lo;
 }
 
+// upper bound of sqrt(d2), with 1e-6 of slack for the rounding of d2 itself
+__device__ __forceinline__ float sqrt_up(double d2) {
+    return __fmul_ru(__fsqrt_ru(__double2float_ru(d2)), 1.000001f);
+}
+
+// Per-thread greedy descent of the box tree: at every level take the child box nearest to the query, then the
+// nearest point of the leaf reached (fp32 throughout: the result is only a starting point, never an answer).
+__device__ __forceinline__ int greedy_seed(const ForestView& F, const TreeDesc& T, double qx, double qy, double qz) {
+    const float fx = (float)qx, fy = (float)qy, fz = (float)qz;
+    int first = 0;
+    for (int level = T.top; level >= 0; --level) {
+        int cnt = T.box_cnt[level] - first;
+        cnt = cnt > 32 ? 32 : cnt;
+        const float2* b = reinterpret_cast<const float2*>(F.boxes + 6 * (T.box_off[level] + first));
+        float best = __int_as_float(0x7f800000);
+        int bi = 0;
+        for (int c = 0; c < cnt; ++c) {
+            float2 b0 = __ldg(b + 3 * c), b1 = __ldg(b + 3 * c + 1), b2 = __ldg(b + 3 * c + 2);
+            float ex = fmaxf(fmaxf(b0.x - fx, fx - b1.y), 0.f);
+            float ey = fmaxf(fmaxf(b0.y - fy, fy - b2.x), 0.f);
+            float ez = fmaxf(fmaxf(b1.x - fz, fz - b2.y), 0.f);
+            float d = ex * ex + ey * ey + ez * ez;
+            if (d < best) { best = d; bi = c; }
+        }
+        first = (first + bi) * 32;
+    }
+    int cnt = T.n - first;
+    cnt = cnt > 32 ? 32 : cnt;
+    const TreePoint* P = F.pts + T.pt_off + first;
+    float best = __int_as_float(0x7f800000);
+    int bi = 0;
+    for (int c = 0; c < cnt; ++c) {
+        const double2 xy = __ldg(reinterpret_cast<const double2*>(P + c));
+        const double z = __ldg(reinterpret_cast<const double*>(P + c) + 2);
+        float dx = (float)xy.x - fx, dy = (float)xy.y - fy, dz = (float)z - fz;
+        float d = dx * dx + dy * dy + dz * dz;
+        if (d < best) { best = d; bi = c; }
+    }
+    return cnt > 0 ? first + bi : -1;
+}
+
 // phase 0: pairs in ST_ACTIVE; phase 1: pairs in ST_EXHAUSTED (final error pass, icp.hpp:235-252).
-// Work item `it` = ITEM_Q consecutive source points of one pair (implicit: binary search over pairs[].item_off).
+// Work item `it` = ITEM_Q consecutive source points of one pair (implicit: binary search over pairs[].item_off),
+// one source point per lane.
+//
+// Correspondence search (replaces KDTree::nearest_batch, kdtree.hpp:43-59, exact):
+//   1. per lane: start from the previous iteration's match (or a greedy tree descent) and walk the target's
+//      k-nearest-neighbour graph.  With c the current centre, entries of c's list are evaluated in ascending
+//      distance from c; every point not yet evaluated is at least r_j from c, hence at least r_j - |q c| from the
+//      query q.  As soon as that bound exceeds the best distance found, the best point IS the nearest neighbour
+//      (all bounds rounded conservatively in fp32, the candidates themselves compared in the oracle's fp64
+//      (d2, index) order).  If the list runs out first, re-centre on the best point and repeat.
+//   2. lanes whose walk did not certify fall back, one after the other, to the warp-cooperative exact tree
+//      traversal (traverse.cuh) seeded with the best point found.
 __global__ void __launch_bounds__(IWARPS * 32) k_icp_iter(const IcpJob* __restrict__ job, int phase) {
     __shared__ WarpStack stacks[IWARPS];
     __shared__ TreeDesc s_tree[IWARPS];
@@ -93,6 +150,7 @@ __global__ void __launch_bounds__(IWARPS * 32) k_icp_iter(const IcpJob* __restri
     const ForestView F = job->F;
     const i64 n_items = job->n_items;
     const int n_pairs = job->n_pairs;
+    const int K = job->nbr_k;
     const int want = phase == 0 ? ST_ACTIVE : ST_EXHAUSTED;
     for (i64 it = (i64)blockIdx.x * IWARPS + warp; it < n_items; it += (i64)gridDim.x * IWARPS) {
         const int pair = find_pair(job->pairs, n_pairs, it);
@@ -111,32 +169,82 @@ __global__ void __launch_bounds__(IWARPS * 32) k_icp_iter(const IcpJob* __restri
         const double* Tm = job->results[pair].transformation;
         // cur = src * R^T + t, the oracle's association (types.hpp:110-115)
         double cx = 0, cy = 0, cz = 0;
-        int my_pos = -1;
+        double bd = 1.7976931348623157e308;
+        int bidx = 0x7fffffff, bpos = -1;
+        bool cert = false;
         if (lane < count) {
             const double* p = job->src + 3 * (P.src_off + s0 + lane);
             double x = p[0], y = p[1], z = p[2];
             cx = ((x * Tm[0] + y * Tm[1]) + z * Tm[2]) + Tm[3];
             cy = ((x * Tm[4] + y * Tm[5]) + z * Tm[6]) + Tm[7];
             cz = ((x * Tm[8] + y * Tm[9]) + z * Tm[10]) + Tm[11];
-            my_pos = job->match[it * ITEM_Q + lane];  // last iteration's correspondence (-1 before the first)
+            // ---- 1. neighbour-graph walk from the last correspondence
+            int center = job->match[it * ITEM_Q + lane];  // -1 before the first pass
+            if (center < 0 || center >= T.n) center = greedy_seed(F, T, cx, cy, cz);
+            if (center >= 0) {
+                const TreePoint* TP = F.pts + T.pt_off;
+                const NbrEntry* TN = job->nbr + T.pt_off * (i64)K;
+                TreePoint c = load_point(TP + center);
+                bd = dist2_rn(c.x, c.y, c.z, cx, cy, cz);
+                bidx = c.idx;
+                bpos = center;
+                if (bd == bd) {
+                    for (int hop = 0; hop < MAX_HOPS; ++hop) {
+                        const float dc = sqrt_up(bd);  // |q centre|: the centre is the best point so far
+                        float sb = dc;
+                        const int2* L = reinterpret_cast<const int2*>(TN + (i64)center * K);
+                        float rlast = 0.f;
+                        for (int j = 0; j < K; ++j) {
+                            const int2 e = __ldg(L + j);
+                            rlast = __int_as_float(e.y);
+                            if (e.x < 0 || __fsub_rd(rlast, dc) > sb) { cert = true; break; }
+                            if (e.x == center) continue;
+                            TreePoint t = load_point(TP + e.x);
+                            double d = dist2_rn(t.x, t.y, t.z, cx, cy, cz);
+                            if (d < bd || (d == bd && t.idx < bidx)) {
+                                bd = d; bidx = t.idx; bpos = e.x;
+                                sb = sqrt_up(bd);
+                            }
+                        }
+                        if (!cert && __fsub_rd(rlast, dc) > sb) cert = true;  // list exhausted: the rest is >= r_{K-1}
+                        if (cert || bpos == center) break;
+                        center = bpos;
+                    }
+                } else {  // NaN query: never matches (kdtree.hpp:125 strict <)
+                    bd = 1.7976931348623157e308; bidx = 0x7fffffff; bpos = -1;
+                }
+            }
         }
-        int last = -1;
-        for (int j = 0; j < count; ++j) {
+        // ---- 2. exact tree traversal for the lanes without a certificate
+        unsigned todo = __ballot_sync(0xffffffffu, lane < count && !cert);
+        if (job->stats && lane == 0) {
+            atomicAdd(&job->stats[0], (unsigned long long)count);
+            if (todo) atomicAdd(&job->stats[1], (unsigned long long)__popc(todo));
+        }
+        int chain = -1;
+        while (todo) {
+            const int j = __ffs(todo) - 1;
+            todo &= todo - 1u;
             double qx = shfl_d(cx, j), qy = shfl_d(cy, j), qz = shfl_d(cz, j);
-            int sd = __shfl_sync(0xffffffffu, my_pos, j);
+            double sd = shfl_d(bd, j);
+            int si = __shfl_sync(0xffffffffu, bidx, j), sp = __shfl_sync(0xffffffffu, bpos, j);
             NearestVisitor V(F, T, qx, qy, qz, lane);
-            V.seed(sd >= 0 ? sd : last);  // temporal seed, else the neighbouring query's match
+            if (sp >= 0) { V.best_d = sd; V.best_idx = si; V.best_pos = sp; }
+            else V.seed(chain);
             traverse(F, T, qx, qy, qz, S, V, lane);
-            last = V.best_pos;
-            if (lane == j) my_pos = V.best_pos;
+            chain = V.best_pos;
+            if (lane == j) { bd = V.best_d; bidx = V.best_idx; bpos = V.best_pos; }
         }
+        const int my_pos = bpos;
         double tx = 0, ty = 0, tz = 0, nx = 0, ny = 0, nz = 0;
         const bool ok = lane < count && my_pos >= 0;
         if (lane < count) job->match[it * ITEM_Q + lane] = my_pos;
         if (ok) {
-            i64 p = T.pt_off + my_pos;
-            tx = F.sx[p]; ty = F.sy[p]; tz = F.sz[p];
-            nx = job->normals[3 * p]; ny = job->normals[3 * p + 1]; nz = job->normals[3 * p + 2];
+            TreePoint q = load_point(F.pts + T.pt_off + my_pos);
+            tx = q.x; ty = q.y; tz = q.z;
+            const double2* np = reinterpret_cast<const double2*>(job->normals + T.pt_off + my_pos);
+            double2 n01 = __ldg(np), n2 = __ldg(np + 1);
+            nx = n01.x; ny = n01.y; nz = n2.x;
         } else {
             cx = cy = cz = 0.0;
         }
@@ -269,7 +377,15 @@ __device__ __forceinline__ double sum_partials(const IcpJob* job, const PairDesc
     double s = 0.0;
     if (lane < NSUM) {
         const double* base = job->partials + P.item_off * NSUM + lane;
-        for (int i = 0; i < P.n_items; ++i) s += base[(i64)i * NSUM];
+        int i = 0;
+        for (; i + 8 <= P.n_items; i += 8) {  // loads issued together, additions in item order
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = base[(i64)(i + u) * NSUM];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s += v[u];
+        }
+        for (; i < P.n_items; ++i) s += base[(i64)i * NSUM];
     }
     return s;
 }
@@ -445,6 +561,7 @@ struct IcpGraph {
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
     int iter_grid = 0, solve_grid = 0;
+    unsigned long long* d_stats = nullptr;  // SB_ICP_STATS=1: [0] queries, [1] queries that fell back to the tree
 };
 
 void icp_graph_free(Ctx* ctx) {
@@ -452,6 +569,13 @@ void icp_graph_free(Ctx* ctx) {
     if (!G) return;
     if (G->exec) cudaGraphExecDestroy(G->exec);
     if (G->graph) cudaGraphDestroy(G->graph);
+    if (G->d_stats) {
+        unsigned long long h[2] = {0, 0};
+        cudaMemcpy(h, G->d_stats, sizeof(h), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[slam_b200] icp nearest-neighbour queries %llu, tree fallbacks %llu (%.3f %%)\n", h[0], h[1],
+                h[0] ? 100.0 * (double)h[1] / (double)h[0] : 0.0);
+        cudaFree(G->d_stats);
+    }
     cudaFree(G->d_job);
     delete G;
     ctx->icp_graph = nullptr;
@@ -482,6 +606,10 @@ static int icp_graph_get(Ctx* ctx, IcpGraph** out) {
     SB_CUDA(ctx, cudaMalloc(&G->d_job, sizeof(IcpJob)));
     G->iter_grid = ctx->sm_count * 8;
     G->solve_grid = ctx->sm_count;
+    if (getenv("SB_ICP_STATS")) {
+        SB_CUDA(ctx, cudaMalloc(&G->d_stats, 2 * sizeof(unsigned long long)));
+        SB_CUDA(ctx, cudaMemset(G->d_stats, 0, 2 * sizeof(unsigned long long)));
+    }
     if (getenv("SB_ICP_NOGRAPH")) return SB_OK;
     SB_CUDA(ctx, cudaGraphCreate(&G->graph, 0));
     cudaGraphConditionalHandle cond;
@@ -527,7 +655,7 @@ int icp_batch(Ctx* ctx, const Forest* f, const double* d_src, const std::vector<
     if (cfg->max_iterations < 0 || cfg->max_iterations > SB_MAX_ICP_ITERATIONS)
         return fail(ctx, SB_ERR_INVALID_ARG, "icp: max_iterations %d outside [0, %d]", cfg->max_iterations,
                     SB_MAX_ICP_ITERATIONS);
-    if (!f->normals) return fail(ctx, SB_ERR_INVALID_ARG, "icp: forest has no normals");
+    if (!f->normals || !f->nbr) return fail(ctx, SB_ERR_INVALID_ARG, "icp: forest has no normals");
     IcpGraph* G;
     SB_TRY(icp_graph_get(ctx, &G));
     std::vector<PairDesc> pairs(pairs_in);
@@ -555,9 +683,12 @@ int icp_batch(Ctx* ctx, const Forest* f, const double* d_src, const std::vector<
     SB_CUDA(ctx, cudaMemsetAsync(d_match, 0xff, sizeof(int) * ni * ITEM_Q, ctx->stream));  // -1: no correspondence yet
     IcpJob job;
     memset(&job, 0, sizeof(job));
-    job.F.sx = f->sx; job.F.sy = f->sy; job.F.sz = f->sz; job.F.sidx = f->sidx; job.F.boxes = f->boxes;
+    job.F.pts = f->pts; job.F.boxes = f->boxes;
     job.F.trees = f->d_trees;
     job.normals = f->normals;
+    job.nbr = f->nbr;
+    job.nbr_k = f->normals_k;
+    job.stats = G->d_stats;
     job.src = d_src;
     job.match = d_match;
     job.n_items = n_items;

@@ -5,7 +5,7 @@
 // boxes over the Morton-sorted points: level-0 box b bounds sorted points [32b, 32b+32), level-l box b bounds the
 // level-(l-1) boxes [32b, 32b+32).  One warp answers one query: the 32 lanes test the 32 children of a node (one
 // coalesced 768-byte load), descend nearest-box-first, and evaluate the 32 points of a leaf with one coalesced
-// load per coordinate.  A subtree is skipped only if a conservative lower bound of its squared distance is
+// 32-byte load per lane (TreePoint).  A subtree is skipped only if a conservative lower bound of its squared distance is
 // strictly greater than the current k-th best, so the result is exact for any density and any radius.
 //
 // Distances are the oracle's (dx*dx + dy*dy) + dz*dz in fp64 without FMA; candidates are ranked by
@@ -22,13 +22,23 @@ struct WarpStack {                       // shared memory, one per warp
 };
 
 struct ForestView {
-    const double* __restrict__ sx;
-    const double* __restrict__ sy;
-    const double* __restrict__ sz;
-    const int* __restrict__ sidx;
+    const TreePoint* __restrict__ pts;
     const float* __restrict__ boxes;
     const TreeDesc* __restrict__ trees;
 };
+
+// one 32-byte sector as two 16-byte read-only loads
+__device__ __forceinline__ TreePoint load_point(const TreePoint* p) {
+    const int4* q = reinterpret_cast<const int4*>(p);
+    int4 a = __ldg(q), b = __ldg(q + 1);
+    TreePoint r;
+    r.x = __hiloint2double(a.y, a.x);
+    r.y = __hiloint2double(a.w, a.z);
+    r.z = __hiloint2double(b.y, b.x);
+    r.idx = b.z;
+    r.pad = b.w;
+    return r;
+}
 
 __device__ __forceinline__ bool lex_less(double da, int ia, double db, int ib) {
     return da < db || (da == db && ia < ib);
@@ -112,9 +122,9 @@ struct NearestVisitor {
     // distance from above, so the traversal only has to visit boxes inside that ball.  Exactness is unaffected.
     __device__ __forceinline__ void seed(int pos) {
         if (pos < 0 || pos >= T.n) return;
-        i64 p = T.pt_off + pos;
-        double d = dist2_rn(F.sx[p], F.sy[p], F.sz[p], qx, qy, qz);
-        int idx = F.sidx[p];
+        TreePoint P = load_point(F.pts + T.pt_off + pos);
+        double d = dist2_rn(P.x, P.y, P.z, qx, qy, qz);
+        int idx = P.idx;
         if (d < best_d || (d == best_d && idx < best_idx)) {
             best_d = d;
             best_idx = idx;
@@ -126,9 +136,9 @@ struct NearestVisitor {
         unsigned hi = 0xffffffffu, lo = 0xffffffffu;
         int idx = 0x7fffffff;
         if (valid) {
-            i64 p = T.pt_off + p0 + lane;
-            double d = dist2_rn(F.sx[p], F.sy[p], F.sz[p], qx, qy, qz);
-            idx = F.sidx[p];
+            TreePoint P = load_point(F.pts + T.pt_off + p0 + lane);
+            double d = dist2_rn(P.x, P.y, P.z, qx, qy, qz);
+            idx = P.idx;
             if (d == d) {  // NaN never wins (kdtree.hpp:125 strict <)
                 long long b = __double_as_longlong(d);
                 hi = (unsigned)((unsigned long long)b >> 32);
@@ -173,9 +183,9 @@ struct KnnVisitor {
     __device__ __forceinline__ void seed(int pos) {
         ld = (double)INFINITY; lidx = 0x7fffffff; lpos = -1;
         if (pos >= 0 && pos < T.n) {
-            i64 p = T.pt_off + pos;
-            double d = dist2_rn(F.sx[p], F.sy[p], F.sz[p], qx, qy, qz);
-            if (d == d) { ld = d; lidx = F.sidx[p]; lpos = pos; }
+            TreePoint P = load_point(F.pts + T.pt_off + pos);
+            double d = dist2_rn(P.x, P.y, P.z, qx, qy, qz);
+            if (d == d) { ld = d; lidx = P.idx; lpos = pos; }
         }
 #pragma unroll
         for (int kk = 2; kk <= 32; kk <<= 1) {
@@ -199,9 +209,9 @@ struct KnnVisitor {
         double cd = 0.0;
         int cidx = 0x7fffffff;
         if (valid) {
-            i64 p = T.pt_off + p0 + lane;
-            cd = dist2_rn(F.sx[p], F.sy[p], F.sz[p], qx, qy, qz);
-            cidx = F.sidx[p];
+            TreePoint P = load_point(F.pts + T.pt_off + p0 + lane);
+            cd = dist2_rn(P.x, P.y, P.z, qx, qy, qz);
+            cidx = P.idx;
         }
         bool want = valid && lex_less(cd, cidx, tau_d, tau_idx);  // NaN compares false: never inserted
         unsigned cm = __ballot_sync(0xffffffffu, want);
