@@ -167,6 +167,18 @@ struct TreeDesc {      // device-resident, one per indexed cloud
     int top;           // top level (boxes at that level <= 32)
     i64 box_off[SB_MAX_LEVELS];  // first box of level l in the forest's box array
     int box_cnt[SB_MAX_LEVELS];  // boxes at level l
+    int tab_shift;     // seed grid: 64 - log2(slots of this tree's hash table)
+    i64 tab_off;       // seed grid: first slot of this tree in the forest's table
+    double glo[3];     // seed grid origin = lower corner of the cloud's bounding box (device copy only)
+    double gext;       // largest extent of the bounding box (device copy only)
+    double ginv;       // 1 / cell size, set by forest_normals (device copy only)
+};
+
+// Seed grid (forest_normals): an open-addressing hash table cell -> one point of that cell per tree.  It only
+// provides STARTING points for icp.cu's neighbour-graph walk, never answers.
+struct GridSlot {
+    unsigned long long key;  // packed cell coordinates, ~0 = empty
+    int pos;                 // cloud-local sorted position of a point in the cell
     int pad;
 };
 
@@ -200,6 +212,8 @@ struct Forest {
     float* boxes = nullptr;        // 6 floats per box: lo xyz (rounded down), hi xyz (up)
     TreeNormal* normals = nullptr; // per sorted point, filled by forest_normals
     NbrEntry* nbr = nullptr;       // normals_k entries per sorted point, filled by forest_normals
+    GridSlot* grid = nullptr;      // n_slots seed-grid slots, filled by forest_normals
+    i64 n_slots = 0;
     TreeDesc* d_trees = nullptr;
     std::vector<TreeDesc> h_trees;
     int normals_k = 0;

@@ -93,7 +93,26 @@ __global__ void __launch_bounds__(256) k_morton(const double* __restrict__ xyz, 
     }
 }
 
-// gathers the sorted points into SoA and builds the level-0 boxes (one warp per leaf)
+// seed-grid origin and extent of every tree (device copy of the descriptors only)
+__global__ void k_tree_bounds(TreeDesc* __restrict__ trees, const long long* __restrict__ bb, int n_trees) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_trees) return;
+    double ext = 0.0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        double lo = 0.0, hi = 0.0;
+        if (trees[t].n > 0) {
+            lo = double_from_ordered(bb[6 * t + a]);
+            hi = double_from_ordered(bb[6 * t + 3 + a]);
+        }
+        trees[t].glo[a] = lo;
+        ext = fmax(ext, hi - lo);
+    }
+    trees[t].gext = ext;
+    trees[t].ginv = 1.0;
+}
+
+// gathers the sorted points into AoS and builds the level-0 boxes (one warp per leaf)
 __global__ void __launch_bounds__(256) k_gather_leaves(const double* __restrict__ xyz, const i64* __restrict__ src_off,
                                                        const Chunk* __restrict__ chunks,
                                                        const TreeDesc* __restrict__ trees,
@@ -175,9 +194,10 @@ __global__ void __launch_bounds__(256) k_boxes_up(const TreeDesc* __restrict__ t
 void forest_free(Forest* f) {
     if (!f) return;
     if (!f->in_arena) {
-        cudaFree(f->pts); cudaFree(f->boxes); cudaFree(f->normals); cudaFree(f->nbr); cudaFree(f->d_trees);
+        cudaFree(f->pts); cudaFree(f->boxes); cudaFree(f->normals); cudaFree(f->nbr); cudaFree(f->grid);
+        cudaFree(f->d_trees);
     }
-    f->pts = nullptr; f->boxes = nullptr; f->normals = nullptr; f->nbr = nullptr; f->d_trees = nullptr;
+    f->pts = nullptr; f->boxes = nullptr; f->normals = nullptr; f->nbr = nullptr; f->grid = nullptr; f->d_trees = nullptr;
     f->h_trees.clear();
     f->n_trees = 0; f->n_points = 0; f->n_boxes = 0;
 }
@@ -188,7 +208,7 @@ int forest_build(Ctx* ctx, const double* d_xyz, const i64* h_off, const int* clo
     f->h_trees.assign((size_t)n_trees, TreeDesc());
     std::vector<i64> src_off((size_t)n_trees), seg_off((size_t)n_trees + 1);
     std::vector<Chunk> chunks;
-    i64 np = 0, nb = 0;
+    i64 np = 0, nb = 0, n_slots = 0;
     int max_top = 0;
     for (int t = 0; t < n_trees; ++t) {
         int c = cloud_ids ? cloud_ids[t] : t;
@@ -211,6 +231,13 @@ int forest_build(Ctx* ctx, const double* d_xyz, const i64* h_off, const int* clo
         }
         T.top = lev;
         if (lev > max_top) max_top = lev;
+        {  // seed grid: a power-of-two table with at least 2 slots per point
+            int lg = 6;
+            while (((i64)1 << lg) < 2 * (i64)T.n) ++lg;
+            T.tab_off = n_slots;
+            T.tab_shift = 64 - lg;
+            n_slots += (i64)1 << lg;
+        }
         for (int s = 0; s < T.n; s += CHUNK) {
             Chunk ch;
             ch.tree = t; ch.start = s; ch.count = T.n - s < CHUNK ? T.n - s : CHUNK; ch.pad = 0;
@@ -221,6 +248,7 @@ int forest_build(Ctx* ctx, const double* d_xyz, const i64* h_off, const int* clo
     seg_off[n_trees] = np;
     f->n_points = np;
     f->n_boxes = nb;
+    f->n_slots = n_slots;
     if (np >= (i64)0xffffffffLL) return fail(ctx, SB_ERR_RANGE, "index: more than 2^32-1 points in one forest");
     size_t npa = (size_t)(np > 0 ? np : 1), nba = (size_t)(nb > 0 ? nb : 1);
     if (f->in_arena) {
@@ -260,6 +288,7 @@ int forest_build(Ctx* ctx, const double* d_xyz, const i64* h_off, const int* clo
     unsigned nch = (unsigned)chunks.size();
     SB_LAUNCH(ctx, k_bbox, nch, 256, 0, d_xyz, d_src_off, d_chunks, d_bb);
     SB_LAUNCH(ctx, k_morton, nch, 256, 0, d_xyz, d_src_off, d_chunks, d_bb, f->d_trees, ka, va);
+    SB_LAUNCH(ctx, k_tree_bounds, ceil_div(n_trees, 128), 128, 0, f->d_trees, d_bb, n_trees);
     SB_TRY(segmented_sort_pairs(ctx, ka, kb, va, vb, seg_off.data(), n_trees, 30, &ks, &vs));
     SB_LAUNCH(ctx, k_gather_leaves, nch, 256, 0, d_xyz, d_src_off, d_chunks, f->d_trees, vs, f->pts, f->boxes);
     for (int l = 1; l <= max_top; ++l) SB_LAUNCH(ctx, k_boxes_up, (unsigned)n_trees, 256, 0, f->d_trees, l, f->boxes);
@@ -382,7 +411,8 @@ __global__ void __launch_bounds__(QWARPS * 32) k_knn(ForestView F, const double*
                                                      int* __restrict__ out_idx, double* __restrict__ out_d2,
                                                      TreeNormal* __restrict__ nrm_sorted,
                                                      NbrEntry* __restrict__ nbr_sorted, double* __restrict__ nrm_orig,
-                                                     double* __restrict__ evals_orig, int n_trees_or_zero) {
+                                                     double* __restrict__ evals_orig, int n_trees_or_zero,
+                                                     unsigned long long* __restrict__ spacing_acc) {
     __shared__ WarpStack stacks[QWARPS];
     __shared__ TreeDesc s_tree[QWARPS];
     __shared__ int s_nbr[MODE == 1 ? QWARPS : 1][32][33];  // neighbour positions (cloud-local sorted), padded
@@ -415,6 +445,7 @@ __global__ void __launch_bounds__(QWARPS * 32) k_knn(ForestView F, const double*
             }
         }
         int my_m = 0;
+        unsigned long long spacing = 0ull;  // lane 1: sum of the nearest-other-point distances, 16.16 fixed point
         int prev_pos = -1;  // this lane's entry of the previous query's list: the seed of the next query
         if (MODE == 1) prev_pos = (int)I.q_off + lane < T.n ? (int)I.q_off + lane : -1;  // own leaf: 32 distinct points
         for (int j = 0; j < I.count; ++j) {
@@ -433,6 +464,7 @@ __global__ void __launch_bounds__(QWARPS * 32) k_knn(ForestView F, const double*
                     e.pos = have ? V.lpos : -1;
                     e.r = have ? __fmul_rd(__fsqrt_rd(__double2float_rd(V.ld)), 0.999999f) : __int_as_float(0x7f800000);
                     nbr_sorted[(T.pt_off + I.q_off + j) * k + lane] = e;
+                    if (lane == 1 && have) spacing += (unsigned long long)(fminf(e.r, 1.0e6f) * 65536.0f);
                 }
                 if (lane == j) my_m = m;
             } else {
@@ -444,6 +476,7 @@ __global__ void __launch_bounds__(QWARPS * 32) k_knn(ForestView F, const double*
             }
         }
         if (MODE == 1) {
+            if (lane == 1 && spacing) atomicAdd(&spacing_acc[I.tree], spacing);  // integer: order-independent
             __syncwarp();
             if (lane < I.count) {
                 const int* nb = s_nbr[warp][lane];
@@ -495,6 +528,46 @@ __global__ void __launch_bounds__(QWARPS * 32) k_knn(ForestView F, const double*
     }
 }
 
+// ----- seed grid: cell size = 3 x the mean distance to the nearest other point, one representative point per cell
+__global__ void k_grid_params(TreeDesc* __restrict__ trees, const unsigned long long* __restrict__ spacing_acc,
+                              int n_trees) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_trees) return;
+    const int n = trees[t].n;
+    double h = n > 0 ? 3.0 * ((double)spacing_acc[t] / 65536.0) / (double)n : 1.0;
+    if (!(h > 1.0e-9) || !(h < 1.0e9)) h = 1.0;
+    const double ext = trees[t].gext;
+    if (ext / h > 1.0e6) h = ext / 1.0e6;  // keep the cell coordinates inside 21 bits
+    trees[t].ginv = 1.0 / h;
+}
+
+// one warp per leaf (implicit items like k_knn<1>): every point claims the slot of its cell
+__global__ void __launch_bounds__(256) k_grid_build(ForestView F, const i64* __restrict__ tio, i64 n_items, int n_trees,
+                                                    GridSlot* __restrict__ grid) {
+    const int lane = threadIdx.x & 31;
+    i64 it = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (it >= n_items) return;
+    const int t = find_segment(tio, n_trees, it);
+    const TreeDesc& T = F.trees[t];
+    const int pos = (int)(it - tio[t]) * 32 + lane;
+    if (pos >= T.n) return;
+    TreePoint P = load_point(F.pts + T.pt_off + pos);
+    int ix, iy, iz;
+    if (!grid_cell(T, P.x, P.y, P.z, ix, iy, iz)) return;  // NaN coordinates: not a seed
+    const unsigned long long key = grid_key(ix, iy, iz);
+    const unsigned mask = (unsigned)(((i64)1 << (64 - T.tab_shift)) - 1);
+    GridSlot* tab = grid + T.tab_off;
+    unsigned slot = grid_hash(key, T.tab_shift);
+    while (true) {
+        unsigned long long prev = atomicCAS(&tab[slot].key, SB_GRID_EMPTY, key);
+        if (prev == SB_GRID_EMPTY || prev == key) {
+            tab[slot].pos = pos;  // any point of the cell will do
+            break;
+        }
+        slot = (slot + 1u) & mask;
+    }
+}
+
 static ForestView view_of(const Forest* f) {
     ForestView v;
     v.pts = f->pts; v.boxes = f->boxes; v.trees = f->d_trees;
@@ -519,7 +592,7 @@ int forest_knn(Ctx* ctx, const Forest* f, const double* d_q, const QueryItem* d_
                int* d_out_idx, double* d_out_d2) {
     if (n_items <= 0) return SB_OK;
     SB_LAUNCH(ctx, k_knn<0>, query_grid(ctx, n_items), QWARPS * 32, 0, view_of(f), d_q, d_items, n_items, k, d_out_idx,
-              d_out_d2, nullptr, nullptr, nullptr, nullptr, 0);
+              d_out_d2, nullptr, nullptr, nullptr, nullptr, 0, nullptr);
     return SB_OK;
 }
 
@@ -528,7 +601,9 @@ int forest_normals(Ctx* ctx, Forest* f, int k, double* d_out_normals, double* d_
     if (f->in_arena) {
         SB_TRY(arena_get(ctx, npa, &f->normals));
         SB_TRY(arena_get(ctx, npa * (size_t)k, &f->nbr));
+        SB_TRY(arena_get(ctx, (size_t)(f->n_slots > 0 ? f->n_slots : 1), &f->grid));
     } else {
+        if (!f->grid) SB_CUDA(ctx, cudaMalloc(&f->grid, sizeof(GridSlot) * (size_t)(f->n_slots > 0 ? f->n_slots : 1)));
         if (!f->normals) SB_CUDA(ctx, cudaMalloc(&f->normals, sizeof(TreeNormal) * npa));
         if (f->nbr && f->normals_k != k) {
             SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -544,11 +619,19 @@ int forest_normals(Ctx* ctx, Forest* f, int k, double* d_out_normals, double* d_
     i64 n_items = tio[f->n_trees];
     if (n_items == 0) return SB_OK;
     i64* d_tio;
+    unsigned long long* d_spacing;
     SB_TRY(arena_get(ctx, tio.size(), &d_tio));
+    SB_TRY(arena_get(ctx, (size_t)f->n_trees, &d_spacing));
     SB_CUDA(ctx, cudaMemcpyAsync(d_tio, tio.data(), sizeof(i64) * tio.size(), cudaMemcpyHostToDevice, ctx->stream));
+    SB_CUDA(ctx, cudaMemsetAsync(d_spacing, 0, sizeof(unsigned long long) * (size_t)f->n_trees, ctx->stream));
+    SB_CUDA(ctx, cudaMemsetAsync(f->grid, 0xff, sizeof(GridSlot) * (size_t)f->n_slots, ctx->stream));
     SB_LAUNCH(ctx, k_knn<1>, query_grid(ctx, n_items), QWARPS * 32, 0, view_of(f), nullptr,
               reinterpret_cast<const QueryItem*>(d_tio), n_items, k, nullptr, nullptr, f->normals, f->nbr, d_out_normals,
-              d_out_evals, f->n_trees);
+              d_out_evals, f->n_trees, d_spacing);
+    // seed grid for icp.cu (cell size from the measured point spacing)
+    SB_LAUNCH(ctx, k_grid_params, ceil_div(f->n_trees, 128), 128, 0, f->d_trees, d_spacing, f->n_trees);
+    SB_LAUNCH(ctx, k_grid_build, (unsigned)((n_items * 32 + 255) / 256), 256, 0, view_of(f), d_tio, n_items, f->n_trees,
+              f->grid);
     return SB_OK;
 }
 

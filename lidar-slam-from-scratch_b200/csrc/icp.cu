@@ -3,12 +3,16 @@
 //
 // The reference runs, per pair and per iteration: a KD-tree 1-NN pass over the source (twice, icp.hpp:185,190),
 // an RMS pass, an n x 6 Jacobian build, J^T J, an LDLT solve, a Rodrigues update and a full rewrite of the
-// source cloud.  Here one iteration of ALL pairs of a batch is two kernels:
-//   k_icp_iter   one warp per 32 source points: cur = T * src (never stored), warp-cooperative exact 1-NN in the
-//                target's tree (traverse.cuh), then lane-parallel residual + the 28 sums (21 of J^T J, 6 of J^T r,
-//                1 of r^2), fixed-order shuffle tree, one 224-byte partial per work item;
-//   k_icp_solve  one warp per pair: adds the pair's partials in item order (run-to-run deterministic), RMS error,
-//                convergence test (icp.hpp:210-217), 6x6 LDL^T, Rodrigues (icp.hpp:127-142), T <- delta * T.
+// source cloud.  Here one iteration of ALL pairs of a batch is four kernels:
+//   k_icp_match     one THREAD per source point: cur = T * src (never stored), then a walk over the target's
+//                   k-nearest-neighbour graph from the previous correspondence (first pass: from the seed grid)
+//                   that ends with a proof that the best point seen is the exact nearest neighbour; points without
+//                   a proof go to a device-wide queue;
+//   k_icp_fallback  one WARP per queued point: the exact warp-cooperative tree traversal of traverse.cuh;
+//   k_icp_accum     one warp per 32 source points: residual + the 28 sums (21 of J^T J, 6 of J^T r, 1 of r^2),
+//                   fixed-order shuffle tree, one 224-byte partial per work item;
+//   k_icp_solve     one warp per pair: adds the pair's partials in item order (run-to-run deterministic), RMS error,
+//                   convergence test (icp.hpp:210-217), 6x6 LDL^T, Rodrigues (icp.hpp:127-142), T <- delta * T.
 // The loop is a CUDA-graph WHILE node whose condition k_icp_solve's last block sets from the device-side count of
 // still-active pairs: no host round trip per iteration.  All kernels read their arguments from one device-resident
 // IcpJob, so the instantiated graph is reused by every call on the context.
@@ -26,18 +30,28 @@ struct PairState {
     int iter;
 };
 
+struct FallbackEntry {   // a source point whose walk did not end with a proof
+    i64 q;               // item * ITEM_Q + lane
+    int seed;            // best target position the walk found (-1: none)
+    int pad;
+};
+
 struct IcpJob {
     ForestView F;
     const TreeNormal* normals;  // per sorted target point
     const NbrEntry* nbr;        // nbr_k entries per sorted target point (forest_normals)
+    const GridSlot* grid;       // seed grid (forest_normals)
     const double* src;          // source rows, fp64 xyz
-    int* match;                 // n_items x ITEM_Q: last correspondence of every source point (seed of the next pass)
+    int* match;                 // n_items x ITEM_Q: correspondence of every source point (seed of the next pass)
     i64 n_items;
     const PairDesc* pairs;
     sb_icp_result* results;
     PairState* state;
     double* partials;           // n_items x 28
-    unsigned long long* stats;  // optional (SB_ICP_STATS): [0] queries, [1] queries that needed the tree traversal
+    FallbackEntry* queue;       // capacity n_items x ITEM_Q
+    int* act_pair;              // pairs the next pass works on (ascending), rebuilt after every solve
+    i64* act_off;               // n_act + 1 prefix sums of their work items
+    unsigned long long* stats;  // optional (SB_ICP_STATS): per iteration bucket [queries, queued]
     double T0[16];
     double tol, min_err;
     int n_pairs;
@@ -45,7 +59,10 @@ struct IcpJob {
     int n_active;
     int ticket;
     int nbr_k;
+    int q_count;                // entries in `queue` (reset by k_icp_solve / k_icp_init)
+    int n_act;                  // entries of act_pair
     int pad;
+    i64 n_act_items;            // = act_off[n_act]
 };
 
 static constexpr int IWARPS = 8;
@@ -54,10 +71,55 @@ static constexpr int ITEM_Q = 32;   // source points per warp work item: one per
 static constexpr int MAX_HOPS = 6;  // re-centrings of the neighbour-graph walk before the tree takes over
 
 // -------------------------------------------------------------------------------------------------------------
+// Block-wide (256 threads): the list of pairs in state `want` and the prefix sums of their work items.  The passes
+// iterate over this list only, so an iteration costs what its ACTIVE pairs cost — the batch keeps running until
+// the slowest pair stops (icp.hpp:181, max_iterations), long after most pairs have converged.
+__device__ void build_active(IcpJob* __restrict__ job, int want) {
+    __shared__ int s_wc[8];
+    __shared__ i64 s_wi[8];
+    __shared__ int s_bc;
+    __shared__ i64 s_bi;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { s_bc = 0; s_bi = 0; }
+    __syncthreads();
+    const int n = job->n_pairs;
+    for (int base = 0; base < n; base += 256) {
+        const int p = base + tid;
+        const bool flag = p < n && __ldcg(&job->state[p].state) == want;
+        const i64 items = flag ? (i64)job->pairs[p].n_items : 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, flag);
+        i64 inc = items;  // inclusive warp scan of the item counts
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            i64 v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += v;
+        }
+        if (lane == 31) { s_wc[warp] = __popc(bal); s_wi[warp] = inc; }
+        __syncthreads();
+        int c0 = s_bc;
+        i64 i0 = s_bi;
+        for (int w = 0; w < warp; ++w) { c0 += s_wc[w]; i0 += s_wi[w]; }
+        if (flag) {
+            const int a = c0 + __popc(bal & lanemask_lt());
+            job->act_pair[a] = p;
+            job->act_off[a] = i0 + inc - items;
+        }
+        __syncthreads();
+        if (tid == 255) { s_bc = c0 + __popc(bal); s_bi = i0 + inc; }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        job->act_off[s_bc] = s_bi;
+        job->n_act = s_bc;
+        job->n_act_items = s_bi;
+    }
+}
+
+// one block
 __global__ void __launch_bounds__(256) k_icp_init(IcpJob* __restrict__ job, cudaGraphConditionalHandle cond,
                                                   int use_cond) {
     const int n = job->n_pairs;
-    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+    for (int p = threadIdx.x; p < n; p += blockDim.x) {
         sb_icp_result& R = job->results[p];
         PairDesc P = job->pairs[p];
 #pragma unroll
@@ -74,8 +136,13 @@ __global__ void __launch_bounds__(256) k_icp_init(IcpJob* __restrict__ job, cuda
         s.state = empty ? ST_DONE : (job->max_it > 0 ? ST_ACTIVE : ST_EXHAUSTED);
         job->state[p] = s;
     }
-    if (use_cond && blockIdx.x == 0 && threadIdx.x == 0)
-        cudaGraphSetConditional(cond, (job->n_active > 0 && job->max_it > 0) ? 1u : 0u);
+    __syncthreads();
+    const bool loop = job->n_active > 0 && job->max_it > 0;
+    build_active(job, loop ? ST_ACTIVE : ST_EXHAUSTED);
+    if (threadIdx.x == 0) {
+        job->q_count = 0;
+        if (use_cond) cudaGraphSetConditional(cond, loop ? 1u : 0u);
+    }
 }
 
 // largest s in [0, n) with pairs[s].item_off <= x
@@ -88,105 +155,108 @@ __device__ __forceinline__ int find_pair(const PairDesc* __restrict__ pairs, int
     return lo;
 }
 
+// largest a in [0, n) with off[a] <= x
+__device__ __forceinline__ int find_active(const i64* __restrict__ off, int n, i64 x) {
+    int lo = 0, hi = n;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (off[mid] <= x) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
 // upper bound of sqrt(d2), with 1e-6 of slack for the rounding of d2 itself
 __device__ __forceinline__ float sqrt_up(double d2) {
     return __fmul_ru(__fsqrt_ru(__double2float_ru(d2)), 1.000001f);
 }
 
-// Per-thread greedy descent of the box tree: at every level take the child box nearest to the query, then the
-// nearest point of the leaf reached (fp32 throughout: the result is only a starting point, never an answer).
-__device__ __forceinline__ int greedy_seed(const ForestView& F, const TreeDesc& T, double qx, double qy, double qz) {
-    const float fx = (float)qx, fy = (float)qy, fz = (float)qz;
-    int first = 0;
-    for (int level = T.top; level >= 0; --level) {
-        int cnt = T.box_cnt[level] - first;
-        cnt = cnt > 32 ? 32 : cnt;
-        const float2* b = reinterpret_cast<const float2*>(F.boxes + 6 * (T.box_off[level] + first));
-        float best = __int_as_float(0x7f800000);
-        int bi = 0;
-        for (int c = 0; c < cnt; ++c) {
-            float2 b0 = __ldg(b + 3 * c), b1 = __ldg(b + 3 * c + 1), b2 = __ldg(b + 3 * c + 2);
-            float ex = fmaxf(fmaxf(b0.x - fx, fx - b1.y), 0.f);
-            float ey = fmaxf(fmaxf(b0.y - fy, fy - b2.x), 0.f);
-            float ez = fmaxf(fmaxf(b1.x - fz, fz - b2.y), 0.f);
-            float d = ex * ex + ey * ey + ez * ez;
-            if (d < best) { best = d; bi = c; }
-        }
-        first = (first + bi) * 32;
-    }
-    int cnt = T.n - first;
-    cnt = cnt > 32 ? 32 : cnt;
-    const TreePoint* P = F.pts + T.pt_off + first;
-    float best = __int_as_float(0x7f800000);
-    int bi = 0;
-    for (int c = 0; c < cnt; ++c) {
-        const double2 xy = __ldg(reinterpret_cast<const double2*>(P + c));
-        const double z = __ldg(reinterpret_cast<const double*>(P + c) + 2);
-        float dx = (float)xy.x - fx, dy = (float)xy.y - fy, dz = (float)z - fz;
-        float d = dx * dx + dy * dy + dz * dz;
-        if (d < best) { best = d; bi = c; }
-    }
-    return cnt > 0 ? first + bi : -1;
+// cur = src * R^T + t with the oracle's association (types.hpp:110-115)
+__device__ __forceinline__ void transform_point(const double* __restrict__ Tm, const double* __restrict__ p,
+                                                double& cx, double& cy, double& cz) {
+    double x = p[0], y = p[1], z = p[2];
+    cx = ((x * Tm[0] + y * Tm[1]) + z * Tm[2]) + Tm[3];
+    cy = ((x * Tm[4] + y * Tm[5]) + z * Tm[6]) + Tm[7];
+    cz = ((x * Tm[8] + y * Tm[9]) + z * Tm[10]) + Tm[11];
 }
 
-// phase 0: pairs in ST_ACTIVE; phase 1: pairs in ST_EXHAUSTED (final error pass, icp.hpp:235-252).
-// Work item `it` = ITEM_Q consecutive source points of one pair (implicit: binary search over pairs[].item_off),
-// one source point per lane.
+__device__ __forceinline__ int grid_find(const GridSlot* __restrict__ tab, unsigned mask, int shift, int ix, int iy,
+                                         int iz) {
+    if ((unsigned)ix > 0x1fffffu || (unsigned)iy > 0x1fffffu || (unsigned)iz > 0x1fffffu) return -1;
+    const unsigned long long key = grid_key(ix, iy, iz);
+    unsigned slot = grid_hash(key, shift);
+    while (true) {
+        const ulonglong2 e = __ldg(reinterpret_cast<const ulonglong2*>(tab + slot));
+        if (e.x == key) return (int)(unsigned)e.y;
+        if (e.x == SB_GRID_EMPTY) return -1;
+        slot = (slot + 1u) & mask;
+    }
+}
+
+// A target point near the query: the representative of the query's grid cell, else the nearest representative of
+// the 26 surrounding cells (fp32: a starting point, never an answer).  -1 if all 27 cells are empty.
+__device__ __forceinline__ int grid_seed(const ForestView& F, const GridSlot* __restrict__ grid, const TreeDesc& T,
+                                         double qx, double qy, double qz) {
+    int ix, iy, iz;
+    if (!grid_cell(T, qx, qy, qz, ix, iy, iz)) return -1;
+    const GridSlot* tab = grid + T.tab_off;
+    const unsigned mask = (unsigned)(((i64)1 << (64 - T.tab_shift)) - 1);
+    int pos = grid_find(tab, mask, T.tab_shift, ix, iy, iz);
+    if (pos >= 0) return pos;
+    float best = __int_as_float(0x7f800000);
+    const float fx = (float)qx, fy = (float)qy, fz = (float)qz;
+    for (int c = 0; c < 27; ++c) {
+        if (c == 13) continue;
+        int p = grid_find(tab, mask, T.tab_shift, ix + c % 3 - 1, iy + (c / 3) % 3 - 1, iz + c / 9 - 1);
+        if (p < 0) continue;
+        const double* P = reinterpret_cast<const double*>(F.pts + T.pt_off + p);
+        const double2 xy = __ldg(reinterpret_cast<const double2*>(P));
+        const double z = __ldg(P + 2);
+        float dx = (float)xy.x - fx, dy = (float)xy.y - fy, dz = (float)z - fz;
+        float d = dx * dx + dy * dy + dz * dz;
+        if (d < best) { best = d; pos = p; }
+    }
+    return pos;
+}
+
+// Works on the pairs listed in job->act_pair: the ST_ACTIVE ones inside the loop, the ST_EXHAUSTED ones in the final
+// error pass (icp.hpp:235-252).  Work item = ITEM_Q consecutive source points of one pair (implicit: binary search
+// over the prefix sums act_off), one source point per lane.
 //
-// Correspondence search (replaces KDTree::nearest_batch, kdtree.hpp:43-59, exact):
-//   1. per lane: start from the previous iteration's match (or a greedy tree descent) and walk the target's
-//      k-nearest-neighbour graph.  With c the current centre, entries of c's list are evaluated in ascending
-//      distance from c; every point not yet evaluated is at least r_j from c, hence at least r_j - |q c| from the
-//      query q.  As soon as that bound exceeds the best distance found, the best point IS the nearest neighbour
-//      (all bounds rounded conservatively in fp32, the candidates themselves compared in the oracle's fp64
-//      (d2, index) order).  If the list runs out first, re-centre on the best point and repeat.
-//   2. lanes whose walk did not certify fall back, one after the other, to the warp-cooperative exact tree
-//      traversal (traverse.cuh) seeded with the best point found.
-__global__ void __launch_bounds__(IWARPS * 32) k_icp_iter(const IcpJob* __restrict__ job, int phase) {
-    __shared__ WarpStack stacks[IWARPS];
-    __shared__ TreeDesc s_tree[IWARPS];
+// Correspondence search (replaces KDTree::nearest_batch, kdtree.hpp:43-59, exact): start from the previous
+// iteration's match (or the seed grid) and walk the target's k-nearest-neighbour graph.  With c the current centre,
+// entries of c's list are evaluated in ascending distance from c; every point not yet evaluated is at least r_j
+// from c, hence at least r_j - |q c| from the query q.  As soon as that bound exceeds the best distance found, the
+// best point IS the nearest neighbour (all bounds rounded conservatively in fp32, the candidates themselves compared
+// in the oracle's fp64 (d2, index) order).  If the list runs out first, re-centre on the best point and repeat.
+// Points whose walk ends without that proof are queued for k_icp_fallback.
+__global__ void __launch_bounds__(IWARPS * 32) k_icp_match(IcpJob* __restrict__ job) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    WarpStack& S = stacks[warp];
     const ForestView F = job->F;
-    const i64 n_items = job->n_items;
-    const int n_pairs = job->n_pairs;
+    const i64 n_act_items = job->n_act_items;
+    const int n_act = job->n_act;
     const int K = job->nbr_k;
-    const int want = phase == 0 ? ST_ACTIVE : ST_EXHAUSTED;
-    for (i64 it = (i64)blockIdx.x * IWARPS + warp; it < n_items; it += (i64)gridDim.x * IWARPS) {
-        const int pair = find_pair(job->pairs, n_pairs, it);
-        if (job->state[pair].state != want) continue;
-        PairDesc P = job->pairs[pair];
+    for (i64 ai = (i64)blockIdx.x * IWARPS + warp; ai < n_act_items; ai += (i64)gridDim.x * IWARPS) {
+        const int a = find_active(job->act_off, n_act, ai);
+        const int pair = job->act_pair[a];
+        const PairDesc P = job->pairs[pair];
+        const i64 it = P.item_off + (ai - job->act_off[a]);
         const int s0 = (int)(it - P.item_off) * ITEM_Q;
         const int count = P.n_src - s0 < ITEM_Q ? P.n_src - s0 : ITEM_Q;
-        __syncwarp();
-        {
-            const int* s = reinterpret_cast<const int*>(&F.trees[P.tree]);
-            int* d = reinterpret_cast<int*>(&s_tree[warp]);
-            for (int i = lane; i < (int)(sizeof(TreeDesc) / 4); i += 32) d[i] = s[i];
-            __syncwarp();
-        }
-        const TreeDesc& T = s_tree[warp];
+        const TreeDesc& T = F.trees[P.tree];
         const double* Tm = job->results[pair].transformation;
-        // cur = src * R^T + t, the oracle's association (types.hpp:110-115)
-        double cx = 0, cy = 0, cz = 0;
-        double bd = 1.7976931348623157e308;
-        int bidx = 0x7fffffff, bpos = -1;
+        int bpos = -1;
         bool cert = false;
         if (lane < count) {
-            const double* p = job->src + 3 * (P.src_off + s0 + lane);
-            double x = p[0], y = p[1], z = p[2];
-            cx = ((x * Tm[0] + y * Tm[1]) + z * Tm[2]) + Tm[3];
-            cy = ((x * Tm[4] + y * Tm[5]) + z * Tm[6]) + Tm[7];
-            cz = ((x * Tm[8] + y * Tm[9]) + z * Tm[10]) + Tm[11];
-            // ---- 1. neighbour-graph walk from the last correspondence
+            double cx, cy, cz;
+            transform_point(Tm, job->src + 3 * (P.src_off + s0 + lane), cx, cy, cz);
             int center = job->match[it * ITEM_Q + lane];  // -1 before the first pass
-            if (center < 0 || center >= T.n) center = greedy_seed(F, T, cx, cy, cz);
+            if (center < 0 || center >= T.n) center = grid_seed(F, job->grid, T, cx, cy, cz);
             if (center >= 0) {
                 const TreePoint* TP = F.pts + T.pt_off;
                 const NbrEntry* TN = job->nbr + T.pt_off * (i64)K;
                 TreePoint c = load_point(TP + center);
-                bd = dist2_rn(c.x, c.y, c.z, cx, cy, cz);
-                bidx = c.idx;
+                double bd = dist2_rn(c.x, c.y, c.z, cx, cy, cz);
+                int bidx = c.idx;
                 bpos = center;
                 if (bd == bd) {
                     for (int hop = 0; hop < MAX_HOPS; ++hop) {
@@ -210,43 +280,92 @@ __global__ void __launch_bounds__(IWARPS * 32) k_icp_iter(const IcpJob* __restri
                         if (cert || bpos == center) break;
                         center = bpos;
                     }
-                } else {  // NaN query: never matches (kdtree.hpp:125 strict <)
-                    bd = 1.7976931348623157e308; bidx = 0x7fffffff; bpos = -1;
+                } else {  // NaN query: never matches (kdtree.hpp:125 strict <); the traversal returns -1 for it
+                    bpos = -1;
                 }
             }
+            if (cert) job->match[it * ITEM_Q + lane] = bpos;
         }
-        // ---- 2. exact tree traversal for the lanes without a certificate
-        unsigned todo = __ballot_sync(0xffffffffu, lane < count && !cert);
-        if (job->stats && lane == 0) {
-            atomicAdd(&job->stats[0], (unsigned long long)count);
-            if (todo) atomicAdd(&job->stats[1], (unsigned long long)__popc(todo));
+        // queue the points without a proof (warp-aggregated append)
+        const unsigned todo = __ballot_sync(0xffffffffu, lane < count && !cert);
+        if (todo) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&job->q_count, __popc(todo));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if ((todo >> lane) & 1u) {
+                FallbackEntry e;
+                e.q = it * ITEM_Q + lane;
+                e.seed = bpos;
+                e.pad = 0;
+                job->queue[base + __popc(todo & lanemask_lt())] = e;
+            }
         }
-        int chain = -1;
-        while (todo) {
-            const int j = __ffs(todo) - 1;
-            todo &= todo - 1u;
-            double qx = shfl_d(cx, j), qy = shfl_d(cy, j), qz = shfl_d(cz, j);
-            double sd = shfl_d(bd, j);
-            int si = __shfl_sync(0xffffffffu, bidx, j), sp = __shfl_sync(0xffffffffu, bpos, j);
-            NearestVisitor V(F, T, qx, qy, qz, lane);
-            if (sp >= 0) { V.best_d = sd; V.best_idx = si; V.best_pos = sp; }
-            else V.seed(chain);
-            traverse(F, T, qx, qy, qz, S, V, lane);
-            chain = V.best_pos;
-            if (lane == j) { bd = V.best_d; bidx = V.best_idx; bpos = V.best_pos; }
+        if (job->stats && lane == 0) {  // SB_ICP_STATS: buckets by iteration: 0, 1, 2..11, >= 12
+            int bkt = job->state[pair].iter;
+            bkt = bkt >= 12 ? 3 : (bkt >= 2 ? 2 : bkt);
+            atomicAdd(&job->stats[2 * bkt], (unsigned long long)count);
+            if (todo) atomicAdd(&job->stats[2 * bkt + 1], (unsigned long long)__popc(todo));
         }
-        const int my_pos = bpos;
-        double tx = 0, ty = 0, tz = 0, nx = 0, ny = 0, nz = 0;
-        const bool ok = lane < count && my_pos >= 0;
-        if (lane < count) job->match[it * ITEM_Q + lane] = my_pos;
-        if (ok) {
-            TreePoint q = load_point(F.pts + T.pt_off + my_pos);
-            tx = q.x; ty = q.y; tz = q.z;
-            const double2* np = reinterpret_cast<const double2*>(job->normals + T.pt_off + my_pos);
-            double2 n01 = __ldg(np), n2 = __ldg(np + 1);
-            nx = n01.x; ny = n01.y; nz = n2.x;
-        } else {
-            cx = cy = cz = 0.0;
+    }
+}
+
+// One warp per queued point: the exact tree traversal, started from the best point of the walk.
+__global__ void __launch_bounds__(IWARPS * 32) k_icp_fallback(IcpJob* __restrict__ job) {
+    __shared__ WarpStack stacks[IWARPS];
+    __shared__ TreeDesc s_tree[IWARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpStack& S = stacks[warp];
+    const ForestView F = job->F;
+    const int n = job->q_count;
+    const int n_pairs = job->n_pairs;
+    for (int e = blockIdx.x * IWARPS + warp; e < n; e += gridDim.x * IWARPS) {
+        const FallbackEntry E = job->queue[e];
+        const i64 it = E.q / ITEM_Q;
+        const int pair = find_pair(job->pairs, n_pairs, it);
+        const PairDesc P = job->pairs[pair];
+        __syncwarp();
+        {
+            const int* s = reinterpret_cast<const int*>(&F.trees[P.tree]);
+            int* d = reinterpret_cast<int*>(&s_tree[warp]);
+            for (int i = lane; i < (int)(sizeof(TreeDesc) / 4); i += 32) d[i] = s[i];
+            __syncwarp();
+        }
+        const TreeDesc& T = s_tree[warp];
+        double qx, qy, qz;
+        transform_point(job->results[pair].transformation, job->src + 3 * (P.src_off + (E.q - P.item_off * ITEM_Q)), qx,
+                        qy, qz);
+        NearestVisitor V(F, T, qx, qy, qz, lane);
+        V.seed(E.seed);
+        traverse(F, T, qx, qy, qz, S, V, lane);
+        if (lane == 0) job->match[E.q] = V.best_pos;
+    }
+}
+
+// Residuals and the 28 sums of one work item from the correspondences in job->match.
+__global__ void __launch_bounds__(IWARPS * 32) k_icp_accum(const IcpJob* __restrict__ job) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const ForestView F = job->F;
+    const i64 n_act_items = job->n_act_items;
+    const int n_act = job->n_act;
+    for (i64 ai = (i64)blockIdx.x * IWARPS + warp; ai < n_act_items; ai += (i64)gridDim.x * IWARPS) {
+        const int a = find_active(job->act_off, n_act, ai);
+        const int pair = job->act_pair[a];
+        const PairDesc P = job->pairs[pair];
+        const i64 it = P.item_off + (ai - job->act_off[a]);
+        const int s0 = (int)(it - P.item_off) * ITEM_Q;
+        const int count = P.n_src - s0 < ITEM_Q ? P.n_src - s0 : ITEM_Q;
+        const i64 pt_off = F.trees[P.tree].pt_off;
+        double cx = 0, cy = 0, cz = 0, tx = 0, ty = 0, tz = 0, nx = 0, ny = 0, nz = 0;
+        if (lane < count) {
+            const int my_pos = job->match[it * ITEM_Q + lane];
+            if (my_pos >= 0) {
+                transform_point(job->results[pair].transformation, job->src + 3 * (P.src_off + s0 + lane), cx, cy, cz);
+                TreePoint q = load_point(F.pts + pt_off + my_pos);
+                tx = q.x; ty = q.y; tz = q.z;
+                const double2* np = reinterpret_cast<const double2*>(job->normals + pt_off + my_pos);
+                double2 n01 = __ldg(np), n2 = __ldg(np + 1);
+                nx = n01.x; ny = n01.y; nz = n2.x;
+            }
         }
         double J[6];
         J[0] = cy * nz - cz * ny;  // p x n, icp.hpp:105
@@ -474,18 +593,24 @@ __global__ void __launch_bounds__(256) k_icp_solve(IcpJob* __restrict__ job, int
     if (mode == 0) {
         // last block to finish decides whether the WHILE node runs another iteration
         __shared__ int s_last;
+        __threadfence();
         __syncthreads();
         if (threadIdx.x == 0) {
-            __threadfence();
             int t = atomicAdd(&job->ticket, 1);
             s_last = (t == (int)gridDim.x - 1);
         }
         __syncthreads();
-        if (s_last && threadIdx.x == 0) {
+        if (s_last) {  // every other block's state updates are visible now
             __threadfence();
-            int active = atomicAdd(&job->n_active, 0);
-            job->ticket = 0;
-            if (use_cond) cudaGraphSetConditional(cond, active > 0 ? 1u : 0u);
+            const int active = *reinterpret_cast<volatile int*>(&job->n_active);
+            // next pass: the pairs still iterating, or — once none is left — the final error pass of the pairs that
+            // ran out of iterations (icp.hpp:235-252)
+            build_active(job, active > 0 ? ST_ACTIVE : ST_EXHAUSTED);
+            if (threadIdx.x == 0) {
+                job->ticket = 0;
+                job->q_count = 0;
+                if (use_cond) cudaGraphSetConditional(cond, active > 0 ? 1u : 0u);
+            }
         }
     }
 }
@@ -561,7 +686,7 @@ struct IcpGraph {
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
     int iter_grid = 0, solve_grid = 0;
-    unsigned long long* d_stats = nullptr;  // SB_ICP_STATS=1: [0] queries, [1] queries that fell back to the tree
+    unsigned long long* d_stats = nullptr;  // SB_ICP_STATS=1: per iteration bucket [queries, queued for the tree]
 };
 
 void icp_graph_free(Ctx* ctx) {
@@ -570,10 +695,12 @@ void icp_graph_free(Ctx* ctx) {
     if (G->exec) cudaGraphExecDestroy(G->exec);
     if (G->graph) cudaGraphDestroy(G->graph);
     if (G->d_stats) {
-        unsigned long long h[2] = {0, 0};
+        unsigned long long h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         cudaMemcpy(h, G->d_stats, sizeof(h), cudaMemcpyDeviceToHost);
-        fprintf(stderr, "[slam_b200] icp nearest-neighbour queries %llu, tree fallbacks %llu (%.3f %%)\n", h[0], h[1],
-                h[0] ? 100.0 * (double)h[1] / (double)h[0] : 0.0);
+        for (int b = 0; b < 4; ++b)
+            fprintf(stderr, "[slam_b200] icp iterations %s: nearest-neighbour queries %llu, tree fallbacks %llu (%.3f %%)\n",
+                    b == 0 ? "0" : b == 1 ? "1" : b == 2 ? "2-11" : ">=12", h[2 * b], h[2 * b + 1],
+                    h[2 * b] ? 100.0 * (double)h[2 * b + 1] / (double)h[2 * b] : 0.0);
         cudaFree(G->d_stats);
     }
     cudaFree(G->d_job);
@@ -595,6 +722,30 @@ static int add_kernel(Ctx* ctx, cudaGraph_t g, cudaGraphNode_t* node, const cuda
     return SB_OK;
 }
 
+// match -> fallback -> accum -> solve(mode) appended to graph g after `dep` (may be null); *last = the solve node
+static int add_pass(Ctx* ctx, IcpGraph* G, cudaGraph_t g, const cudaGraphNode_t* dep, int phase,
+                    cudaGraphConditionalHandle cond, int use_cond, cudaGraphNode_t* last) {
+    IcpJob* job = G->d_job;
+    cudaGraphNode_t n_match, n_fb, n_acc;
+    {
+        void* args[] = {&job};
+        SB_TRY(add_kernel(ctx, g, &n_match, dep, (void*)k_icp_match, G->iter_grid, IWARPS * 32, args));
+    }
+    {
+        void* args[] = {&job};
+        SB_TRY(add_kernel(ctx, g, &n_fb, &n_match, (void*)k_icp_fallback, G->iter_grid, IWARPS * 32, args));
+    }
+    {
+        void* args[] = {&job};
+        SB_TRY(add_kernel(ctx, g, &n_acc, &n_fb, (void*)k_icp_accum, G->iter_grid, IWARPS * 32, args));
+    }
+    {
+        void* args[] = {&job, &phase, &cond, &use_cond};
+        SB_TRY(add_kernel(ctx, g, last, &n_acc, (void*)k_icp_solve, G->solve_grid, 256, args));
+    }
+    return SB_OK;
+}
+
 static int icp_graph_get(Ctx* ctx, IcpGraph** out) {
     if (ctx->icp_graph) {
         *out = static_cast<IcpGraph*>(ctx->icp_graph);
@@ -607,19 +758,19 @@ static int icp_graph_get(Ctx* ctx, IcpGraph** out) {
     G->iter_grid = ctx->sm_count * 8;
     G->solve_grid = ctx->sm_count;
     if (getenv("SB_ICP_STATS")) {
-        SB_CUDA(ctx, cudaMalloc(&G->d_stats, 2 * sizeof(unsigned long long)));
-        SB_CUDA(ctx, cudaMemset(G->d_stats, 0, 2 * sizeof(unsigned long long)));
+        SB_CUDA(ctx, cudaMalloc(&G->d_stats, 8 * sizeof(unsigned long long)));
+        SB_CUDA(ctx, cudaMemset(G->d_stats, 0, 8 * sizeof(unsigned long long)));
     }
     if (getenv("SB_ICP_NOGRAPH")) return SB_OK;
     SB_CUDA(ctx, cudaGraphCreate(&G->graph, 0));
     cudaGraphConditionalHandle cond;
     SB_CUDA(ctx, cudaGraphConditionalHandleCreate(&cond, G->graph, 1, cudaGraphCondAssignDefault));
     IcpJob* job = G->d_job;
-    int one = 1, zero = 0;
-    cudaGraphNode_t n_init, n_while, n_iter, n_solve, n_fiter, n_final;
+    int one = 1;
+    cudaGraphNode_t n_init, n_while, n_body_last, n_final;
     {
         void* args[] = {&job, &cond, &one};
-        SB_TRY(add_kernel(ctx, G->graph, &n_init, nullptr, (void*)k_icp_init, ctx->sm_count, 256, args));
+        SB_TRY(add_kernel(ctx, G->graph, &n_init, nullptr, (void*)k_icp_init, 1, 256, args));
     }
     cudaGraphNodeParams wp = {};
     wp.type = cudaGraphNodeTypeConditional;
@@ -628,22 +779,8 @@ static int icp_graph_get(Ctx* ctx, IcpGraph** out) {
     wp.conditional.size = 1;
     SB_CUDA(ctx, cudaGraphAddNode(&n_while, G->graph, &n_init, 1, &wp));
     cudaGraph_t body = wp.conditional.phGraph_out[0];
-    {
-        void* args[] = {&job, &zero};
-        SB_TRY(add_kernel(ctx, body, &n_iter, nullptr, (void*)k_icp_iter, G->iter_grid, IWARPS * 32, args));
-    }
-    {
-        void* args[] = {&job, &zero, &cond, &one};
-        SB_TRY(add_kernel(ctx, body, &n_solve, &n_iter, (void*)k_icp_solve, G->solve_grid, 256, args));
-    }
-    {
-        void* args[] = {&job, &one};
-        SB_TRY(add_kernel(ctx, G->graph, &n_fiter, &n_while, (void*)k_icp_iter, G->iter_grid, IWARPS * 32, args));
-    }
-    {
-        void* args[] = {&job, &one, &cond, &zero};
-        SB_TRY(add_kernel(ctx, G->graph, &n_final, &n_fiter, (void*)k_icp_solve, G->solve_grid, 256, args));
-    }
+    SB_TRY(add_pass(ctx, G, body, nullptr, 0, cond, 1, &n_body_last));       // icp.hpp:181-232
+    SB_TRY(add_pass(ctx, G, G->graph, &n_while, 1, cond, 0, &n_final));      // icp.hpp:235-255
     SB_CUDA(ctx, cudaGraphInstantiate(&G->exec, G->graph, 0));
     return SB_OK;
 }
@@ -655,7 +792,7 @@ int icp_batch(Ctx* ctx, const Forest* f, const double* d_src, const std::vector<
     if (cfg->max_iterations < 0 || cfg->max_iterations > SB_MAX_ICP_ITERATIONS)
         return fail(ctx, SB_ERR_INVALID_ARG, "icp: max_iterations %d outside [0, %d]", cfg->max_iterations,
                     SB_MAX_ICP_ITERATIONS);
-    if (!f->normals || !f->nbr) return fail(ctx, SB_ERR_INVALID_ARG, "icp: forest has no normals");
+    if (!f->normals || !f->nbr || !f->grid) return fail(ctx, SB_ERR_INVALID_ARG, "icp: forest has no normals");
     IcpGraph* G;
     SB_TRY(icp_graph_get(ctx, &G));
     std::vector<PairDesc> pairs(pairs_in);
@@ -668,17 +805,24 @@ int icp_batch(Ctx* ctx, const Forest* f, const double* d_src, const std::vector<
         n_items += P.n_items;
         if (P.n_src > 0 && f->h_trees[P.tree].n > 0) ++n_valid;
     }
+    if (n_items * ITEM_Q >= 0x7fffffffLL) return fail(ctx, SB_ERR_RANGE, "icp: more than 2^31 source points in one batch");
     PairDesc* d_pairs;
     int* d_match;
     sb_icp_result* d_res;
     PairState* d_state;
     double* d_part;
+    FallbackEntry* d_queue;
+    int* d_act_pair;
+    i64* d_act_off;
     size_t ni = (size_t)(n_items > 0 ? n_items : 1);
     SB_TRY(arena_get(ctx, (size_t)n_pairs, &d_pairs));
     SB_TRY(arena_get(ctx, ni * ITEM_Q, &d_match));
     SB_TRY(arena_get(ctx, (size_t)n_pairs, &d_res));
     SB_TRY(arena_get(ctx, (size_t)n_pairs, &d_state));
     SB_TRY(arena_get(ctx, ni * NSUM, &d_part));
+    SB_TRY(arena_get(ctx, ni * ITEM_Q, &d_queue));
+    SB_TRY(arena_get(ctx, (size_t)n_pairs, &d_act_pair));
+    SB_TRY(arena_get(ctx, (size_t)n_pairs + 1, &d_act_off));
     SB_CUDA(ctx, cudaMemcpyAsync(d_pairs, pairs.data(), sizeof(PairDesc) * n_pairs, cudaMemcpyHostToDevice, ctx->stream));
     SB_CUDA(ctx, cudaMemsetAsync(d_match, 0xff, sizeof(int) * ni * ITEM_Q, ctx->stream));  // -1: no correspondence yet
     IcpJob job;
@@ -687,6 +831,7 @@ int icp_batch(Ctx* ctx, const Forest* f, const double* d_src, const std::vector<
     job.F.trees = f->d_trees;
     job.normals = f->normals;
     job.nbr = f->nbr;
+    job.grid = f->grid;
     job.nbr_k = f->normals_k;
     job.stats = G->d_stats;
     job.src = d_src;
@@ -696,6 +841,9 @@ int icp_batch(Ctx* ctx, const Forest* f, const double* d_src, const std::vector<
     job.results = d_res;
     job.state = d_state;
     job.partials = d_part;
+    job.queue = d_queue;
+    job.act_pair = d_act_pair;
+    job.act_off = d_act_off;
     memcpy(job.T0, cfg->initial_transform, sizeof(job.T0));
     job.tol = cfg->tolerance;
     job.min_err = cfg->min_error;
@@ -703,14 +851,17 @@ int icp_batch(Ctx* ctx, const Forest* f, const double* d_src, const std::vector<
     job.max_it = cfg->max_iterations;
     job.n_active = cfg->max_iterations > 0 ? n_valid : 0;
     job.ticket = 0;
+    job.q_count = 0;
     SB_CUDA(ctx, cudaMemcpyAsync(G->d_job, &job, sizeof(job), cudaMemcpyHostToDevice, ctx->stream));
     if (G->exec) {
         SB_CUDA(ctx, cudaGraphLaunch(G->exec, ctx->stream));
-    } else {  // debugging path (SB_ICP_NOGRAPH=1): same kernels, host-driven loop
+    } else {  // debugging / profiling path (SB_ICP_NOGRAPH=1): same kernels, host-driven loop
         cudaGraphConditionalHandle none = 0;
-        SB_LAUNCH(ctx, k_icp_init, ctx->sm_count, 256, 0, G->d_job, none, 0);
+        SB_LAUNCH(ctx, k_icp_init, 1, 256, 0, G->d_job, none, 0);
         for (int it = 0; it < cfg->max_iterations; ++it) {
-            SB_LAUNCH(ctx, k_icp_iter, G->iter_grid, IWARPS * 32, 0, G->d_job, 0);
+            SB_LAUNCH(ctx, k_icp_match, G->iter_grid, IWARPS * 32, 0, G->d_job);
+            SB_LAUNCH(ctx, k_icp_fallback, G->iter_grid, IWARPS * 32, 0, G->d_job);
+            SB_LAUNCH(ctx, k_icp_accum, G->iter_grid, IWARPS * 32, 0, G->d_job);
             SB_LAUNCH(ctx, k_icp_solve, G->solve_grid, 256, 0, G->d_job, 0, none, 0);
             if ((it & 3) == 3) {
                 int active = 0;
@@ -719,23 +870,18 @@ int icp_batch(Ctx* ctx, const Forest* f, const double* d_src, const std::vector<
                 if (active <= 0) break;
             }
         }
-        SB_LAUNCH(ctx, k_icp_iter, G->iter_grid, IWARPS * 32, 0, G->d_job, 1);
+        SB_LAUNCH(ctx, k_icp_match, G->iter_grid, IWARPS * 32, 0, G->d_job);
+        SB_LAUNCH(ctx, k_icp_fallback, G->iter_grid, IWARPS * 32, 0, G->d_job);
+        SB_LAUNCH(ctx, k_icp_accum, G->iter_grid, IWARPS * 32, 0, G->d_job);
         SB_LAUNCH(ctx, k_icp_solve, G->solve_grid, 256, 0, G->d_job, 1, none, 0);
     }
     SB_CUDA(ctx, cudaMemcpyAsync(results, d_res, sizeof(sb_icp_result) * n_pairs, cudaMemcpyDeviceToHost, ctx->stream));
     SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (G->exec) {
-        int max_hist = 1;
-        for (int p = 0; p < n_pairs; ++p)
-            if (results[p].history_len > max_hist) max_hist = results[p].history_len;
-        ctx->launches += 3 + 2 * (i64)(max_hist - 1);
-    }
-    {
-        int max_hist = 1;
-        for (int p = 0; p < n_pairs; ++p)
-            if (results[p].history_len > max_hist) max_hist = results[p].history_len;
-        ctx->last_icp_iterations = max_hist;
-    }
+    int max_hist = 1;
+    for (int p = 0; p < n_pairs; ++p)
+        if (results[p].history_len > max_hist) max_hist = results[p].history_len;
+    if (G->exec) ctx->launches += 5 + 4 * (i64)(max_hist - 1);  // init + 4 per loop pass + 4 of the final pass
+    ctx->last_icp_iterations = max_hist;
     return SB_OK;
 }
 

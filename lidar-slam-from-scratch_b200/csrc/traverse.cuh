@@ -27,6 +27,22 @@ struct ForestView {
     const TreeDesc* __restrict__ trees;
 };
 
+// ---- seed grid (GridSlot, common.cuh): cell coordinates are offset by +1 so that the cells just outside the
+// bounding box are representable; 21 bits per axis.
+#define SB_GRID_EMPTY 0xffffffffffffffffull
+__device__ __forceinline__ bool grid_cell(const TreeDesc& T, double x, double y, double z, int& ix, int& iy, int& iz) {
+    double fx = floor((x - T.glo[0]) * T.ginv), fy = floor((y - T.glo[1]) * T.ginv), fz = floor((z - T.glo[2]) * T.ginv);
+    if (!(fx >= -1.0 && fx < 2097150.0 && fy >= -1.0 && fy < 2097150.0 && fz >= -1.0 && fz < 2097150.0)) return false;
+    ix = (int)fx + 1; iy = (int)fy + 1; iz = (int)fz + 1;
+    return true;
+}
+__device__ __forceinline__ unsigned long long grid_key(int ix, int iy, int iz) {
+    return (unsigned long long)ix | ((unsigned long long)iy << 21) | ((unsigned long long)iz << 42);
+}
+__device__ __forceinline__ unsigned grid_hash(unsigned long long key, int shift) {
+    return (unsigned)((key * 0x9E3779B97F4A7C15ull) >> shift);
+}
+
 // one 32-byte sector as two 16-byte read-only loads
 __device__ __forceinline__ TreePoint load_point(const TreePoint* p) {
     const int4* q = reinterpret_cast<const int4*>(p);
