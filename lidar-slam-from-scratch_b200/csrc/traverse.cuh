@@ -60,21 +60,41 @@ __device__ __forceinline__ bool lex_less(double da, int ia, double db, int ib) {
     return da < db || (da == db && ia < ib);
 }
 
+// What is searched for: a point, or (self k-NN of a whole leaf at once) the bounding box of a packet of queries.
+// lb() is a conservative lower bound of the squared distance from the query to a box given as 3 float2
+// (lo.x lo.y | lo.z hi.x | hi.y hi.z; lo rounded down, hi rounded up): a few ulps shaved off, then rounded towards
+// -inf into a float.
+struct PointQuery {
+    double x, y, z;
+    __device__ __forceinline__ float lb(float2 b0, float2 b1, float2 b2) const {
+        double ex = fmax(fmax((double)b0.x - x, x - (double)b1.y), 0.0);
+        double ey = fmax(fmax((double)b0.y - y, y - (double)b2.x), 0.0);
+        double ez = fmax(fmax((double)b1.x - z, z - (double)b2.y), 0.0);
+        double d = (ex * ex + ey * ey) + ez * ez;
+        return __double2float_rd(d * (1.0 - 1.0e-14));
+    }
+};
+struct BoxQuery {
+    double lox, loy, loz, hix, hiy, hiz;
+    __device__ __forceinline__ float lb(float2 b0, float2 b1, float2 b2) const {
+        double ex = fmax(fmax((double)b0.x - hix, lox - (double)b1.y), 0.0);
+        double ey = fmax(fmax((double)b0.y - hiy, loy - (double)b2.x), 0.0);
+        double ez = fmax(fmax((double)b1.x - hiz, loz - (double)b2.y), 0.0);
+        double d = (ex * ex + ey * ey) + ez * ez;
+        return __double2float_rd(d * (1.0 - 1.0e-14));
+    }
+};
+
 // Tests the (up to 32) boxes [first, first+32) of `level` against the query; records the survivors.
+template <class Query>
 __device__ __forceinline__ void test_children(const ForestView& F, const TreeDesc& T, int level, int first,
-                                              double qx, double qy, double qz, double tau, WarpStack& S, int lane) {
+                                              const Query& Q, double tau, WarpStack& S, int lane) {
     int ci = first + lane;
     bool valid = ci < T.box_cnt[level];
     float dmf = __int_as_float(0x7f800000);
     if (valid) {
         const float2* b = reinterpret_cast<const float2*>(F.boxes + 6 * (T.box_off[level] + ci));
-        float2 b0 = b[0], b1 = b[1], b2 = b[2];  // lo.x lo.y | lo.z hi.x | hi.y hi.z
-        double ex = fmax(fmax((double)b0.x - qx, qx - (double)b1.y), 0.0);
-        double ey = fmax(fmax((double)b0.y - qy, qy - (double)b2.x), 0.0);
-        double ez = fmax(fmax((double)b1.x - qz, qz - (double)b2.y), 0.0);
-        double d = (ex * ex + ey * ey) + ez * ez;
-        // conservative: shave a few ulps, then round towards -inf into a float
-        dmf = __double2float_rd(d * (1.0 - 1.0e-14));
+        dmf = Q.lb(b[0], b[1], b[2]);
     }
     bool pass = valid && !((double)dmf > tau);
     unsigned m = __ballot_sync(0xffffffffu, pass);
@@ -85,13 +105,13 @@ __device__ __forceinline__ void test_children(const ForestView& F, const TreeDes
 
 // Generic nearest-first traversal.  V must provide:
 //   double tau() const            — current pruning bound (k-th best d2; +inf/DBL_MAX while the list is not full)
-//   void leaf(int p0, int cnt)    — visit sorted points [p0, p0+cnt) (absolute indices into the SoA arrays)
-template <class Visitor>
-__device__ __forceinline__ void traverse(const ForestView& F, const TreeDesc& T, double qx, double qy, double qz,
-                                         WarpStack& S, Visitor& V, int lane) {
+//   void leaf(int p0, int cnt)    — visit sorted points [p0, p0+cnt) (cloud-local positions)
+template <class Query, class Visitor>
+__device__ __forceinline__ void traverse(const ForestView& F, const TreeDesc& T, const Query& Q, WarpStack& S,
+                                         Visitor& V, int lane) {
     if (T.n <= 0) return;
     int level = T.top;
-    test_children(F, T, level, 0, qx, qy, qz, V.tau(), S, lane);
+    test_children(F, T, level, 0, Q, V.tau(), S, lane);
     while (true) {
         unsigned m = S.mask[level];
         if (m == 0u) {
@@ -115,9 +135,17 @@ __device__ __forceinline__ void traverse(const ForestView& F, const TreeDesc& T,
             V.leaf(p0, cnt > 32 ? 32 : cnt);
         } else {
             --level;
-            test_children(F, T, level, node * 32, qx, qy, qz, V.tau(), S, lane);
+            test_children(F, T, level, node * 32, Q, V.tau(), S, lane);
         }
     }
+}
+
+template <class Visitor>
+__device__ __forceinline__ void traverse(const ForestView& F, const TreeDesc& T, double qx, double qy, double qz,
+                                         WarpStack& S, Visitor& V, int lane) {
+    PointQuery Q;
+    Q.x = qx; Q.y = qy; Q.z = qz;
+    traverse(F, T, Q, S, V, lane);
 }
 
 // -------------------------------------------------------------------------------------------------------------
