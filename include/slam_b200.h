@@ -107,6 +107,9 @@ int sb_ctx_stage_ms(sb_ctx* ctx, double* ms7);
 /* host wall-clock milliseconds between the same marks (enqueue + host-side bookkeeping of each stage) */
 int sb_ctx_stage_host_ms(sb_ctx* ctx, double* ms7);
 int sb_ctx_last_counts(sb_ctx* ctx, int64_t* counts5);
+/* which voxel-grid pipeline the last call on this context used: 1 = one-pass hashed fixed-point sums (float32-born
+ * scans), 2 = sort-based (any fp64 input, any key range); 0 = none yet.  Both give the same rows, bit for bit. */
+int sb_ctx_last_voxel_path(const sb_ctx* ctx);
 void sb_default_icp_config(sb_icp_config* cfg);
 void sb_default_loop_config(sb_loop_config* cfg);
 

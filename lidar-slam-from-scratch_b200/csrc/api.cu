@@ -3,6 +3,7 @@
 // There is no CPU implementation of any stage behind these entry points.
 #include <chrono>
 #include <cstdarg>
+#include <cstdlib>
 #include <algorithm>
 
 #include "common.cuh"
@@ -234,6 +235,7 @@ int sb_ctx_create(int device, void* stream, sb_ctx** out) {
         }
         c->c.own_stream = true;
     }
+    c->c.vox_force_sort = getenv("SB_VOXEL_SORT") != nullptr;
     if (cudaMalloc(&c->c.d_flags, sizeof(int)) != cudaSuccess) {
         delete c;
         return SB_ERR_CUDA;
@@ -306,6 +308,8 @@ int sb_ctx_last_counts(sb_ctx* ctx, int64_t* counts5) {
     counts5[4] = ctx->c.last_icp_iterations;
     return SB_OK;
 }
+
+int sb_ctx_last_voxel_path(const sb_ctx* ctx) { return ctx ? ctx->c.vox_last_path : 0; }
 
 void sb_default_icp_config(sb_icp_config* cfg) {  // types.hpp:143-148, icp.hpp:170
     cfg->max_iterations = 50;

@@ -66,6 +66,11 @@ struct Ctx {
     int* d_flags = nullptr;
     // cached ICP loop graph (icp.cu)
     void* icp_graph = nullptr;
+    // voxel.cu: slots of the per-cloud voxel hash table per input row (raised to 2 after a table overflowed),
+    // SB_VOXEL_SORT=1 forces the sort-based path, and which path the last call took (1 hashed, 2 sorted)
+    double vox_slots_per_point = 0.25;
+    bool vox_force_sort = false;
+    int vox_last_path = 0;
     // optional per-stage CUDA-event timing of the last pipeline call (bench.py's roofline figures)
     bool profiling = false;
     cudaEvent_t ev[32];

@@ -7,6 +7,16 @@
 // batch-wide key minimum, stable segmented radix sort (scan_sort.cu), run-start flags + exclusive scan for the
 // compaction, and one thread per voxel that adds its members in sorted (= ascending input) order with __dadd_rn.
 // Output rows are ascending in (kx, ky, kz) inside each cloud.
+//
+// That sort-based pipeline is the GENERAL path.  Scans that come from a float32 file (file_utils.cpp:91-97 widens
+// float32 to double) take a one-pass FAST path first: every point is hashed into a per-cloud table of voxels and its
+// coordinates are added to the voxel's sums as 20.44 fixed-point integers with 64-bit atomics.  Integer addition
+// is exact and order-free.  When every member coordinate of a voxel is a multiple of 2^g and sum|v| < 2^(53+g),
+// every partial sum of the reference's left-to-right fp64 loop is a multiple of 2^g below 2^(53+g), i.e. exactly
+// representable — so that loop never rounds and its result IS the integer sum.  The kernel proves this per voxel
+// and axis with g = -33 (every float32 of magnitude >= 2^-10) or, flagged, g = -44.  Voxels that cannot be proven
+// exact (a member finer than 2^-44, or too large a sum) are re-summed in input order from a list of their members;
+// if there are too many of them, or keys do not fit 21 bits per axis, the call falls back to the sort.
 #include "common.cuh"
 
 namespace sb {
@@ -128,8 +138,9 @@ static int bits_for(u64 range) {
     return b;
 }
 
-int voxel_downsample_dev(Ctx* ctx, const double* d_xyz, const i64* h_off, int n_clouds, double voxel,
-                         double* d_out_xyz, i64* h_out_off, i64* d_out_keys) {
+// General path: any key range that packs into 64 bits, any fp64 input.
+static int voxel_sorted_dev(Ctx* ctx, const double* d_xyz, const i64* h_off, int n_clouds, double voxel,
+                            double* d_out_xyz, i64* h_out_off, i64* d_out_keys) {
     i64 n = h_off[n_clouds];
     if (h_off[0] != 0) return fail(ctx, SB_ERR_INVALID_ARG, "voxel: offsets must start at 0");
     if (n >= (i64)0xffffffffLL) return fail(ctx, SB_ERR_RANGE, "voxel: more than 2^32-1 rows in one call");
@@ -198,6 +209,428 @@ int voxel_downsample_dev(Ctx* ctx, const double* d_xyz, const i64* h_off, int n_
     SB_CUDA(ctx, cudaMemcpyAsync(h_out_off, d_out_off, sizeof(i64) * (n_clouds + 1), cudaMemcpyDeviceToHost, ctx->stream));
     SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return SB_OK;
+}
+
+// =============================================================================================================
+// fast path
+// =============================================================================================================
+static constexpr int VQ_BITS = 44;                     // fixed-point fraction bits
+static constexpr double VQ_SCALE = 17592186044416.0;   // 2^44
+static constexpr int VQ_COARSE_TZ = 11;                // a coordinate is "coarse" if it is a multiple of 2^(11-44)
+static constexpr double VQ_LIMIT_COARSE = 524288.0;    // 2^19: sum|v| below this -> no wrap, fp64 loop exact (coarse)
+static constexpr double VQ_LIMIT_FINE = 512.0;         // 2^(53-44): sum|v| bound when some member is finer
+static constexpr int VK_BIAS = 1 << 20;                // keys are packed as (k + 2^20), 21 bits per axis
+static constexpr int VROWS = 4;                        // rows per thread and block iteration
+static constexpr int VTILE = 256 * VROWS;              // rows per block iteration
+static constexpr int PATCH_CAP = 4096;                 // members of unproven voxels that the patch-up pass can take
+#define VOX_EMPTY 0xffffffffffffffffull
+enum { FLAG_TABLE_FULL = 4, FLAG_PATCH_OVERFLOW = 8 };
+// VoxSlot::flags while inserting: bit a (0..2): a member's coordinate a is finer than 2^-33; bit 3: finer than
+// 2^-44 (not representable in the sums).  After k_vox_finalize: 0, or 1 + output row of a voxel that needs the
+// ordered sum.
+enum { VF_FINE_X = 1, VF_FINE_Y = 2, VF_FINE_Z = 4, VF_UNREPRESENTABLE = 8 };
+
+struct VoxCloud {   // per cloud, device-resident
+    i64 pt_off;     // first input row
+    i64 tab_off;    // first slot of the cloud's table
+    i64 tile_off;   // first tile (VTILE rows) of the cloud
+    int n;
+    unsigned mask;  // slots - 1
+};
+
+// one voxel of a cloud's hash table: 48 bytes, at most two 32-byte sectors
+struct alignas(16) VoxSlot {
+    unsigned long long key;   // packed (kx, ky, kz) or VOX_EMPTY
+    long long sx, sy, sz;     // fixed-point sums of the member coordinates
+    unsigned cnt;
+    unsigned flags;
+    unsigned long long pad;
+};
+
+// fixed-point image of a coordinate; bit: this axis' "fine" flag
+__device__ __forceinline__ long long vox_fixed(double v, unsigned bit, unsigned* fl) {
+    double t = v * VQ_SCALE;  // exact: a power of two
+    long long f = (long long)t;
+    if (!(t == rint(t) && fabs(t) < 4.0e18)) *fl |= VF_UNREPRESENTABLE;
+    else if (f != 0 && (f & ((1ll << VQ_COARSE_TZ) - 1)) != 0) *fl |= bit;
+    return f;
+}
+
+// hash + accumulate.  mm: [0..2] min keys, [3..5] max keys; n_vox[c]: distinct voxels of cloud c.
+__global__ void __launch_bounds__(256) k_vox_insert(const double* __restrict__ xyz, const VoxCloud* __restrict__ clouds,
+                                                    const int* __restrict__ tile_cloud, i64 n_tiles, double voxel,
+                                                    VoxSlot* __restrict__ table, unsigned* __restrict__ slot_of_point,
+                                                    int* __restrict__ n_vox, i64* __restrict__ mm,
+                                                    int* __restrict__ flags) {
+    __shared__ i64 s_red[8][6];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    i64 lo[3] = {INT64_MAX, INT64_MAX, INT64_MAX}, hi[3] = {INT64_MIN, INT64_MIN, INT64_MIN};
+    int bad = 0;
+    for (i64 tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int c = tile_cloud[tile];
+        const VoxCloud C = clouds[c];
+        const i64 t0 = (tile - C.tile_off) * VTILE;
+        VoxSlot* tab = table + C.tab_off;
+#pragma unroll
+        for (int r = 0; r < VROWS; ++r) {
+            const i64 i = t0 + r * 256 + threadIdx.x;  // row inside the cloud
+            unsigned slot = 0xffffffffu - (unsigned)lane;  // lanes without a voxel never share a run
+            long long fx = 0, fy = 0, fz = 0;
+            unsigned fl = 0u;
+            if (i < C.n) {
+                const double* p = xyz + 3 * (C.pt_off + i);
+                const double x = p[0], y = p[1], z = p[2];
+                i64 kx, ky, kz;
+                bool ok = voxel_key(x, voxel, &kx) & voxel_key(y, voxel, &ky) & voxel_key(z, voxel, &kz);
+                if (!ok) {
+                    bad |= FLAG_NONFINITE;
+                } else if (kx < -VK_BIAS || kx >= VK_BIAS || ky < -VK_BIAS || ky >= VK_BIAS || kz < -VK_BIAS ||
+                           kz >= VK_BIAS) {
+                    bad |= FLAG_KEY_RANGE;
+                } else {
+                    lo[0] = min(lo[0], kx); hi[0] = max(hi[0], kx);
+                    lo[1] = min(lo[1], ky); hi[1] = max(hi[1], ky);
+                    lo[2] = min(lo[2], kz); hi[2] = max(hi[2], kz);
+                    const unsigned long long key = ((unsigned long long)(kx + VK_BIAS) << 42) |
+                                                   ((unsigned long long)(ky + VK_BIAS) << 21) |
+                                                   (unsigned long long)(kz + VK_BIAS);
+                    unsigned s = (unsigned)((key * 0x9E3779B97F4A7C15ull) >> 32) & C.mask;
+                    unsigned probes = 0;
+                    while (true) {
+                        unsigned long long cur = __ldcg(&tab[s].key);
+                        if (cur == VOX_EMPTY) {
+                            cur = atomicCAS(&tab[s].key, VOX_EMPTY, key);
+                            if (cur == VOX_EMPTY) {
+                                atomicAdd(&n_vox[c], 1);
+                                cur = key;
+                            }
+                        }
+                        if (cur == key) { slot = s; break; }
+                        s = (s + 1u) & C.mask;
+                        if (++probes > C.mask) { bad |= FLAG_TABLE_FULL; break; }
+                    }
+                    slot_of_point[C.pt_off + i] = slot;
+                    fx = vox_fixed(x, VF_FINE_X, &fl);
+                    fy = vox_fixed(y, VF_FINE_Y, &fl);
+                    fz = vox_fixed(z, VF_FINE_Z, &fl);
+                }
+            }
+            // runs of consecutive lanes in the same voxel (neighbouring rays) add up inside the warp first: a segmented
+            // inclusive scan, integers, exact in any order; the last lane of a run sends the run to the table
+            const unsigned prev_slot = __shfl_up_sync(0xffffffffu, slot, 1);
+            const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || slot != prev_slot);
+            const int run_start = 31 - __clz(heads & (lanemask_lt() | (1u << lane)));
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const long long ox = __shfl_up_sync(0xffffffffu, fx, d), oy = __shfl_up_sync(0xffffffffu, fy, d),
+                                oz = __shfl_up_sync(0xffffffffu, fz, d);
+                const unsigned of = __shfl_up_sync(0xffffffffu, fl, d);
+                if (lane - d >= run_start) {
+                    fx += ox; fy += oy; fz += oz;
+                    fl |= of;
+                }
+            }
+            const bool tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
+            if (tail && slot < 0xffffffe0u) {
+                VoxSlot* S = tab + slot;
+                atomicAdd(reinterpret_cast<unsigned long long*>(&S->sx), (unsigned long long)fx);
+                atomicAdd(reinterpret_cast<unsigned long long*>(&S->sy), (unsigned long long)fy);
+                atomicAdd(reinterpret_cast<unsigned long long*>(&S->sz), (unsigned long long)fz);
+                atomicAdd(&S->cnt, (unsigned)(lane - run_start + 1));
+                if (fl) atomicOr(&S->flags, fl);
+            }
+        }
+    }
+    // key range + flags of this block
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[a] = min(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+            hi[a] = max(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+    if (lane == 0) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { s_red[warp][a] = lo[a]; s_red[warp][3 + a] = hi[a]; }
+        if (bad) atomicOr(flags, bad);
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        const int a = threadIdx.x;
+        i64 v = s_red[0][a];
+        for (int w = 1; w < 8; ++w) v = a < 3 ? min(v, s_red[w][a]) : max(v, s_red[w][a]);
+        if (a < 3) { if (v != INT64_MAX) atomicMin(&mm[a], v); }
+        else if (v != INT64_MIN) atomicMax(&mm[a], v);
+    }
+}
+
+// empty table: key = VOX_EMPTY, everything else 0
+__global__ void __launch_bounds__(256) k_vox_clear(VoxSlot* __restrict__ table, i64 n_slots) {
+    const i64 g = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_slots) return;
+    uint4* w = reinterpret_cast<uint4*>(table + g);
+    w[0] = make_uint4(0xffffffffu, 0xffffffffu, 0u, 0u);
+    w[1] = make_uint4(0u, 0u, 0u, 0u);
+    w[2] = make_uint4(0u, 0u, 0u, 0u);
+}
+
+// occupied slots -> per-cloud compact (relative key, slot) lists.  Tables are multiples of 256 slots, so the 256
+// slots of a block belong to one cloud: one cursor atomic per block.
+__global__ void __launch_bounds__(256) k_vox_list(const VoxCloud* __restrict__ clouds, int n_clouds, i64 n_slots,
+                                                  const VoxSlot* __restrict__ table, const i64* __restrict__ out_off,
+                                                  int* __restrict__ cursor, VoxelPack P, u64* __restrict__ lst_key,
+                                                  uint32_t* __restrict__ lst_slot) {
+    __shared__ int s_wcnt[8];
+    __shared__ i64 s_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const i64 g = (i64)blockIdx.x * 256 + threadIdx.x;
+    const unsigned long long key = g < n_slots ? table[g].key : VOX_EMPTY;
+    const bool occ = key != VOX_EMPTY;
+    const unsigned bal = __ballot_sync(0xffffffffu, occ);
+    if (lane == 0) s_wcnt[warp] = __popc(bal);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int total = 0;
+        for (int w = 0; w < 8; ++w) { int c = s_wcnt[w]; s_wcnt[w] = total; total += c; }
+        i64 base = 0;
+        if (total > 0) {
+            const i64 g0 = (i64)blockIdx.x * 256;
+            int lo = 0, hi = n_clouds;  // cloud of the block's slots
+            while (hi - lo > 1) {
+                int mid = (lo + hi) >> 1;
+                if (clouds[mid].tab_off <= g0) lo = mid; else hi = mid;
+            }
+            base = out_off[lo] + atomicAdd(&cursor[lo], total);
+        }
+        s_base = base;
+    }
+    __syncthreads();
+    if (!occ) return;
+    const i64 kx = (i64)(key >> 42) - VK_BIAS, ky = (i64)((key >> 21) & 0x1fffffu) - VK_BIAS,
+              kz = (i64)(key & 0x1fffffu) - VK_BIAS;
+    const i64 dst = s_base + s_wcnt[warp] + __popc(bal & lanemask_lt());
+    lst_key[dst] = ((u64)(kx - P.minx) << P.sx) | ((u64)(ky - P.miny) << P.sy) | (u64)(kz - P.minz);
+    lst_slot[dst] = (uint32_t)g;
+}
+
+// one thread per output voxel (sorted by key): centroid from the integer sums, or a request for the ordered sum
+__global__ void __launch_bounds__(256) k_vox_finalize(const u64* __restrict__ keys, const uint32_t* __restrict__ slots,
+                                                      i64 m, double voxel, VoxelPack P, VoxSlot* __restrict__ table,
+                                                      double* __restrict__ out_xyz, i64* __restrict__ out_keys) {
+    const i64 v = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= m) return;
+    const u64 k = keys[v];
+    VoxSlot* S = table + slots[v];
+    const i64 kk[3] = {(i64)(P.sx >= 64 ? 0ull : (k >> P.sx)) + P.minx, (i64)((k >> P.sy) & P.mask_y) + P.miny,
+                       (i64)(k & P.mask_z) + P.minz};
+    const unsigned cnt = S->cnt, fl = S->flags;
+    const double dc = (double)cnt;
+    // |member| <= (|key| + 1) * voxel bounds B = the sum of the absolute values on each axis.  The 64-bit sums did
+    // not wrap and — all members being multiples of 2^-33 — the fp64 loop was exact if B < 2^19; if some member is
+    // finer (but a multiple of 2^-44) the loop was exact if B < 2^9.
+    bool proven = !(fl & VF_UNREPRESENTABLE);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const double B = dc * ((double)(kk[a] < 0 ? -kk[a] : kk[a]) + 1.0) * voxel * 1.0001;
+        proven = proven && B < ((fl >> a) & 1u ? VQ_LIMIT_FINE : VQ_LIMIT_COARSE);
+    }
+    S->flags = proven ? 0u : (unsigned)(v + 1);
+    out_xyz[3 * v + 0] = __ddiv_rn((double)S->sx / VQ_SCALE, dc);  // file_utils.cpp:191
+    out_xyz[3 * v + 1] = __ddiv_rn((double)S->sy / VQ_SCALE, dc);
+    out_xyz[3 * v + 2] = __ddiv_rn((double)S->sz / VQ_SCALE, dc);
+    if (out_keys) { out_keys[3 * v + 0] = kk[0]; out_keys[3 * v + 1] = kk[1]; out_keys[3 * v + 2] = kk[2]; }
+}
+
+// members of the voxels that asked for the ordered sum: (output row << 32 | input row)
+__global__ void __launch_bounds__(256) k_vox_collect(const VoxCloud* __restrict__ clouds,
+                                                     const int* __restrict__ tile_cloud, i64 n_tiles,
+                                                     const unsigned* __restrict__ slot_of_point,
+                                                     const VoxSlot* __restrict__ table, u64* __restrict__ list,
+                                                     int* __restrict__ list_n, int* __restrict__ flags) {
+    for (i64 tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const VoxCloud C = clouds[tile_cloud[tile]];
+        const i64 t0 = (tile - C.tile_off) * VTILE;
+#pragma unroll
+        for (int r = 0; r < VROWS; ++r) {
+            const i64 i = t0 + r * 256 + threadIdx.x;
+            if (i >= C.n) continue;
+            const unsigned row1 = __ldg(&table[C.tab_off + slot_of_point[C.pt_off + i]].flags);
+            if (row1 == 0u) continue;
+            const int at = atomicAdd(list_n, 1);
+            if (at < PATCH_CAP) list[at] = ((u64)(row1 - 1u) << 32) | (u64)(C.pt_off + i);
+            else atomicOr(flags, FLAG_PATCH_OVERFLOW);
+        }
+    }
+}
+
+// one block: bitonic sort of the member list, then one thread per voxel run adds its members in input order
+__global__ void __launch_bounds__(1024) k_vox_patch(const double* __restrict__ xyz, u64* __restrict__ list,
+                                                    const int* __restrict__ list_n, double* __restrict__ out_xyz) {
+    __shared__ u64 s[PATCH_CAP];
+    int n = *list_n;
+    if (n <= 0) return;
+    if (n > PATCH_CAP) n = PATCH_CAP;  // overflow: the host discards this result
+    int cap = 2;
+    while (cap < n) cap <<= 1;
+    for (int i = threadIdx.x; i < cap; i += 1024) s[i] = i < n ? list[i] : ~0ull;
+    __syncthreads();
+    for (int k = 2; k <= cap; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < cap; i += 1024) {
+                int l = i ^ j;
+                if (l > i) {
+                    u64 a = s[i], b = s[l];
+                    bool up = (i & k) == 0;
+                    if ((a > b) == up) { s[i] = b; s[l] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = threadIdx.x; i < n; i += 1024) {
+        const u64 e = s[i];
+        if (i > 0 && (s[i - 1] >> 32) == (e >> 32)) continue;  // not the first member of its voxel
+        double sx = 0.0, sy = 0.0, sz = 0.0;
+        int j = i;
+        do {  // members in ascending input row, file_utils.cpp:186-190
+            const double* p = xyz + 3 * (i64)(s[j] & 0xffffffffull);
+            sx = __dadd_rn(sx, p[0]); sy = __dadd_rn(sy, p[1]); sz = __dadd_rn(sz, p[2]);
+            ++j;
+        } while (j < n && (s[j] >> 32) == (e >> 32));
+        const double cnt = (double)(j - i);
+        const i64 v = (i64)(e >> 32);
+        out_xyz[3 * v + 0] = __ddiv_rn(sx, cnt);
+        out_xyz[3 * v + 1] = __ddiv_rn(sy, cnt);
+        out_xyz[3 * v + 2] = __ddiv_rn(sz, cnt);
+    }
+}
+
+// returns SB_OK with *done = 1 if the fast path produced the result, *done = 0 if the caller must use the sort
+static int voxel_hashed_dev(Ctx* ctx, const double* d_xyz, const i64* h_off, int n_clouds, double voxel,
+                            double* d_out_xyz, i64* h_out_off, i64* d_out_keys, int* done) {
+    *done = 0;
+    const i64 n = h_off[n_clouds];
+    if (n >= (i64)0xffffffffLL) return SB_OK;
+    // ---- per-cloud tables: a power of two of slots, vox_slots_per_point * rows (the ratio adapts, see below)
+    std::vector<VoxCloud> hc((size_t)n_clouds);
+    i64 n_slots = 0, n_tiles = 0;
+    for (int c = 0; c < n_clouds; ++c) {
+        VoxCloud& C = hc[c];
+        i64 nc = h_off[c + 1] - h_off[c];
+        if (nc > 0x7fffffffLL) return SB_OK;
+        i64 want = (i64)(ctx->vox_slots_per_point * (double)nc);
+        i64 sl = 256;
+        while (sl < want) sl <<= 1;
+        if (sl > 0x40000000LL) return SB_OK;
+        C.pt_off = h_off[c];
+        C.tab_off = n_slots;
+        C.tile_off = n_tiles;
+        C.n = (int)nc;
+        C.mask = (unsigned)(sl - 1);
+        n_slots += sl;
+        n_tiles += (nc + VTILE - 1) / VTILE;
+    }
+    if (n_slots >= (i64)0xffffffffLL) return SB_OK;
+    std::vector<int> h_tile_cloud((size_t)n_tiles);
+    for (int c = 0; c < n_clouds; ++c) {
+        i64 t1 = c + 1 < n_clouds ? hc[c + 1].tile_off : n_tiles;
+        for (i64 t = hc[c].tile_off; t < t1; ++t) h_tile_cloud[(size_t)t] = c;
+    }
+    VoxCloud* d_clouds;
+    int* d_tile_cloud;
+    VoxSlot* d_table;
+    unsigned* d_slot_of;
+    int *d_nvox, *d_cursor, *d_list_n;
+    i64* d_mm;
+    u64* d_list;
+    SB_TRY(arena_get(ctx, (size_t)n_clouds, &d_clouds));
+    SB_TRY(arena_get(ctx, (size_t)(n_tiles > 0 ? n_tiles : 1), &d_tile_cloud));
+    SB_TRY(arena_get(ctx, (size_t)n_slots, &d_table));
+    SB_TRY(arena_get(ctx, (size_t)n, &d_slot_of));
+    SB_TRY(arena_get(ctx, (size_t)2 * n_clouds + 1, &d_nvox));
+    SB_TRY(arena_get(ctx, 6, &d_mm));
+    SB_TRY(arena_get(ctx, (size_t)PATCH_CAP, &d_list));
+    d_cursor = d_nvox + n_clouds;
+    d_list_n = d_nvox + 2 * n_clouds;
+    SB_CUDA(ctx, cudaMemcpyAsync(d_clouds, hc.data(), sizeof(VoxCloud) * n_clouds, cudaMemcpyHostToDevice, ctx->stream));
+    SB_CUDA(ctx, cudaMemcpyAsync(d_tile_cloud, h_tile_cloud.data(), sizeof(int) * (size_t)n_tiles, cudaMemcpyHostToDevice,
+                                 ctx->stream));
+    SB_LAUNCH(ctx, k_vox_clear, ceil_div(n_slots, 256), 256, 0, d_table, n_slots);
+    SB_CUDA(ctx, cudaMemsetAsync(d_nvox, 0, sizeof(int) * (2 * (size_t)n_clouds + 1), ctx->stream));
+    SB_CUDA(ctx, cudaMemsetAsync(ctx->d_flags, 0, sizeof(int), ctx->stream));
+    i64 init[6] = {INT64_MAX, INT64_MAX, INT64_MAX, INT64_MIN, INT64_MIN, INT64_MIN};
+    SB_CUDA(ctx, cudaMemcpyAsync(d_mm, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+    const int pgrid = (int)(n_tiles < (i64)ctx->sm_count * 8 ? n_tiles : (i64)ctx->sm_count * 8);
+    SB_LAUNCH(ctx, k_vox_insert, pgrid, 256, 0, d_xyz, d_clouds, d_tile_cloud, n_tiles, voxel, d_table, d_slot_of, d_nvox,
+              d_mm, ctx->d_flags);
+    // ---- the only host round trip: flags, key range, voxels per cloud
+    std::vector<int> nvox((size_t)n_clouds);
+    i64 mm[6];
+    int flags = 0;
+    SB_CUDA(ctx, cudaMemcpyAsync(nvox.data(), d_nvox, sizeof(int) * n_clouds, cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(ctx, cudaMemcpyAsync(mm, d_mm, sizeof(mm), cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(ctx, cudaMemcpyAsync(&flags, ctx->d_flags, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (flags & FLAG_NONFINITE) return fail(ctx, SB_ERR_RANGE, "voxel: non-finite coordinate or |coord/voxel| >= 4e18");
+    if (flags & FLAG_TABLE_FULL) {  // more voxels per point than the tables were sized for: this call takes the
+        ctx->vox_slots_per_point = 2.0;  // sort, the next one gets worst-case tables (one voxel per point)
+        return SB_OK;
+    }
+    if (flags & FLAG_KEY_RANGE) return SB_OK;
+    h_out_off[0] = 0;
+    for (int c = 0; c < n_clouds; ++c) h_out_off[c + 1] = h_out_off[c] + nvox[c];
+    const i64 m = h_out_off[n_clouds];
+    {  // size the next call's tables for 2 slots per voxel (before rounding up to a power of two) at this density
+        double r = 2.0 * (double)m / (double)n;
+        ctx->vox_slots_per_point = r < 0.125 ? 0.125 : (r > 2.0 ? 2.0 : r);
+    }
+    int bx = bits_for((u64)(mm[3] - mm[0])), by = bits_for((u64)(mm[4] - mm[1])), bz = bits_for((u64)(mm[5] - mm[2]));
+    VoxelPack P;
+    P.minx = mm[0]; P.miny = mm[1]; P.minz = mm[2];
+    P.sy = bz;
+    P.sx = by + bz;
+    P.mask_z = (1ull << bz) - 1ull;
+    P.mask_y = (1ull << by) - 1ull;
+    // ---- voxels of every cloud in key order
+    u64 *ka, *kb, *ks;
+    uint32_t *va, *vb, *vs;
+    i64* d_out_off;
+    SB_TRY(arena_get(ctx, (size_t)m, &ka));
+    SB_TRY(arena_get(ctx, (size_t)m, &kb));
+    SB_TRY(arena_get(ctx, (size_t)m, &va));
+    SB_TRY(arena_get(ctx, (size_t)m, &vb));
+    SB_TRY(arena_get(ctx, (size_t)n_clouds + 1, &d_out_off));
+    SB_CUDA(ctx, cudaMemcpyAsync(d_out_off, h_out_off, sizeof(i64) * (n_clouds + 1), cudaMemcpyHostToDevice, ctx->stream));
+    SB_LAUNCH(ctx, k_vox_list, ceil_div(n_slots, 256), 256, 0, d_clouds, n_clouds, n_slots, d_table, d_out_off, d_cursor, P,
+              ka, va);
+    SB_TRY(segmented_sort_pairs(ctx, ka, kb, va, vb, h_out_off, n_clouds, bx + by + bz, &ks, &vs));
+    SB_LAUNCH(ctx, k_vox_finalize, ceil_div(m, 256), 256, 0, ks, vs, m, voxel, P, d_table, d_out_xyz, d_out_keys);
+    // ---- ordered re-summation of the voxels that could not be proven exact
+    SB_LAUNCH(ctx, k_vox_collect, pgrid, 256, 0, d_clouds, d_tile_cloud, n_tiles, d_slot_of, d_table, d_list, d_list_n,
+              ctx->d_flags);
+    SB_LAUNCH(ctx, k_vox_patch, 1, 1024, 0, d_xyz, d_list, d_list_n, d_out_xyz);
+    SB_CUDA(ctx, cudaMemcpyAsync(&flags, ctx->d_flags, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (flags & FLAG_PATCH_OVERFLOW) return SB_OK;  // e.g. arbitrary fp64 input: the sort handles it
+    *done = 1;
+    return SB_OK;
+}
+
+int voxel_downsample_dev(Ctx* ctx, const double* d_xyz, const i64* h_off, int n_clouds, double voxel,
+                         double* d_out_xyz, i64* h_out_off, i64* d_out_keys) {
+    if (h_off[0] != 0) return fail(ctx, SB_ERR_INVALID_ARG, "voxel: offsets must start at 0");
+    if (voxel > 0 && h_off[n_clouds] > 0 && !ctx->vox_force_sort) {
+        int done = 0;
+        SB_TRY(voxel_hashed_dev(ctx, d_xyz, h_off, n_clouds, voxel, d_out_xyz, h_out_off, d_out_keys, &done));
+        ctx->vox_last_path = done ? 1 : 2;
+        if (done) return SB_OK;
+    } else {
+        ctx->vox_last_path = 2;
+    }
+    return voxel_sorted_dev(ctx, d_xyz, h_off, n_clouds, voxel, d_out_xyz, h_out_off, d_out_keys);
 }
 
 }  // namespace sb

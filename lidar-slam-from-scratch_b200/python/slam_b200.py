@@ -75,6 +75,7 @@ SYMBOLS = {
     "sb_ctx_stage_ms": (C.c_int, [_P, _D]),
     "sb_ctx_stage_host_ms": (C.c_int, [_P, _D]),
     "sb_ctx_last_counts": (C.c_int, [_P, _I64]),
+    "sb_ctx_last_voxel_path": (C.c_int, [_P]),
     "sb_default_icp_config": (None, [C.POINTER(ICPConfigC)]),
     "sb_default_loop_config": (None, [C.POINTER(LoopConfigC)]),
     "sb_voxel_downsample": (C.c_int, [_P, _D, C.c_int64, C.c_double, _D, _I64, _I64]),
@@ -196,6 +197,11 @@ class Engine:
         self._check(self.lib.sb_ctx_last_counts(self.h, c.ctypes.data_as(_I64)))
         return dict(raw_rows=int(c[0]), voxel_rows=int(c[1]), target_rows=int(c[2]), nn_queries=int(c[3]),
                     icp_iter_launches=int(c[4]))
+
+    @property
+    def last_voxel_path(self):
+        """1 = hashed fixed-point sums (float32-born scans), 2 = sort-based; same rows either way."""
+        return int(self.lib.sb_ctx_last_voxel_path(self.h))
 
     # ---- config helpers
     def icp_config(self, max_iterations=50, tolerance=1e-6, min_error=1e-9, initial_transform=None, normals_k=20):

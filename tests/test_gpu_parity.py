@@ -44,6 +44,50 @@ def test_voxel_full_scan_bit_exact(engine, oracle, synth, scene):
         assert np.array_equal(out, ref)  # same members, same summation order -> bit-identical centroids
 
 
+def test_voxel_hashed_and_sorted_paths_agree(engine, oracle, synth, scene, monkeypatch):
+    """The one-pass hashed path (float32-born scans) and the sort-based path give the oracle's rows bit for bit;
+    voxels whose integer sums cannot be proven exact are re-summed in input order; arbitrary fp64 input falls back."""
+    import slam_b200
+    raw = synth.scan(oracle_lib.SENSOR64, scene, (2.0, -1.0, 0.3), 21)
+    ref, rkeys = oracle.voxel_downsample(raw, 0.5)
+    out, keys = engine.voxel_downsample(raw, 0.5, return_keys=True)
+    assert engine.last_voxel_path == 1
+    assert np.array_equal(keys, rkeys) and np.array_equal(out, ref)
+    monkeypatch.setenv("SB_VOXEL_SORT", "1")
+    eng2 = slam_b200.Engine(0)
+    monkeypatch.delenv("SB_VOXEL_SORT")
+    out2, keys2 = eng2.voxel_downsample(raw, 0.5, return_keys=True)
+    assert eng2.last_voxel_path == 2
+    assert np.array_equal(keys2, rkeys) and np.array_equal(out2, ref)
+    eng2.close()
+    # a few members finer than 2^-44, members whose low bits make the fp64 loop round (1e-7 next to 40.x), and one
+    # voxel whose sum of |v| is too large for the 64-bit fixed-point sums
+    rng = np.random.default_rng(5)
+    odd = raw.copy()
+    pick = rng.choice(len(odd), 40, replace=False)
+    odd[pick] += rng.uniform(-1e-9, 1e-9, (40, 3))
+    pick2 = rng.choice(len(odd), 40, replace=False)
+    odd[pick2, 2] = np.float32(1e-7) * rng.integers(1, 9, 40)
+    odd = np.vstack([odd, np.tile([[400000.3, 0.1, 0.2]], (3, 1)) + rng.integers(0, 8, (3, 3)) / 64.0])
+    ref3, rkeys3 = oracle.voxel_downsample(odd, 0.5)
+    out3, keys3 = engine.voxel_downsample(odd, 0.5, return_keys=True)
+    assert engine.last_voxel_path == 1
+    assert np.array_equal(keys3, rkeys3) and np.array_equal(out3, ref3)
+    # arbitrary doubles: nothing can be proven, the call falls back to the sort and is still exact
+    arb = rng.uniform(-40, 40, (20000, 3))
+    ref4, rkeys4 = oracle.voxel_downsample(arb, 0.5)
+    out4, keys4 = engine.voxel_downsample(arb, 0.5, return_keys=True)
+    assert engine.last_voxel_path == 2
+    assert np.array_equal(keys4, rkeys4) and np.array_equal(out4, ref4)
+    # one voxel per point (tables sized for 4 points per slot overflow), then the adapted sizing on the next call
+    sparse = np.round(rng.uniform(-400, 400, (30000, 3)), 1).astype(np.float32).astype(np.float64)
+    for _ in range(2):
+        out5, keys5 = engine.voxel_downsample(sparse, 0.05, return_keys=True)
+        ref5, rkeys5 = oracle.voxel_downsample(sparse, 0.05)
+        assert np.array_equal(keys5, rkeys5) and np.array_equal(out5, ref5)
+    assert engine.last_voxel_path == 1
+
+
 def test_voxel_edge_cases(engine, oracle):
     pts = np.array([[0.6, -0.6, 0.0], [0.6000000000000001, -0.2, 1e-300], [-1e-300, 0.2, -0.0]])
     out, keys = engine.voxel_downsample(pts, 0.2, return_keys=True)
