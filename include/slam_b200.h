@@ -167,6 +167,21 @@ int sb_register_batch_dev(sb_ctx* ctx, const double* d_xyz, const int64_t* offse
                           const int32_t* pair_src, const int32_t* pair_tgt, int32_t n_pairs,
                           const sb_icp_config* cfg, sb_icp_result* results, double* sc_desc);
 
+/* float32 ingest.  The reference reads x, y, z as float32 from binary PLY and KITTI .bin records
+ * and widens them to double on the host (file_utils.cpp:91-97, 133-136; tools/convert_to_ply.cpp:14-67 writes
+ * x, y, z, intensity).  These entry points take the float32 records as they are on disk — rows of `stride_floats`
+ * floats with x, y, z first (3 for xyz, 4 for KITTI) — and widen on the device: half (or a third) of the
+ * host-to-device bytes, identical results.  Host rows are uploaded in chunks that overlap with the voxel grid. */
+int sb_register_batch_f32(sb_ctx* ctx, const float* xyz, int32_t stride_floats, const int64_t* offsets, int32_t n_clouds,
+                          double voxel, const int32_t* pair_src, const int32_t* pair_tgt, int32_t n_pairs,
+                          const sb_icp_config* cfg, sb_icp_result* results, double* sc_desc);
+int sb_register_batch_f32_dev(sb_ctx* ctx, const float* d_xyz, int32_t stride_floats, const int64_t* offsets,
+                              int32_t n_clouds, double voxel, const int32_t* pair_src, const int32_t* pair_tgt,
+                              int32_t n_pairs, const sb_icp_config* cfg, sb_icp_result* results, double* sc_desc);
+int sb_voxel_downsample_batch_f32(sb_ctx* ctx, const float* xyz, int32_t stride_floats, const int64_t* offsets,
+                                  int32_t n_clouds, double voxel, double* out_xyz, int64_t* out_offsets,
+                                  int64_t* out_keys);
+
 /* ---------------------------------------------------------------- Scan Context ----------------------------- */
 /* Replaces slam::ScanContext::compute (scan_context.hpp:44-82).  desc: 1200 doubles, COLUMN-major 20x60 like
  * Eigen::MatrixXd::data(): element (ring i, sector j) at desc[j*20 + i]. */

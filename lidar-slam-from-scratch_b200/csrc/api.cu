@@ -46,15 +46,29 @@ int arena_reset(Ctx* ctx) {
         }
     }
     A.used = 0;
+    A.req = 0;
     A.high = 0;
     return SB_OK;
+}
+
+ArenaMark arena_mark(Ctx* ctx) {
+    ArenaMark m;
+    m.used = ctx->arena.used;
+    m.req = ctx->arena.req;
+    return m;
+}
+
+void arena_release(Ctx* ctx, ArenaMark m) {
+    ctx->arena.used = m.used;  // overflow blocks stay allocated until the next reset
+    ctx->arena.req = m.req;
 }
 
 int arena_alloc(Ctx* ctx, size_t bytes, void** out) {
     Arena& A = ctx->arena;
     size_t sz = (bytes + 255) & ~(size_t)255;
     if (sz == 0) sz = 256;
-    A.high += sz;
+    A.req += sz;
+    if (A.req > A.high) A.high = A.req;
     if (A.used + sz <= A.cap) {
         *out = A.base + A.used;
         A.used += sz;
@@ -127,8 +141,65 @@ static std::vector<QueryItem> items_for(i64 nq) {
     return items;
 }
 
-// shared implementation of sb_register_batch / _dev once the clouds are on the device
-static int register_batch_impl(Ctx* ctx, const double* d_xyz, const i64* offsets, int n_clouds, double voxel,
+// Host clouds -> device, voxel grid.  The raw rows are copied in chunks of whole clouds on a second stream and the
+// voxel grid of chunk c runs while chunk c+1 is in flight (pinned host memory; pageable memory still works, without
+// the overlap).  d_ds receives the downsampled rows of all clouds, off_ds their CSR offsets.
+static int upload_voxel_pipelined(Ctx* ctx, const void* h_raw, int f32, int stride, const i64* offsets, int n_clouds,
+                                  double voxel, double* d_ds, i64* off_ds) {
+    const size_t row_bytes = (size_t)stride * (f32 ? sizeof(float) : sizeof(double));
+    const i64 n = offsets[n_clouds];
+    char* d_raw;
+    SB_TRY(arena_get(ctx, (size_t)(n > 0 ? n : 1) * row_bytes, &d_raw));
+    if (!ctx->copy_stream) {
+        SB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) SB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->copy_ev[i], cudaEventDisableTiming));
+    }
+    // chunk boundaries: whole clouds, about 96 MB each
+    std::vector<int> cb(1, 0);
+    {
+        const i64 target_rows = (i64)((96u << 20) / row_bytes);
+        i64 start = 0;
+        for (int c = 0; c < n_clouds; ++c)
+            if (offsets[c + 1] - start >= target_rows || c == n_clouds - 1) {
+                cb.push_back(c + 1);
+                start = offsets[c + 1];
+            }
+        if (cb.back() != n_clouds) cb.push_back(n_clouds);
+    }
+    const int n_chunks = (int)cb.size() - 1;
+    auto enqueue_copy = [&](int k) -> int {
+        const i64 r0 = offsets[cb[k]], r1 = offsets[cb[k + 1]];
+        if (r1 > r0)
+            SB_CUDA(ctx, cudaMemcpyAsync(d_raw + (size_t)r0 * row_bytes, static_cast<const char*>(h_raw) + (size_t)r0 * row_bytes,
+                                         (size_t)(r1 - r0) * row_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+        SB_CUDA(ctx, cudaEventRecord(ctx->copy_ev[k & 1], ctx->copy_stream));
+        return SB_OK;
+    };
+    off_ds[0] = 0;
+    if (n_chunks > 0) SB_TRY(enqueue_copy(0));
+    std::vector<i64> in_off, out_off;
+    for (int k = 0; k < n_chunks; ++k) {
+        SB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[k & 1], 0));
+        if (k + 1 < n_chunks) SB_TRY(enqueue_copy(k + 1));  // in flight while chunk k is voxelised
+        const int c0 = cb[k], nc = cb[k + 1] - cb[k];
+        in_off.assign((size_t)nc + 1, 0);
+        out_off.assign((size_t)nc + 1, 0);
+        for (int i = 0; i <= nc; ++i) in_off[i] = offsets[c0 + i] - offsets[c0];
+        PointSrc src;
+        src.base = d_raw + (size_t)offsets[c0] * row_bytes;
+        src.f32 = f32;
+        src.stride = stride;
+        const ArenaMark mark = arena_mark(ctx);
+        SB_TRY(voxel_downsample_src(ctx, src, in_off.data(), nc, voxel, d_ds + 3 * off_ds[c0], out_off.data(), nullptr));
+        arena_release(ctx, mark);
+        for (int i = 1; i <= nc; ++i) off_ds[c0 + i] = off_ds[c0] + out_off[i];
+    }
+    return SB_OK;
+}
+
+// shared implementation of sb_register_batch / _dev.  The clouds are either on the device already (src.base) or
+// on the host (h_raw != nullptr: uploaded in chunks, overlapped with the voxel grid).
+static int register_batch_impl(Ctx* ctx, PointSrc src, const void* h_raw, const i64* offsets, int n_clouds, double voxel,
                                const int32_t* pair_src, const int32_t* pair_tgt, int n_pairs, const sb_icp_config* cfg,
                                sb_icp_result* results, double* sc_desc) {
     for (int p = 0; p < n_pairs; ++p)
@@ -138,17 +209,42 @@ static int register_batch_impl(Ctx* ctx, const double* d_xyz, const i64* offsets
         return fail(ctx, SB_ERR_INVALID_ARG, "normals_k %d outside [1, %d]", cfg->normals_k, SB_MAX_K);
     // 1. voxel grid (slam_node.cpp:122)
     stage_mark(ctx, STAGE_VOXEL);
-    const double* d_pts = d_xyz;
+    const i64 n_raw = offsets[n_clouds];
+    const double* d_pts = nullptr;
     std::vector<i64> off(offsets, offsets + n_clouds + 1);
     if (voxel > 0) {
         double* d_ds;
-        SB_TRY(arena_get(ctx, (size_t)3 * (offsets[n_clouds] > 0 ? offsets[n_clouds] : 1), &d_ds));
-        SB_TRY(voxel_downsample_dev(ctx, d_xyz, offsets, n_clouds, voxel, d_ds, off.data(), nullptr));
+        SB_TRY(arena_get(ctx, (size_t)3 * (n_raw > 0 ? n_raw : 1), &d_ds));
+        if (h_raw) {
+            SB_TRY(upload_voxel_pipelined(ctx, h_raw, src.f32, src.stride, offsets, n_clouds, voxel, d_ds, off.data()));
+        } else {
+            const ArenaMark mark = arena_mark(ctx);
+            SB_TRY(voxel_downsample_src(ctx, src, offsets, n_clouds, voxel, d_ds, off.data(), nullptr));
+            arena_release(ctx, mark);
+        }
         d_pts = d_ds;
+    } else {  // no voxel grid: the clouds themselves, as packed fp64 rows on the device
+        double* d_all;
+        SB_TRY(arena_get(ctx, (size_t)3 * (n_raw > 0 ? n_raw : 1), &d_all));
+        if (h_raw && !src.f32 && src.stride == 3) {
+            if (n_raw > 0) SB_CUDA(ctx, cudaMemcpyAsync(d_all, h_raw, sizeof(double) * 3 * n_raw, cudaMemcpyHostToDevice, ctx->stream));
+        } else {
+            PointSrc s2 = src;
+            if (h_raw) {
+                const size_t bytes = (size_t)n_raw * src.stride * (src.f32 ? sizeof(float) : sizeof(double));
+                char* d_raw;
+                SB_TRY(arena_get(ctx, bytes ? bytes : 1, &d_raw));
+                if (bytes) SB_CUDA(ctx, cudaMemcpyAsync(d_raw, h_raw, bytes, cudaMemcpyHostToDevice, ctx->stream));
+                s2.base = d_raw;
+            }
+            i64 dummy_off[2] = {0, n_raw}, out_off2[2];
+            SB_TRY(voxel_downsample_src(ctx, s2, dummy_off, 1, 0.0, d_all, out_off2, nullptr));  // voxel <= 0: copy
+        }
+        d_pts = d_all;
     }
     // 2. Scan Context of every cloud (loop_closure.hpp:53-59)
     stage_mark(ctx, STAGE_SC);
-    ctx->last_counts[0] = offsets[n_clouds];
+    ctx->last_counts[0] = n_raw;
     ctx->last_counts[1] = off[n_clouds];
     if (sc_desc) {
         i64* d_off;
@@ -255,6 +351,9 @@ void sb_ctx_destroy(sb_ctx* ctx) {
     cudaFree(c->d_flags);
     for (int i = 0; i < c->ev_created; ++i) cudaEventDestroy(c->ev[i]);
     if (c->pinned) cudaFreeHost(c->pinned);
+    for (int i = 0; i < 2; ++i)
+        if (c->copy_ev[i]) cudaEventDestroy(c->copy_ev[i]);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete ctx;
 }
@@ -359,6 +458,34 @@ int sb_voxel_downsample_batch(sb_ctx* ctx, const double* xyz, const int64_t* off
     SB_TRY(arena_get(c, (size_t)3 * (n > 0 ? n : 1), &d_out));
     if (out_keys) SB_TRY(arena_get(c, (size_t)3 * (n > 0 ? n : 1), &d_keys));
     SB_TRY(voxel_downsample_dev(c, d_in, (const i64*)offsets, n_clouds, voxel, d_out, (i64*)out_offsets, d_keys));
+    i64 m = out_offsets[n_clouds];
+    SB_TRY(download(c, out_xyz, d_out, sizeof(double) * 3 * m));
+    if (out_keys) SB_TRY(download(c, out_keys, d_keys, sizeof(i64) * 3 * m));
+    SB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return SB_OK;
+}
+
+int sb_voxel_downsample_batch_f32(sb_ctx* ctx, const float* xyz, int32_t stride_floats, const int64_t* offsets,
+                                  int32_t n_clouds, double voxel, double* out_xyz, int64_t* out_offsets,
+                                  int64_t* out_keys) {
+    if (!ctx || !offsets || !out_offsets || n_clouds < 0) return SB_ERR_INVALID_ARG;
+    Ctx* c = &ctx->c;
+    Enter g(c);
+    if (stride_floats < 3) return fail(c, SB_ERR_INVALID_ARG, "row stride %d < 3", stride_floats);
+    if (offsets[0] != 0) return fail(c, SB_ERR_INVALID_ARG, "offsets must start at 0");
+    for (int i = 0; i < n_clouds; ++i)
+        if (offsets[i + 1] < offsets[i]) return fail(c, SB_ERR_INVALID_ARG, "offsets must be non-decreasing");
+    i64 n = offsets[n_clouds];
+    if (n > 0 && (!xyz || !out_xyz)) return fail(c, SB_ERR_INVALID_ARG, "null point buffer");
+    float* d_in;
+    double* d_out;
+    i64* d_keys = nullptr;
+    SB_TRY(upload(c, xyz, sizeof(float) * (size_t)stride_floats * n, (void**)&d_in));
+    SB_TRY(arena_get(c, (size_t)3 * (n > 0 ? n : 1), &d_out));
+    if (out_keys) SB_TRY(arena_get(c, (size_t)3 * (n > 0 ? n : 1), &d_keys));
+    PointSrc src;
+    src.base = d_in; src.f32 = 1; src.stride = stride_floats;
+    SB_TRY(voxel_downsample_src(c, src, (const i64*)offsets, n_clouds, voxel, d_out, (i64*)out_offsets, d_keys));
     i64 m = out_offsets[n_clouds];
     SB_TRY(download(c, out_xyz, d_out, sizeof(double) * 3 * m));
     if (out_keys) SB_TRY(download(c, out_keys, d_keys, sizeof(i64) * 3 * m));
@@ -521,35 +648,52 @@ int sb_solve_point_to_plane(sb_ctx* ctx, const double* source, const double* tar
     return SB_OK;
 }
 
-int sb_register_batch_dev(sb_ctx* ctx, const double* d_xyz, const int64_t* offsets, int32_t n_clouds, double voxel,
-                          const int32_t* pair_src, const int32_t* pair_tgt, int32_t n_pairs, const sb_icp_config* cfg,
-                          sb_icp_result* results, double* sc_desc) {
+static int register_batch_entry(sb_ctx* ctx, const void* xyz, int on_host, int f32, int stride, const int64_t* offsets,
+                                int32_t n_clouds, double voxel, const int32_t* pair_src, const int32_t* pair_tgt,
+                                int32_t n_pairs, const sb_icp_config* cfg, sb_icp_result* results, double* sc_desc) {
     if (!ctx || !offsets || n_clouds < 0 || n_pairs < 0 || !cfg) return SB_ERR_INVALID_ARG;
     if (n_pairs > 0 && (!pair_src || !pair_tgt || !results)) return SB_ERR_INVALID_ARG;
     Ctx* c = &ctx->c;
     Enter g(c);
+    if (stride < 3) return fail(c, SB_ERR_INVALID_ARG, "row stride %d < 3", stride);
+    if (offsets[0] != 0) return fail(c, SB_ERR_INVALID_ARG, "offsets must start at 0");
     for (int i = 0; i < n_clouds; ++i)
         if (offsets[i + 1] < offsets[i]) return fail(c, SB_ERR_INVALID_ARG, "offsets must be non-decreasing");
-    return register_batch_impl(c, d_xyz, (const i64*)offsets, n_clouds, voxel, pair_src, pair_tgt, n_pairs, cfg, results,
-                               sc_desc);
+    if (offsets[n_clouds] > 0 && !xyz) return fail(c, SB_ERR_INVALID_ARG, "null point buffer");
+    PointSrc src;
+    src.base = on_host ? nullptr : xyz;
+    src.f32 = f32;
+    src.stride = stride;
+    return register_batch_impl(c, src, on_host ? xyz : nullptr, (const i64*)offsets, n_clouds, voxel, pair_src, pair_tgt,
+                               n_pairs, cfg, results, sc_desc);
+}
+
+int sb_register_batch_dev(sb_ctx* ctx, const double* d_xyz, const int64_t* offsets, int32_t n_clouds, double voxel,
+                          const int32_t* pair_src, const int32_t* pair_tgt, int32_t n_pairs, const sb_icp_config* cfg,
+                          sb_icp_result* results, double* sc_desc) {
+    return register_batch_entry(ctx, d_xyz, 0, 0, 3, offsets, n_clouds, voxel, pair_src, pair_tgt, n_pairs, cfg, results,
+                                sc_desc);
 }
 
 int sb_register_batch(sb_ctx* ctx, const double* xyz, const int64_t* offsets, int32_t n_clouds, double voxel,
                       const int32_t* pair_src, const int32_t* pair_tgt, int32_t n_pairs, const sb_icp_config* cfg,
                       sb_icp_result* results, double* sc_desc) {
-    if (!ctx || !offsets || n_clouds < 0 || n_pairs < 0 || !cfg) return SB_ERR_INVALID_ARG;
-    if (n_pairs > 0 && (!pair_src || !pair_tgt || !results)) return SB_ERR_INVALID_ARG;
-    Ctx* c = &ctx->c;
-    Enter g(c);
-    for (int i = 0; i < n_clouds; ++i)
-        if (offsets[i + 1] < offsets[i]) return fail(c, SB_ERR_INVALID_ARG, "offsets must be non-decreasing");
-    i64 n = offsets[n_clouds];
-    if (n > 0 && !xyz) return fail(c, SB_ERR_INVALID_ARG, "null point buffer");
-    double* d_xyz;
-    stage_mark(c, STAGE_H2D);
-    SB_TRY(upload(c, xyz, sizeof(double) * 3 * n, (void**)&d_xyz));
-    return register_batch_impl(c, d_xyz, (const i64*)offsets, n_clouds, voxel, pair_src, pair_tgt, n_pairs, cfg, results,
-                               sc_desc);
+    return register_batch_entry(ctx, xyz, 1, 0, 3, offsets, n_clouds, voxel, pair_src, pair_tgt, n_pairs, cfg, results,
+                                sc_desc);
+}
+
+int sb_register_batch_f32(sb_ctx* ctx, const float* xyz, int32_t stride_floats, const int64_t* offsets, int32_t n_clouds,
+                          double voxel, const int32_t* pair_src, const int32_t* pair_tgt, int32_t n_pairs,
+                          const sb_icp_config* cfg, sb_icp_result* results, double* sc_desc) {
+    return register_batch_entry(ctx, xyz, 1, 1, stride_floats, offsets, n_clouds, voxel, pair_src, pair_tgt, n_pairs, cfg,
+                                results, sc_desc);
+}
+
+int sb_register_batch_f32_dev(sb_ctx* ctx, const float* d_xyz, int32_t stride_floats, const int64_t* offsets,
+                              int32_t n_clouds, double voxel, const int32_t* pair_src, const int32_t* pair_tgt,
+                              int32_t n_pairs, const sb_icp_config* cfg, sb_icp_result* results, double* sc_desc) {
+    return register_batch_entry(ctx, d_xyz, 0, 1, stride_floats, offsets, n_clouds, voxel, pair_src, pair_tgt, n_pairs, cfg,
+                                results, sc_desc);
 }
 
 int sb_icp_point_to_plane(sb_ctx* ctx, const double* source, int64_t ns, const double* target, int64_t nt,

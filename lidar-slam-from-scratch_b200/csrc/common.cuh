@@ -48,8 +48,12 @@ int fail(Ctx* ctx, int status, const char* fmt, ...);
 // ---------------------------------------------------------------------------------------------------------------
 struct Arena {
     char* base = nullptr;
-    size_t cap = 0, used = 0, high = 0;
+    size_t cap = 0, used = 0;
+    size_t req = 0, high = 0;  // bytes currently handed out (slab + overflow) and their peak since the last reset
     std::vector<void*> overflow;
+};
+struct ArenaMark {
+    size_t used, req;
 };
 
 struct Ctx {
@@ -57,6 +61,8 @@ struct Ctx {
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t copy_stream = nullptr;   // host-to-device chunks of the pipelined entry points (api.cu)
+    cudaEvent_t copy_ev[2] = {nullptr, nullptr};
     Arena arena;
     char* pinned = nullptr;  // pinned host staging
     size_t pinned_cap = 0;
@@ -87,6 +93,10 @@ enum { STAGE_H2D = 0, STAGE_VOXEL = 1, STAGE_SC = 2, STAGE_INDEX = 3, STAGE_NORM
 void stage_mark(Ctx* ctx, int stage);
 
 int arena_reset(Ctx* ctx);
+// Temporaries of one pipeline stage: everything allocated after arena_mark is handed back by arena_release.  Safe
+// because all work is ordered on the context's stream (later kernels run after the ones that used the memory).
+ArenaMark arena_mark(Ctx* ctx);
+void arena_release(Ctx* ctx, ArenaMark m);
 int arena_alloc(Ctx* ctx, size_t bytes, void** out);
 int pinned_reserve(Ctx* ctx, size_t bytes);
 
@@ -156,6 +166,15 @@ int segmented_sort_pairs(Ctx* ctx, u64* keys_a, u64* keys_b, uint32_t* vals_a, u
 // ---------------------------------------------------------------------------------------------------------------
 // voxel.cu
 // ---------------------------------------------------------------------------------------------------------------
+// Where the raw points of a call live on the device: fp64 rows (the ABI's PointCloud::Matrix layout) or float32 rows
+// of `stride` floats with x, y, z first (binary PLY / KITTI .bin records, file_utils.cpp:91-97, 133-136).
+struct PointSrc {
+    const void* base;
+    int f32;
+    int stride;
+};
+int voxel_downsample_src(Ctx* ctx, const PointSrc src, const i64* h_off, int n_clouds, double voxel, double* d_out_xyz,
+                         i64* h_out_off, i64* d_out_keys);
 // Device-to-device batched voxel grid.  d_out_xyz / d_out_keys (optional) sized for the input row count;
 // h_out_off (host, n_clouds + 1) receives the CSR offsets of the output.  Synchronises the stream.
 int voxel_downsample_dev(Ctx* ctx, const double* d_xyz, const i64* h_off, int n_clouds, double voxel,

@@ -247,6 +247,16 @@ struct alignas(16) VoxSlot {
     unsigned long long pad;
 };
 
+__device__ __forceinline__ void load_xyz(const PointSrc& S, i64 row, double& x, double& y, double& z) {
+    if (S.f32) {  // float32 rows widened exactly like load_ply does (file_utils.cpp:91-97)
+        const float* p = static_cast<const float*>(S.base) + row * S.stride;
+        x = (double)p[0]; y = (double)p[1]; z = (double)p[2];
+    } else {
+        const double* p = static_cast<const double*>(S.base) + row * S.stride;
+        x = p[0]; y = p[1]; z = p[2];
+    }
+}
+
 // fixed-point image of a coordinate; bit: this axis' "fine" flag
 __device__ __forceinline__ long long vox_fixed(double v, unsigned bit, unsigned* fl) {
     double t = v * VQ_SCALE;  // exact: a power of two
@@ -257,7 +267,7 @@ __device__ __forceinline__ long long vox_fixed(double v, unsigned bit, unsigned*
 }
 
 // hash + accumulate.  mm: [0..2] min keys, [3..5] max keys; n_vox[c]: distinct voxels of cloud c.
-__global__ void __launch_bounds__(256) k_vox_insert(const double* __restrict__ xyz, const VoxCloud* __restrict__ clouds,
+__global__ void __launch_bounds__(256) k_vox_insert(const PointSrc src, const VoxCloud* __restrict__ clouds,
                                                     const int* __restrict__ tile_cloud, i64 n_tiles, double voxel,
                                                     VoxSlot* __restrict__ table, unsigned* __restrict__ slot_of_point,
                                                     int* __restrict__ n_vox, i64* __restrict__ mm,
@@ -278,8 +288,8 @@ __global__ void __launch_bounds__(256) k_vox_insert(const double* __restrict__ x
             long long fx = 0, fy = 0, fz = 0;
             unsigned fl = 0u;
             if (i < C.n) {
-                const double* p = xyz + 3 * (C.pt_off + i);
-                const double x = p[0], y = p[1], z = p[2];
+                double x, y, z;
+                load_xyz(src, C.pt_off + i, x, y, z);
                 i64 kx, ky, kz;
                 bool ok = voxel_key(x, voxel, &kx) & voxel_key(y, voxel, &ky) & voxel_key(z, voxel, &kz);
                 if (!ok) {
@@ -467,7 +477,7 @@ __global__ void __launch_bounds__(256) k_vox_collect(const VoxCloud* __restrict_
 }
 
 // one block: bitonic sort of the member list, then one thread per voxel run adds its members in input order
-__global__ void __launch_bounds__(1024) k_vox_patch(const double* __restrict__ xyz, u64* __restrict__ list,
+__global__ void __launch_bounds__(1024) k_vox_patch(const PointSrc src, u64* __restrict__ list,
                                                     const int* __restrict__ list_n, double* __restrict__ out_xyz) {
     __shared__ u64 s[PATCH_CAP];
     int n = *list_n;
@@ -496,8 +506,9 @@ __global__ void __launch_bounds__(1024) k_vox_patch(const double* __restrict__ x
         double sx = 0.0, sy = 0.0, sz = 0.0;
         int j = i;
         do {  // members in ascending input row, file_utils.cpp:186-190
-            const double* p = xyz + 3 * (i64)(s[j] & 0xffffffffull);
-            sx = __dadd_rn(sx, p[0]); sy = __dadd_rn(sy, p[1]); sz = __dadd_rn(sz, p[2]);
+            double x, y, z;
+            load_xyz(src, (i64)(s[j] & 0xffffffffull), x, y, z);
+            sx = __dadd_rn(sx, x); sy = __dadd_rn(sy, y); sz = __dadd_rn(sz, z);
             ++j;
         } while (j < n && (s[j] >> 32) == (e >> 32));
         const double cnt = (double)(j - i);
@@ -509,7 +520,7 @@ __global__ void __launch_bounds__(1024) k_vox_patch(const double* __restrict__ x
 }
 
 // returns SB_OK with *done = 1 if the fast path produced the result, *done = 0 if the caller must use the sort
-static int voxel_hashed_dev(Ctx* ctx, const double* d_xyz, const i64* h_off, int n_clouds, double voxel,
+static int voxel_hashed_dev(Ctx* ctx, const PointSrc src, const i64* h_off, int n_clouds, double voxel,
                             double* d_out_xyz, i64* h_out_off, i64* d_out_keys, int* done) {
     *done = 0;
     const i64 n = h_off[n_clouds];
@@ -564,7 +575,7 @@ static int voxel_hashed_dev(Ctx* ctx, const double* d_xyz, const i64* h_off, int
     i64 init[6] = {INT64_MAX, INT64_MAX, INT64_MAX, INT64_MIN, INT64_MIN, INT64_MIN};
     SB_CUDA(ctx, cudaMemcpyAsync(d_mm, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
     const int pgrid = (int)(n_tiles < (i64)ctx->sm_count * 8 ? n_tiles : (i64)ctx->sm_count * 8);
-    SB_LAUNCH(ctx, k_vox_insert, pgrid, 256, 0, d_xyz, d_clouds, d_tile_cloud, n_tiles, voxel, d_table, d_slot_of, d_nvox,
+    SB_LAUNCH(ctx, k_vox_insert, pgrid, 256, 0, src, d_clouds, d_tile_cloud, n_tiles, voxel, d_table, d_slot_of, d_nvox,
               d_mm, ctx->d_flags);
     // ---- the only host round trip: flags, key range, voxels per cloud
     std::vector<int> nvox((size_t)n_clouds);
@@ -611,7 +622,7 @@ static int voxel_hashed_dev(Ctx* ctx, const double* d_xyz, const i64* h_off, int
     // ---- ordered re-summation of the voxels that could not be proven exact
     SB_LAUNCH(ctx, k_vox_collect, pgrid, 256, 0, d_clouds, d_tile_cloud, n_tiles, d_slot_of, d_table, d_list, d_list_n,
               ctx->d_flags);
-    SB_LAUNCH(ctx, k_vox_patch, 1, 1024, 0, d_xyz, d_list, d_list_n, d_out_xyz);
+    SB_LAUNCH(ctx, k_vox_patch, 1, 1024, 0, src, d_list, d_list_n, d_out_xyz);
     SB_CUDA(ctx, cudaMemcpyAsync(&flags, ctx->d_flags, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (flags & FLAG_PATCH_OVERFLOW) return SB_OK;  // e.g. arbitrary fp64 input: the sort handles it
@@ -619,18 +630,41 @@ static int voxel_hashed_dev(Ctx* ctx, const double* d_xyz, const i64* h_off, int
     return SB_OK;
 }
 
-int voxel_downsample_dev(Ctx* ctx, const double* d_xyz, const i64* h_off, int n_clouds, double voxel,
-                         double* d_out_xyz, i64* h_out_off, i64* d_out_keys) {
+__global__ void __launch_bounds__(256) k_widen(const PointSrc src, i64 n, double* __restrict__ out) {
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double x, y, z;
+    load_xyz(src, i, x, y, z);
+    out[3 * i] = x; out[3 * i + 1] = y; out[3 * i + 2] = z;
+}
+
+int voxel_downsample_src(Ctx* ctx, const PointSrc src, const i64* h_off, int n_clouds, double voxel, double* d_out_xyz,
+                         i64* h_out_off, i64* d_out_keys) {
     if (h_off[0] != 0) return fail(ctx, SB_ERR_INVALID_ARG, "voxel: offsets must start at 0");
-    if (voxel > 0 && h_off[n_clouds] > 0 && !ctx->vox_force_sort) {
+    const i64 n = h_off[n_clouds];
+    if (voxel > 0 && n > 0 && !ctx->vox_force_sort) {
         int done = 0;
-        SB_TRY(voxel_hashed_dev(ctx, d_xyz, h_off, n_clouds, voxel, d_out_xyz, h_out_off, d_out_keys, &done));
+        SB_TRY(voxel_hashed_dev(ctx, src, h_off, n_clouds, voxel, d_out_xyz, h_out_off, d_out_keys, &done));
         ctx->vox_last_path = done ? 1 : 2;
         if (done) return SB_OK;
     } else {
         ctx->vox_last_path = 2;
     }
+    const double* d_xyz = static_cast<const double*>(src.base);
+    if (src.f32 || src.stride != 3) {  // the sort path works on packed fp64 rows
+        double* tmp;
+        SB_TRY(arena_get(ctx, (size_t)3 * (n > 0 ? n : 1), &tmp));
+        if (n > 0) SB_LAUNCH(ctx, k_widen, ceil_div(n, 256), 256, 0, src, n, tmp);
+        d_xyz = tmp;
+    }
     return voxel_sorted_dev(ctx, d_xyz, h_off, n_clouds, voxel, d_out_xyz, h_out_off, d_out_keys);
+}
+
+int voxel_downsample_dev(Ctx* ctx, const double* d_xyz, const i64* h_off, int n_clouds, double voxel,
+                         double* d_out_xyz, i64* h_out_off, i64* d_out_keys) {
+    PointSrc src;
+    src.base = d_xyz; src.f32 = 0; src.stride = 3;
+    return voxel_downsample_src(ctx, src, h_off, n_clouds, voxel, d_out_xyz, h_out_off, d_out_keys);
 }
 
 }  // namespace sb

@@ -94,6 +94,11 @@ SYMBOLS = {
                                     C.POINTER(ICPConfigC), C.POINTER(ICPResultC), _D]),
     "sb_register_batch_dev": (C.c_int, [_P, _P, _I64, C.c_int32, C.c_double, _I32, _I32, C.c_int32,
                                         C.POINTER(ICPConfigC), C.POINTER(ICPResultC), _D]),
+    "sb_register_batch_f32": (C.c_int, [_P, _P, C.c_int32, _I64, C.c_int32, C.c_double, _I32, _I32, C.c_int32,
+                                        C.POINTER(ICPConfigC), C.POINTER(ICPResultC), _D]),
+    "sb_register_batch_f32_dev": (C.c_int, [_P, _P, C.c_int32, _I64, C.c_int32, C.c_double, _I32, _I32, C.c_int32,
+                                            C.POINTER(ICPConfigC), C.POINTER(ICPResultC), _D]),
+    "sb_voxel_downsample_batch_f32": (C.c_int, [_P, _P, C.c_int32, _I64, C.c_int32, C.c_double, _D, _I64, _I64]),
     "sb_sc_compute": (C.c_int, [_P, _D, C.c_int64, _D]),
     "sb_sc_distance": (C.c_int, [_P, _D, _D, _D]),
     "sb_sc_distance_batch": (C.c_int, [_P, _D, _D, C.c_int32, _D]),
@@ -230,6 +235,21 @@ class Engine:
             return out[:m.value].copy(), keys[:m.value].copy()
         return out[:m.value].copy()
 
+    def voxel_downsample_batch_f32(self, points, offsets, voxel, return_keys=False):
+        """float32 rows (n x 3 or n x 4) widened on the device; same rows as voxel_downsample_batch of the widened input."""
+        pts = np.ascontiguousarray(points, dtype=np.float32)
+        off = np.ascontiguousarray(offsets, dtype=np.int64)
+        nc = off.shape[0] - 1
+        out = np.empty((max(pts.shape[0], 1), 3))
+        keys = np.empty((max(pts.shape[0], 1), 3), dtype=np.int64) if return_keys else None
+        out_off = np.zeros(nc + 1, dtype=np.int64)
+        self._check(self.lib.sb_voxel_downsample_batch_f32(self.h, _P(pts.ctypes.data), int(pts.shape[1]),
+                                                           off.ctypes.data_as(_I64), nc, float(voxel), _dp(out),
+                                                           out_off.ctypes.data_as(_I64),
+                                                           keys.ctypes.data_as(_I64) if return_keys else None))
+        m = int(out_off[-1])
+        return (out[:m], out_off, keys[:m]) if return_keys else (out[:m], out_off)
+
     def voxel_downsample_batch(self, points, offsets, voxel, return_keys=False):
         pts = _f64(points, 3)
         off = np.ascontiguousarray(offsets, dtype=np.int64)
@@ -272,7 +292,13 @@ class Engine:
         res = np.zeros(max(npairs, 1), dtype=ICP_DTYPE)
         rp = res.ctypes.data_as(C.POINTER(ICPResultC))
         sc = np.empty((nc, SB_SC_SIZE)) if want_sc else None
-        if device_ptr is None:
+        if device_ptr is None and isinstance(points, np.ndarray) and points.dtype == np.float32:
+            # float32 records as they are on disk (rows of 3 or 4 floats: xyz / KITTI xyzi), widened on the device
+            pts = np.ascontiguousarray(points)
+            s = self.lib.sb_register_batch_f32(self.h, _P(pts.ctypes.data), int(pts.shape[1]), off.ctypes.data_as(_I64),
+                                               nc, float(voxel), ps.ctypes.data_as(_I32), pt.ctypes.data_as(_I32),
+                                               npairs, C.byref(cfg), rp, _dp(sc) if want_sc else None)
+        elif device_ptr is None:
             pts = _f64(points, 3)
             s = self.lib.sb_register_batch(self.h, _dp(pts), off.ctypes.data_as(_I64), nc, float(voxel),
                                            ps.ctypes.data_as(_I32), pt.ctypes.data_as(_I32), npairs, C.byref(cfg), rp,

@@ -88,6 +88,34 @@ def test_voxel_hashed_and_sorted_paths_agree(engine, oracle, synth, scene, monke
     assert engine.last_voxel_path == 1
 
 
+def test_float32_ingest_matches_widened_input(engine, oracle, synth, scene):
+    """sb_*_f32 (rows of 3 or 4 float32, widened on the device; file_utils.cpp:91-97) == the fp64 entry points on the
+    host-widened rows, and the chunked host upload of sb_register_batch gives the device-resident result."""
+    s = oracle_lib.small_sensor(32, 600)
+    scans = [synth.scan(s, scene, (1.0 * i, 0.1 * i, 0.01 * i), 30 + i) for i in range(5)]
+    off = np.r_[0, np.cumsum([len(c) for c in scans])]
+    all64 = np.vstack(scans)
+    all32 = all64.astype(np.float32)
+    assert np.array_equal(all32.astype(np.float64), all64)  # the synthetic scans are float32-born
+    xyzi = np.hstack([all32, np.ones((len(all32), 1), np.float32)])  # KITTI records: x, y, z, intensity
+    ref, ref_off, ref_keys = engine.voxel_downsample_batch(all64, off, 0.5, return_keys=True)
+    for pts in (all32, xyzi):
+        out, out_off, keys = engine.voxel_downsample_batch_f32(pts, off, 0.5, return_keys=True)
+        assert np.array_equal(out_off, ref_off) and np.array_equal(keys, ref_keys) and np.array_equal(out, ref)
+    src, tgt = [1, 2, 3, 4], [0, 1, 2, 3]
+    r64, sc64 = engine.register_batch(all64, off, src, tgt, voxel=0.5, want_sc=True)
+    for pts in (all32, xyzi):
+        r32, sc32 = engine.register_batch(pts, off, src, tgt, voxel=0.5, want_sc=True)
+        assert np.array_equal(r32.transformations, r64.transformations)
+        assert np.array_equal(r32.num_iterations, r64.num_iterations) and np.array_equal(sc32, sc64)
+    o = oracle.icp_point_to_plane(oracle.voxel_downsample(scans[1], 0.5)[0], oracle.voxel_downsample(scans[0], 0.5)[0])
+    check_icp(r64[0], o)
+    # voxel <= 0 keeps the rows (file_utils.cpp:152)
+    r0 = engine.register_batch(all32[:off[2]], off[:3], [1], [0], voxel=0.0)
+    r1 = engine.register_batch(all64[:off[2]], off[:3], [1], [0], voxel=0.0)
+    assert np.array_equal(r0.transformations, r1.transformations)
+
+
 def test_voxel_edge_cases(engine, oracle):
     pts = np.array([[0.6, -0.6, 0.0], [0.6000000000000001, -0.2, 1e-300], [-1e-300, 0.2, -0.0]])
     out, keys = engine.voxel_downsample(pts, 0.2, return_keys=True)
