@@ -19,6 +19,9 @@ struct WarpStack {                       // shared memory, one per warp
     float dm[SB_MAX_LEVELS][32];         // lower-bound d^2 of "my" child at each level
     unsigned mask[SB_MAX_LEVELS];        // children still to visit at each level (warp-uniform)
     int base[SB_MAX_LEVELS];             // first child index at each level (warp-uniform)
+    double sd[32];                       // scratch of KnnVisitor::seed: the seeds in rank order
+    int si[32];
+    int sp[32];
 };
 
 struct ForestView {
@@ -222,29 +225,27 @@ struct KnnVisitor {
           lidx(0x7fffffff), lpos(-1), tau_d((double)INFINITY), tau_idx(0x7fffffff) {}
     __device__ __forceinline__ double tau() const { return tau_d; }
     // Seeds the list with up to 32 DISTINCT tree points (this lane's `pos`, cloud-local sorted position, or -1):
-    // distances to the new query are evaluated and the 32 entries are bitonic-sorted by (d2, idx) across the warp.
-    // Any k distinct real points bound the k-th nearest distance from above, so the result stays exact.
-    __device__ __forceinline__ void seed(int pos) {
+    // distances to the new query are evaluated and the 32 entries are put in (d2, idx) order across the warp — every
+    // lane counts the entries that precede its own (32 broadcasts) and drops its entry at that rank through shared
+    // memory.  Any k distinct real points bound the k-th nearest distance from above, so the result stays exact.
+    __device__ __forceinline__ void seed(int pos, WarpStack& S) {
         ld = (double)INFINITY; lidx = 0x7fffffff; lpos = -1;
         if (pos >= 0 && pos < T.n) {
             TreePoint P = load_point(F.pts + T.pt_off + pos);
             double d = dist2_rn(P.x, P.y, P.z, qx, qy, qz);
             if (d == d) { ld = d; lidx = P.idx; lpos = pos; }
         }
-#pragma unroll
-        for (int kk = 2; kk <= 32; kk <<= 1) {
-#pragma unroll
-            for (int j = kk >> 1; j > 0; j >>= 1) {
-                double od = shfl_d_xor(ld, j);
-                int oi = __shfl_xor_sync(0xffffffffu, lidx, j);
-                int op = __shfl_xor_sync(0xffffffffu, lpos, j);
-                bool lower = (lane & j) == 0;            // this lane is the lower index of the pair
-                bool asc = (lane & kk) == 0;             // sort direction of this block
-                bool other_less = lex_less(od, oi, ld, lidx);
-                bool take = (lower == asc) ? other_less : !other_less && !(od == ld && oi == lidx);
-                if (take) { ld = od; lidx = oi; lpos = op; }
-            }
+        int rank = 0;
+#pragma unroll 8
+        for (int j = 0; j < 32; ++j) {
+            const double od = shfl_d(ld, j);
+            const int oi = __shfl_sync(0xffffffffu, lidx, j);
+            rank += (od < ld || (od == ld && (oi < lidx || (oi == lidx && j < lane)))) ? 1 : 0;
         }
+        __syncwarp();
+        S.sd[rank] = ld; S.si[rank] = lidx; S.sp[rank] = lpos;
+        __syncwarp();
+        ld = S.sd[lane]; lidx = S.si[lane]; lpos = S.sp[lane];
         tau_d = shfl_d(ld, k - 1);
         tau_idx = __shfl_sync(0xffffffffu, lidx, k - 1);
     }
@@ -258,14 +259,17 @@ struct KnnVisitor {
             cidx = P.idx;
         }
         bool want = valid && lex_less(cd, cidx, tau_d, tau_idx);  // NaN compares false: never inserted
-        unsigned cm = __ballot_sync(0xffffffffu, want);
+        // points of this leaf that are in the list already (seeds): each leaf is visited once per query, so these
+        // are the only possible duplicates
+        const unsigned off = (unsigned)(lpos - p0);
+        const unsigned listed = __reduce_or_sync(0xffffffffu, (lpos >= 0 && off < 32u) ? (1u << off) : 0u);
+        unsigned cm = __ballot_sync(0xffffffffu, want) & ~listed;
         while (cm) {
             int b = __ffs(cm) - 1;
             cm &= cm - 1u;
             double bd = shfl_d(cd, b);
             int bi = __shfl_sync(0xffffffffu, cidx, b);
             if (!lex_less(bd, bi, tau_d, tau_idx)) continue;  // warp-uniform: the bound moved past it
-            if (__any_sync(0xffffffffu, lidx == bi)) continue;  // already listed (seeded entries)
             int bp = p0 + b;
             int pos = __popc(__ballot_sync(0xffffffffu, lex_less(ld, lidx, bd, bi)));  // sorted: a prefix
             double ud = __shfl_up_sync(0xffffffffu, ld, 1);
