@@ -48,6 +48,7 @@ struct IcpJob {
     sb_icp_result* results;
     PairState* state;
     double* partials;           // n_items x 28
+    unsigned char* item_done;   // n_items: 1 if k_icp_match already wrote the item's partial in this pass
     FallbackEntry* queue;       // capacity n_items x ITEM_Q
     int* act_pair;              // pairs the next pass works on (ascending), rebuilt after every solve
     i64* act_off;               // n_act + 1 prefix sums of their work items
@@ -218,6 +219,9 @@ __device__ __forceinline__ int grid_seed(const ForestView& F, const GridSlot* __
     return pos;
 }
 
+__device__ __forceinline__ void accumulate_item(const IcpJob* __restrict__ job, const ForestView& F, i64 it, i64 pt_off,
+                                                int lane, int my_pos, double cx, double cy, double cz);
+
 // Works on the pairs listed in job->act_pair: the ST_ACTIVE ones inside the loop, the ST_EXHAUSTED ones in the final
 // error pass (icp.hpp:235-252).  Work item = ITEM_Q consecutive source points of one pair (implicit: binary search
 // over the prefix sums act_off), one source point per lane.
@@ -246,8 +250,8 @@ __global__ void __launch_bounds__(IWARPS * 32) k_icp_match(IcpJob* __restrict__ 
         const double* Tm = job->results[pair].transformation;
         int bpos = -1;
         bool cert = false;
+        double cx = 0, cy = 0, cz = 0;
         if (lane < count) {
-            double cx, cy, cz;
             transform_point(Tm, job->src + 3 * (P.src_off + s0 + lane), cx, cy, cz);
             int center = job->match[it * ITEM_Q + lane];  // -1 before the first pass
             if (center < 0 || center >= T.n) center = grid_seed(F, job->grid, T, cx, cy, cz);
@@ -300,6 +304,9 @@ __global__ void __launch_bounds__(IWARPS * 32) k_icp_match(IcpJob* __restrict__ 
                 job->queue[base + __popc(todo & lanemask_lt())] = e;
             }
         }
+        // every point of the item has its proven correspondence: finish the item here (k_icp_accum skips it)
+        if (!todo) accumulate_item(job, F, it, T.pt_off, lane, lane < count ? bpos : -1, cx, cy, cz);
+        if (lane == 0) job->item_done[it] = todo ? 0 : 1;
         if (job->stats && lane == 0) {  // SB_ICP_STATS: buckets by iteration: 0, 1, 2..11, >= 12
             int bkt = job->state[pair].iter;
             bkt = bkt >= 12 ? 3 : (bkt >= 2 ? 2 : bkt);
@@ -341,7 +348,58 @@ __global__ void __launch_bounds__(IWARPS * 32) k_icp_fallback(IcpJob* __restrict
     }
 }
 
-// Residuals and the 28 sums of one work item from the correspondences in job->match.
+// Residual and the 28 sums of one work item (32 source points, one per lane; my_pos < 0: no correspondence, the lane
+// adds zeros): fixed-order butterfly, one 224-byte partial per item.  (cx, cy, cz) = the lane's transformed source
+// point.
+__device__ __forceinline__ void accumulate_item(const IcpJob* __restrict__ job, const ForestView& F, i64 it, i64 pt_off,
+                                                int lane, int my_pos, double cx, double cy, double cz) {
+    double tx = 0, ty = 0, tz = 0, nx = 0, ny = 0, nz = 0;
+    if (my_pos >= 0) {
+        TreePoint q = load_point(F.pts + pt_off + my_pos);
+        tx = q.x; ty = q.y; tz = q.z;
+        const double2* np = reinterpret_cast<const double2*>(job->normals + pt_off + my_pos);
+        double2 n01 = __ldg(np), n2 = __ldg(np + 1);
+        nx = n01.x; ny = n01.y; nz = n2.x;
+    } else {
+        cx = cy = cz = 0.0;
+    }
+    double J[6];
+    J[0] = cy * nz - cz * ny;  // p x n, icp.hpp:105
+    J[1] = cz * nx - cx * nz;
+    J[2] = cx * ny - cy * nx;
+    J[3] = nx; J[4] = ny; J[5] = nz;
+    const double b = ((tx - cx) * nx + (ty - cy) * ny) + (tz - cz) * nz;  // icp.hpp:116
+    // 28 sums over the item points: term i is kept by lane i
+    double mine = 0.0;
+    int t = 0;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+#pragma unroll
+        for (int c = a; c < 6; ++c) {
+            double v = J[a] * J[c];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += shfl_d_xor(v, o);
+            if (lane == t) mine = v;
+            ++t;
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+        double v = J[a] * b;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += shfl_d_xor(v, o);
+        if (lane == 21 + a) mine = v;
+    }
+    {
+        double v = b * b;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += shfl_d_xor(v, o);
+        if (lane == 27) mine = v;
+    }
+    if (lane < NSUM) job->partials[it * NSUM + lane] = mine;
+}
+
+// Residuals and sums of the work items that k_icp_match could not finish itself (some point was queued).
 __global__ void __launch_bounds__(IWARPS * 32) k_icp_accum(const IcpJob* __restrict__ job) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const ForestView F = job->F;
@@ -352,55 +410,18 @@ __global__ void __launch_bounds__(IWARPS * 32) k_icp_accum(const IcpJob* __restr
         const int pair = job->act_pair[a];
         const PairDesc P = job->pairs[pair];
         const i64 it = P.item_off + (ai - job->act_off[a]);
+        if (job->item_done[it]) continue;  // k_icp_match wrote this item's partial already
         const int s0 = (int)(it - P.item_off) * ITEM_Q;
         const int count = P.n_src - s0 < ITEM_Q ? P.n_src - s0 : ITEM_Q;
         const i64 pt_off = F.trees[P.tree].pt_off;
-        double cx = 0, cy = 0, cz = 0, tx = 0, ty = 0, tz = 0, nx = 0, ny = 0, nz = 0;
+        double cx = 0, cy = 0, cz = 0;
+        int my_pos = -1;
         if (lane < count) {
-            const int my_pos = job->match[it * ITEM_Q + lane];
-            if (my_pos >= 0) {
+            my_pos = job->match[it * ITEM_Q + lane];
+            if (my_pos >= 0)
                 transform_point(job->results[pair].transformation, job->src + 3 * (P.src_off + s0 + lane), cx, cy, cz);
-                TreePoint q = load_point(F.pts + pt_off + my_pos);
-                tx = q.x; ty = q.y; tz = q.z;
-                const double2* np = reinterpret_cast<const double2*>(job->normals + pt_off + my_pos);
-                double2 n01 = __ldg(np), n2 = __ldg(np + 1);
-                nx = n01.x; ny = n01.y; nz = n2.x;
-            }
         }
-        double J[6];
-        J[0] = cy * nz - cz * ny;  // p x n, icp.hpp:105
-        J[1] = cz * nx - cx * nz;
-        J[2] = cx * ny - cy * nx;
-        J[3] = nx; J[4] = ny; J[5] = nz;
-        const double b = ((tx - cx) * nx + (ty - cy) * ny) + (tz - cz) * nz;  // icp.hpp:116
-        // 28 sums over the item points (idle lanes add zeros): fixed-order butterfly, term i is kept by lane i
-        double mine = 0.0;
-        int t = 0;
-#pragma unroll
-        for (int a = 0; a < 6; ++a) {
-#pragma unroll
-            for (int c = a; c < 6; ++c) {
-                double v = J[a] * J[c];
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v += shfl_d_xor(v, o);
-                if (lane == t) mine = v;
-                ++t;
-            }
-        }
-#pragma unroll
-        for (int a = 0; a < 6; ++a) {
-            double v = J[a] * b;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += shfl_d_xor(v, o);
-            if (lane == 21 + a) mine = v;
-        }
-        {
-            double v = b * b;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += shfl_d_xor(v, o);
-            if (lane == 27) mine = v;
-        }
-        if (lane < NSUM) job->partials[it * NSUM + lane] = mine;
+        accumulate_item(job, F, it, pt_off, lane, my_pos, cx, cy, cz);
     }
 }
 
@@ -491,36 +512,21 @@ __device__ __forceinline__ void mat4_mul(const double (&A)[16], const double* B,
         }
 }
 
-// sums the pair's partials in item order; lane l gets sum l (l < 28)
-__device__ __forceinline__ double sum_partials(const IcpJob* job, const PairDesc& P, int lane) {
-    double s = 0.0;
-    if (lane < NSUM) {
-        const double* base = job->partials + P.item_off * NSUM + lane;
-        int i = 0;
-        for (; i + 8 <= P.n_items; i += 8) {  // loads issued together, additions in item order
-            double v[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = base[(i64)(i + u) * NSUM];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) s += v[u];
-        }
-        for (; i < P.n_items; ++i) s += base[(i64)i * NSUM];
-    }
-    return s;
-}
-
-// mode 0: loop body (icp.hpp:181-232); mode 1: final error (icp.hpp:235-255)
+// mode 0: loop body (icp.hpp:181-232) for the pairs of the active list; mode 1: final error (icp.hpp:235-255).
+// One block per pair: warp w adds the partials of the items w, w+8, w+16, ... in that order, warp 0 adds the eight
+// warp sums in warp order — a fixed association, so the result is run-to-run and batch-composition independent.
 __global__ void __launch_bounds__(256) k_icp_solve(IcpJob* __restrict__ job, int mode, cudaGraphConditionalHandle cond,
                                                    int use_cond) {
-    const int lane = threadIdx.x & 31;
-    const int wpb = blockDim.x >> 5;
-    const int n = job->n_pairs;
-    for (int p = blockIdx.x * wpb + (threadIdx.x >> 5); p < n; p += gridDim.x * wpb) {
-        PairState st = job->state[p];
+    __shared__ double s_part[8][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_loop = mode == 0 ? job->n_act : job->n_pairs;
+    for (int a = blockIdx.x; a < n_loop; a += gridDim.x) {
+        const int p = mode == 0 ? job->act_pair[a] : a;
+        const PairState st = job->state[p];  // block-uniform
         sb_icp_result& R = job->results[p];
         if (mode == 1) {
             if (st.state == ST_CONVERGED) {
-                if (lane == 0) {  // broke out of the loop: the final pass repeats the last error (Appendix A.5)
+                if (threadIdx.x == 0) {  // broke out of the loop: the final pass repeats the last error (Appendix A.5)
                     double e = R.error_history[R.history_len - 1];
                     R.final_error = e;
                     R.error_history[R.history_len] = e;
@@ -534,8 +540,27 @@ __global__ void __launch_bounds__(256) k_icp_solve(IcpJob* __restrict__ job, int
         } else if (st.state != ST_ACTIVE) {
             continue;
         }
-        PairDesc P = job->pairs[p];
-        double s = sum_partials(job, P, lane);
+        const PairDesc P = job->pairs[p];
+        {
+            double s = 0.0;
+            if (lane < NSUM) {
+                const double* base = job->partials + P.item_off * NSUM + lane;
+                int i = warp;
+                for (; i + 24 < P.n_items; i += 32) {  // four loads in flight, additions in item order
+                    const double v0 = base[(i64)i * NSUM], v1 = base[(i64)(i + 8) * NSUM],
+                                 v2 = base[(i64)(i + 16) * NSUM], v3 = base[(i64)(i + 24) * NSUM];
+                    s += v0; s += v1; s += v2; s += v3;
+                }
+                for (; i < P.n_items; i += 8) s += base[(i64)i * NSUM];
+            }
+            __syncthreads();  // the previous pair's sums have been consumed
+            s_part[warp][lane] = s;
+            __syncthreads();
+        }
+        if (warp != 0) continue;
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += s_part[w][lane];
         double sr2 = shfl_d(s, 27);
         double e = sqrt(sr2 / (double)P.n_src);  // icp.hpp:198-207
         if (mode == 1) {
@@ -552,16 +577,16 @@ __global__ void __launch_bounds__(256) k_icp_solve(IcpJob* __restrict__ job, int
         {
             int t = 0;
 #pragma unroll
-            for (int a = 0; a < 6; ++a)
+            for (int a2 = 0; a2 < 6; ++a2)
 #pragma unroll
-                for (int c = a; c < 6; ++c) {
+                for (int c = a2; c < 6; ++c) {
                     double v = shfl_d(s, t);
-                    A[a][c] = v;
-                    A[c][a] = v;
+                    A[a2][c] = v;
+                    A[c][a2] = v;
                     ++t;
                 }
 #pragma unroll
-            for (int a = 0; a < 6; ++a) g[a] = shfl_d(s, 21 + a);
+            for (int a2 = 0; a2 < 6; ++a2) g[a2] = shfl_d(s, 21 + a2);
         }
         if (lane == 0) {
             int hl = R.history_len;
@@ -756,7 +781,7 @@ static int icp_graph_get(Ctx* ctx, IcpGraph** out) {
     *out = G;
     SB_CUDA(ctx, cudaMalloc(&G->d_job, sizeof(IcpJob)));
     G->iter_grid = ctx->sm_count * 8;
-    G->solve_grid = ctx->sm_count;
+    G->solve_grid = ctx->sm_count * 4;
     if (getenv("SB_ICP_STATS")) {
         SB_CUDA(ctx, cudaMalloc(&G->d_stats, 8 * sizeof(unsigned long long)));
         SB_CUDA(ctx, cudaMemset(G->d_stats, 0, 8 * sizeof(unsigned long long)));
@@ -812,6 +837,7 @@ int icp_batch(Ctx* ctx, const Forest* f, const double* d_src, const std::vector<
     PairState* d_state;
     double* d_part;
     FallbackEntry* d_queue;
+    unsigned char* d_item_done;
     int* d_act_pair;
     i64* d_act_off;
     size_t ni = (size_t)(n_items > 0 ? n_items : 1);
@@ -821,6 +847,7 @@ int icp_batch(Ctx* ctx, const Forest* f, const double* d_src, const std::vector<
     SB_TRY(arena_get(ctx, (size_t)n_pairs, &d_state));
     SB_TRY(arena_get(ctx, ni * NSUM, &d_part));
     SB_TRY(arena_get(ctx, ni * ITEM_Q, &d_queue));
+    SB_TRY(arena_get(ctx, ni, &d_item_done));
     SB_TRY(arena_get(ctx, (size_t)n_pairs, &d_act_pair));
     SB_TRY(arena_get(ctx, (size_t)n_pairs + 1, &d_act_off));
     SB_CUDA(ctx, cudaMemcpyAsync(d_pairs, pairs.data(), sizeof(PairDesc) * n_pairs, cudaMemcpyHostToDevice, ctx->stream));
@@ -842,6 +869,7 @@ int icp_batch(Ctx* ctx, const Forest* f, const double* d_src, const std::vector<
     job.state = d_state;
     job.partials = d_part;
     job.queue = d_queue;
+    job.item_done = d_item_done;
     job.act_pair = d_act_pair;
     job.act_off = d_act_off;
     memcpy(job.T0, cfg->initial_transform, sizeof(job.T0));
