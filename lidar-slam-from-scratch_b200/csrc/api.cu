@@ -3,6 +3,7 @@
 // There is no CPU implementation of any stage behind these entry points.
 #include <chrono>
 #include <cstdarg>
+#include <functional>
 #include <cstdlib>
 #include <algorithm>
 
@@ -145,7 +146,8 @@ static std::vector<QueryItem> items_for(i64 nq) {
 // voxel grid of chunk c runs while chunk c+1 is in flight (pinned host memory; pageable memory still works, without
 // the overlap).  d_ds receives the downsampled rows of all clouds, off_ds their CSR offsets.
 static int upload_voxel_pipelined(Ctx* ctx, const void* h_raw, int f32, int stride, const i64* offsets, int n_clouds,
-                                  double voxel, double* d_ds, i64* off_ds) {
+                                  double voxel, double* d_ds, i64* off_ds,
+                                  const std::function<int(int, int)>& after_chunk) {
     const size_t row_bytes = (size_t)stride * (f32 ? sizeof(float) : sizeof(double));
     const i64 n = offsets[n_clouds];
     char* d_raw;
@@ -154,10 +156,12 @@ static int upload_voxel_pipelined(Ctx* ctx, const void* h_raw, int f32, int stri
         SB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
         for (int i = 0; i < 2; ++i) SB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->copy_ev[i], cudaEventDisableTiming));
     }
-    // chunk boundaries: whole clouds, about 96 MB each
+    // chunk boundaries: whole clouds, about 192 MB each (SB_CHUNK_MB): smaller chunks pay more per-chunk host
+    // round trips than they gain in overlap (measured: 24 MB 93 ms, 96 MB 64 ms, 192 MB 63 ms, 384 MB 66 ms per C2 step)
     std::vector<int> cb(1, 0);
     {
-        const i64 target_rows = (i64)((96u << 20) / row_bytes);
+        static const long chunk_mb = getenv("SB_CHUNK_MB") ? atol(getenv("SB_CHUNK_MB")) : 192;
+        const i64 target_rows = (i64)(((size_t)(chunk_mb > 0 ? chunk_mb : 192) << 20) / row_bytes);
         i64 start = 0;
         for (int c = 0; c < n_clouds; ++c)
             if (offsets[c + 1] - start >= target_rows || c == n_clouds - 1) {
@@ -193,6 +197,7 @@ static int upload_voxel_pipelined(Ctx* ctx, const void* h_raw, int f32, int stri
         SB_TRY(voxel_downsample_src(ctx, src, in_off.data(), nc, voxel, d_ds + 3 * off_ds[c0], out_off.data(), nullptr));
         arena_release(ctx, mark);
         for (int i = 1; i <= nc; ++i) off_ds[c0 + i] = off_ds[c0] + out_off[i];
+        if (after_chunk) SB_TRY(after_chunk(c0, c0 + nc));  // more device work on these clouds while the next chunk copies
     }
     return SB_OK;
 }
@@ -207,22 +212,46 @@ static int register_batch_impl(Ctx* ctx, PointSrc src, const void* h_raw, const 
             return fail(ctx, SB_ERR_INVALID_ARG, "register_batch: pair %d references a cloud outside [0, %d)", p, n_clouds);
     if (cfg->normals_k < 1 || cfg->normals_k > SB_MAX_K)
         return fail(ctx, SB_ERR_INVALID_ARG, "normals_k %d outside [1, %d]", cfg->normals_k, SB_MAX_K);
+    // one tree + normals per distinct target cloud (icp.hpp:166-171), numbered in cloud order
+    std::vector<int> tree_of((size_t)n_clouds, -1);
+    int n_targets = 0;
+    for (int p = 0; p < n_pairs; ++p) tree_of[pair_tgt[p]] = 0;
+    for (int c = 0; c < n_clouds; ++c)
+        if (tree_of[c] == 0) tree_of[c] = n_targets++;
+    Forest F;
+    F.in_arena = true;
+    SB_TRY(forest_reserve(ctx, &F, n_targets));
+    std::vector<i64> off(offsets, offsets + n_clouds + 1);
+    const double* d_pts = nullptr;
+    // index + normals of the target clouds in [c0, c1) (their downsampled rows are final)
+    auto index_clouds = [&](int c0, int c1) -> int {
+        std::vector<int> ids;
+        for (int c = c0; c < c1; ++c)
+            if (tree_of[c] >= 0) ids.push_back(c);
+        if (ids.empty()) return SB_OK;
+        if (!h_raw) stage_mark(ctx, STAGE_INDEX);
+        SB_TRY(forest_append(ctx, &F, d_pts, off.data(), ids.data(), (int)ids.size()));
+        if (!h_raw) stage_mark(ctx, STAGE_NORMALS);
+        return forest_normals(ctx, &F, cfg->normals_k, nullptr, nullptr);
+    };
     // 1. voxel grid (slam_node.cpp:122)
     stage_mark(ctx, STAGE_VOXEL);
     const i64 n_raw = offsets[n_clouds];
-    const double* d_pts = nullptr;
-    std::vector<i64> off(offsets, offsets + n_clouds + 1);
+    bool indexed = false;
     if (voxel > 0) {
         double* d_ds;
         SB_TRY(arena_get(ctx, (size_t)3 * (n_raw > 0 ? n_raw : 1), &d_ds));
-        if (h_raw) {
-            SB_TRY(upload_voxel_pipelined(ctx, h_raw, src.f32, src.stride, offsets, n_clouds, voxel, d_ds, off.data()));
+        d_pts = d_ds;
+        if (h_raw) {  // upload, voxel grid, index and normals chunk by chunk: the copies overlap all of it
+            SB_TRY(upload_voxel_pipelined(ctx, h_raw, src.f32, src.stride, offsets, n_clouds, voxel, d_ds, off.data(),
+                                          n_pairs > 0 ? std::function<int(int, int)>(index_clouds)
+                                                      : std::function<int(int, int)>()));
+            indexed = true;
         } else {
             const ArenaMark mark = arena_mark(ctx);
             SB_TRY(voxel_downsample_src(ctx, src, offsets, n_clouds, voxel, d_ds, off.data(), nullptr));
             arena_release(ctx, mark);
         }
-        d_pts = d_ds;
     } else {  // no voxel grid: the clouds themselves, as packed fp64 rows on the device
         double* d_all;
         SB_TRY(arena_get(ctx, (size_t)3 * (n_raw > 0 ? n_raw : 1), &d_all));
@@ -257,23 +286,12 @@ static int register_batch_impl(Ctx* ctx, PointSrc src, const void* h_raw, const 
     if (n_pairs == 0) {
         stage_mark(ctx, STAGE_END);
         SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        forest_free(&F);
         return SB_OK;
     }
-    stage_mark(ctx, STAGE_INDEX);
-    // 3. one tree + normals per distinct target cloud (icp.hpp:166-171)
-    std::vector<int> tree_of((size_t)n_clouds, -1), cloud_ids;
-    for (int p = 0; p < n_pairs; ++p) {
-        int t = pair_tgt[p];
-        if (tree_of[t] < 0) {
-            tree_of[t] = (int)cloud_ids.size();
-            cloud_ids.push_back(t);
-        }
-    }
-    Forest F;
-    F.in_arena = true;
-    int s = forest_build(ctx, d_pts, off.data(), cloud_ids.data(), (int)cloud_ids.size(), &F);
-    stage_mark(ctx, STAGE_NORMALS);
-    if (s == SB_OK) s = forest_normals(ctx, &F, cfg->normals_k, nullptr, nullptr);
+    // 3. index + normals of the targets (already done chunk by chunk on the pipelined host path)
+    int s = SB_OK;
+    if (!indexed) s = index_clouds(0, n_clouds);
     stage_mark(ctx, STAGE_ICP);
     ctx->last_counts[2] = F.n_points;
     // 4. the ICP loop for all pairs (icp.hpp:174-255)
@@ -602,7 +620,7 @@ int sb_index_find_correspondences(sb_index* index, const double* source, int64_t
     const Forest& F = index->forest;
     i64 n = F.n_points;
     std::vector<TreePoint> pts((size_t)n);
-    SB_TRY(download(c, pts.data(), F.pts, sizeof(TreePoint) * n));
+    SB_TRY(download(c, pts.data(), F.batches[0].pts, sizeof(TreePoint) * n));
     SB_CUDA(c, cudaStreamSynchronize(c->stream));
     std::vector<int> pos_of((size_t)n);
     for (i64 p = 0; p < n; ++p) pos_of[pts[p].idx] = (int)p;

@@ -185,8 +185,20 @@ int voxel_downsample_dev(Ctx* ctx, const double* d_xyz, const i64* h_off, int n_
 // ---------------------------------------------------------------------------------------------------------------
 #define SB_MAX_LEVELS 7
 
+struct TreePoint;
+struct TreeNormal;
+struct NbrEntry;
+struct GridSlot;
 struct TreeDesc {      // device-resident, one per indexed cloud
-    i64 pt_off;        // first sorted point of this cloud in the forest's SoA arrays
+    // The arrays of the batch of trees this tree was built with (forest_append): several batches can live in one
+    // forest, e.g. one per uploaded chunk of clouds, so every tree carries its own base pointers.
+    const TreePoint* pts;   // Morton-sorted points
+    const float* boxes;     // 6 floats per box: lo xyz (rounded down), hi xyz (up)
+    TreeNormal* nrm;        // per sorted point, filled by forest_normals
+    NbrEntry* nbr;          // normals_k entries per sorted point, filled by forest_normals
+    GridSlot* grid;         // seed-grid slots, filled by forest_normals
+    i64 out_off;       // first row of this cloud in forest-wide outputs in ORIGINAL row order
+    i64 pt_off;        // first sorted point of this cloud in pts / nrm / nbr
     int n;             // points
     int top;           // top level (boxes at that level <= 32)
     i64 box_off[SB_MAX_LEVELS];  // first box of level l in the forest's box array
@@ -227,24 +239,33 @@ struct NbrEntry {
     float r;   // sqrt(d2) rounded down and shrunk by 1e-6 (+inf for padding)
 };
 
+struct ForestBatch {    // the arrays of the trees [t0, t0 + n_trees) appended together
+    int t0 = 0, n_trees = 0;
+    i64 n_points = 0, n_boxes = 0, n_slots = 0;
+    TreePoint* pts = nullptr;
+    float* boxes = nullptr;
+    TreeNormal* normals = nullptr;
+    NbrEntry* nbr = nullptr;
+    GridSlot* grid = nullptr;
+};
+
 struct Forest {
     Ctx* ctx = nullptr;
-    int n_trees = 0;
-    i64 n_points = 0, n_boxes = 0;
-    // device arrays (owned, cudaMalloc)
-    TreePoint* pts = nullptr;      // Morton-sorted points
-    float* boxes = nullptr;        // 6 floats per box: lo xyz (rounded down), hi xyz (up)
-    TreeNormal* normals = nullptr; // per sorted point, filled by forest_normals
-    NbrEntry* nbr = nullptr;       // normals_k entries per sorted point, filled by forest_normals
-    GridSlot* grid = nullptr;      // n_slots seed-grid slots, filled by forest_normals
-    i64 n_slots = 0;
+    int n_trees = 0, cap_trees = 0;
+    i64 n_points = 0;       // over all batches
+    std::vector<ForestBatch> batches;
     TreeDesc* d_trees = nullptr;
-    std::vector<TreeDesc> h_trees;
-    int normals_k = 0;
+    std::vector<TreeDesc> h_trees;   // host mirror (the seed-grid fields glo/gext/ginv are device-only)
+    int normals_k = 0;      // 0: no normals yet
     bool in_arena = false;  // arrays live in the context arena (valid until the next C-ABI call), not cudaMalloc
 };
 
-// Builds trees over clouds `cloud_ids[0..n_trees)` of a device CSR point set.  d_xyz rows are row-major fp64.
+// Room for `cap_trees` tree descriptors (forest_append fails beyond that).
+int forest_reserve(Ctx* ctx, Forest* f, int cap_trees);
+// Appends trees over clouds `cloud_ids[0..n_new)` (null: 0..n_new-1) of a device CSR point set as one batch;
+// d_xyz rows are row-major fp64.  The new trees are [f->n_trees - n_new, f->n_trees).
+int forest_append(Ctx* ctx, Forest* f, const double* d_xyz, const i64* h_off, const int* cloud_ids, int n_new);
+// reserve + append: a forest of exactly these trees
 int forest_build(Ctx* ctx, const double* d_xyz, const i64* h_off, const int* cloud_ids, int n_trees, Forest* out);
 void forest_free(Forest* f);
 
@@ -261,9 +282,10 @@ int forest_knn(Ctx* ctx, const Forest* f, const double* d_q, const QueryItem* d_
 // 1-NN over arbitrary query rows.
 int forest_nearest(Ctx* ctx, const Forest* f, const double* d_q, const QueryItem* d_items, i64 n_items,
                    int* d_out_idx, double* d_out_d2, int* d_out_pos);
-// Normals of every tree's own points (icp.hpp:23-67) into f->normals (sorted order); optional outputs in the
-// ORIGINAL row order of the clouds as laid out by (h_off, cloud_ids): d_out_normals[3*(pt_off+orig)] etc.
-int forest_normals(Ctx* ctx, Forest* f, int k, double* d_out_normals, double* d_out_evals);
+// Normals, neighbour graph and seed grid of the trees of batch `batch` (-1: the last one) (icp.hpp:23-67); optional
+// outputs in the ORIGINAL row order of the clouds: d_out_normals[3*(out_off+orig)] etc.  All batches of a forest
+// must use the same k.
+int forest_normals(Ctx* ctx, Forest* f, int k, double* d_out_normals, double* d_out_evals, int batch = -1);
 // host helper: items covering all points of all trees (queries = the trees' own sorted points)
 int make_items_dev(Ctx* ctx, const std::vector<QueryItem>& items, QueryItem** d_items);
 

@@ -194,29 +194,52 @@ __global__ void __launch_bounds__(256) k_boxes_up(const TreeDesc* __restrict__ t
 void forest_free(Forest* f) {
     if (!f) return;
     if (!f->in_arena) {
-        cudaFree(f->pts); cudaFree(f->boxes); cudaFree(f->normals); cudaFree(f->nbr); cudaFree(f->grid);
+        for (ForestBatch& B : f->batches) {
+            cudaFree(B.pts); cudaFree(B.boxes); cudaFree(B.normals); cudaFree(B.nbr); cudaFree(B.grid);
+        }
         cudaFree(f->d_trees);
     }
-    f->pts = nullptr; f->boxes = nullptr; f->normals = nullptr; f->nbr = nullptr; f->grid = nullptr; f->d_trees = nullptr;
+    f->batches.clear();
+    f->d_trees = nullptr;
     f->h_trees.clear();
-    f->n_trees = 0; f->n_points = 0; f->n_boxes = 0;
+    f->n_trees = 0; f->cap_trees = 0; f->n_points = 0; f->normals_k = 0;
+}
+
+int forest_reserve(Ctx* ctx, Forest* f, int cap_trees) {
+    f->ctx = ctx;
+    if (f->d_trees) return fail(ctx, SB_ERR_INVALID_ARG, "forest: already reserved");
+    const size_t cap = (size_t)(cap_trees > 0 ? cap_trees : 1);
+    if (f->in_arena) SB_TRY(arena_get(ctx, cap, &f->d_trees));
+    else SB_CUDA(ctx, cudaMalloc(&f->d_trees, sizeof(TreeDesc) * cap));
+    f->cap_trees = cap_trees;
+    f->h_trees.reserve(cap);
+    return SB_OK;
 }
 
 int forest_build(Ctx* ctx, const double* d_xyz, const i64* h_off, const int* cloud_ids, int n_trees, Forest* f) {
-    f->ctx = ctx;
-    f->n_trees = n_trees;
-    f->h_trees.assign((size_t)n_trees, TreeDesc());
-    std::vector<i64> src_off((size_t)n_trees), seg_off((size_t)n_trees + 1);
+    SB_TRY(forest_reserve(ctx, f, n_trees));
+    return forest_append(ctx, f, d_xyz, h_off, cloud_ids, n_trees);
+}
+
+int forest_append(Ctx* ctx, Forest* f, const double* d_xyz, const i64* h_off, const int* cloud_ids, int n_new) {
+    if (f->n_trees + n_new > f->cap_trees) return fail(ctx, SB_ERR_CAPACITY, "forest: more trees than reserved");
+    const int t0 = f->n_trees;
+    ForestBatch B;
+    B.t0 = t0;
+    B.n_trees = n_new;
+    f->h_trees.resize((size_t)(t0 + n_new));
+    std::vector<i64> src_off((size_t)n_new), seg_off((size_t)n_new + 1);
     std::vector<Chunk> chunks;
     i64 np = 0, nb = 0, n_slots = 0;
     int max_top = 0;
-    for (int t = 0; t < n_trees; ++t) {
+    for (int t = 0; t < n_new; ++t) {
         int c = cloud_ids ? cloud_ids[t] : t;
         i64 n64 = h_off[c + 1] - h_off[c];
         if (n64 < 0 || n64 > 0x7fffffffLL) return fail(ctx, SB_ERR_RANGE, "index: cloud %d has %lld rows", c, n64);
-        TreeDesc& T = f->h_trees[t];
+        TreeDesc& T = f->h_trees[(size_t)(t0 + t)];
         memset(&T, 0, sizeof(T));
         T.pt_off = np;
+        T.out_off = f->n_points + np;
         T.n = (int)n64;
         src_off[t] = h_off[c];
         seg_off[t] = np;
@@ -245,53 +268,62 @@ int forest_build(Ctx* ctx, const double* d_xyz, const i64* h_off, const int* clo
         }
         np += T.n;
     }
-    seg_off[n_trees] = np;
-    f->n_points = np;
-    f->n_boxes = nb;
-    f->n_slots = n_slots;
-    if (np >= (i64)0xffffffffLL) return fail(ctx, SB_ERR_RANGE, "index: more than 2^32-1 points in one forest");
+    seg_off[n_new] = np;
+    B.n_points = np;
+    B.n_boxes = nb;
+    B.n_slots = n_slots;
+    if (np >= (i64)0xffffffffLL) return fail(ctx, SB_ERR_RANGE, "index: more than 2^32-1 points in one batch of trees");
     size_t npa = (size_t)(np > 0 ? np : 1), nba = (size_t)(nb > 0 ? nb : 1);
     if (f->in_arena) {
-        SB_TRY(arena_get(ctx, (size_t)(n_trees > 0 ? n_trees : 1), &f->d_trees));
-        SB_TRY(arena_get(ctx, npa, &f->pts));
-        SB_TRY(arena_get(ctx, 6 * nba, &f->boxes));
+        SB_TRY(arena_get(ctx, npa, &B.pts));
+        SB_TRY(arena_get(ctx, 6 * nba, &B.boxes));
     } else {
-        SB_CUDA(ctx, cudaMalloc(&f->d_trees, sizeof(TreeDesc) * (size_t)(n_trees > 0 ? n_trees : 1)));
-        SB_CUDA(ctx, cudaMalloc(&f->pts, sizeof(TreePoint) * npa));
-        SB_CUDA(ctx, cudaMalloc(&f->boxes, sizeof(float) * 6 * nba));
+        SB_CUDA(ctx, cudaMalloc(&B.pts, sizeof(TreePoint) * npa));
+        SB_CUDA(ctx, cudaMalloc(&B.boxes, sizeof(float) * 6 * nba));
     }
-    SB_CUDA(ctx, cudaMemcpyAsync(f->d_trees, f->h_trees.data(), sizeof(TreeDesc) * (size_t)n_trees,
-                                 cudaMemcpyHostToDevice, ctx->stream));
+    for (int t = 0; t < n_new; ++t) {
+        f->h_trees[(size_t)(t0 + t)].pts = B.pts;
+        f->h_trees[(size_t)(t0 + t)].boxes = B.boxes;
+    }
+    f->batches.push_back(B);
+    f->n_trees = t0 + n_new;
+    f->n_points += np;
+    TreeDesc* d_new = f->d_trees + t0;
+    if (n_new > 0)
+        SB_CUDA(ctx, cudaMemcpyAsync(d_new, f->h_trees.data() + t0, sizeof(TreeDesc) * (size_t)n_new, cudaMemcpyHostToDevice,
+                                     ctx->stream));
     if (np == 0) return SB_OK;
 
+    const ArenaMark mark = arena_mark(ctx);  // everything below is scratch of this build
     i64* d_src_off;
     Chunk* d_chunks;
     long long* d_bb;
     u64 *ka, *kb, *ks;
     uint32_t *va, *vb, *vs;
-    SB_TRY(arena_get(ctx, (size_t)n_trees, &d_src_off));
+    SB_TRY(arena_get(ctx, (size_t)n_new, &d_src_off));
     SB_TRY(arena_get(ctx, chunks.size(), &d_chunks));
-    SB_TRY(arena_get(ctx, (size_t)6 * n_trees, &d_bb));
+    SB_TRY(arena_get(ctx, (size_t)6 * n_new, &d_bb));
     SB_TRY(arena_get(ctx, (size_t)np, &ka));
     SB_TRY(arena_get(ctx, (size_t)np, &kb));
     SB_TRY(arena_get(ctx, (size_t)np, &va));
     SB_TRY(arena_get(ctx, (size_t)np, &vb));
-    SB_CUDA(ctx, cudaMemcpyAsync(d_src_off, src_off.data(), sizeof(i64) * (size_t)n_trees, cudaMemcpyHostToDevice, ctx->stream));
+    SB_CUDA(ctx, cudaMemcpyAsync(d_src_off, src_off.data(), sizeof(i64) * (size_t)n_new, cudaMemcpyHostToDevice, ctx->stream));
     SB_CUDA(ctx, cudaMemcpyAsync(d_chunks, chunks.data(), sizeof(Chunk) * chunks.size(), cudaMemcpyHostToDevice, ctx->stream));
     {
-        std::vector<long long> init((size_t)6 * n_trees);
-        for (int t = 0; t < n_trees; ++t)
+        std::vector<long long> init((size_t)6 * n_new);
+        for (int t = 0; t < n_new; ++t)
             for (int a = 0; a < 3; ++a) { init[6 * t + a] = INT64_MAX; init[6 * t + 3 + a] = INT64_MIN; }
         SB_CUDA(ctx, cudaMemcpyAsync(d_bb, init.data(), sizeof(long long) * init.size(), cudaMemcpyHostToDevice, ctx->stream));
         SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the host vectors above go out of scope
     }
     unsigned nch = (unsigned)chunks.size();
     SB_LAUNCH(ctx, k_bbox, nch, 256, 0, d_xyz, d_src_off, d_chunks, d_bb);
-    SB_LAUNCH(ctx, k_morton, nch, 256, 0, d_xyz, d_src_off, d_chunks, d_bb, f->d_trees, ka, va);
-    SB_LAUNCH(ctx, k_tree_bounds, ceil_div(n_trees, 128), 128, 0, f->d_trees, d_bb, n_trees);
-    SB_TRY(segmented_sort_pairs(ctx, ka, kb, va, vb, seg_off.data(), n_trees, 30, &ks, &vs));
-    SB_LAUNCH(ctx, k_gather_leaves, nch, 256, 0, d_xyz, d_src_off, d_chunks, f->d_trees, vs, f->pts, f->boxes);
-    for (int l = 1; l <= max_top; ++l) SB_LAUNCH(ctx, k_boxes_up, (unsigned)n_trees, 256, 0, f->d_trees, l, f->boxes);
+    SB_LAUNCH(ctx, k_morton, nch, 256, 0, d_xyz, d_src_off, d_chunks, d_bb, d_new, ka, va);
+    SB_LAUNCH(ctx, k_tree_bounds, ceil_div(n_new, 128), 128, 0, d_new, d_bb, n_new);
+    SB_TRY(segmented_sort_pairs(ctx, ka, kb, va, vb, seg_off.data(), n_new, 30, &ks, &vs));
+    SB_LAUNCH(ctx, k_gather_leaves, nch, 256, 0, d_xyz, d_src_off, d_chunks, d_new, vs, B.pts, B.boxes);
+    for (int l = 1; l <= max_top; ++l) SB_LAUNCH(ctx, k_boxes_up, (unsigned)n_new, 256, 0, d_new, l, B.boxes);
+    arena_release(ctx, mark);
     return SB_OK;
 }
 
@@ -437,7 +469,7 @@ __global__ void __launch_bounds__(QWARPS * 32) k_knn(ForestView F, const double*
         double mx = 0, my = 0, mz = 0;
         if (lane < I.count) {
             if (MODE == 1) {
-                TreePoint P = load_point(F.pts + T.pt_off + I.q_off + lane);
+                TreePoint P = load_point(T.pts + T.pt_off + I.q_off + lane);
                 mx = P.x; my = P.y; mz = P.z;
             } else {
                 const double* p = q + 3 * (I.q_off + lane);
@@ -485,14 +517,14 @@ __global__ void __launch_bounds__(QWARPS * 32) k_knn(ForestView F, const double*
                 if (m >= 3) {  // icp.hpp:34-37
                     double c0 = 0.0, c1 = 0.0, c2 = 0.0;
                     for (int j = 0; j < m; ++j) {  // icp.hpp:40-44, neighbours ascending by (d2, idx)
-                        TreePoint P = load_point(F.pts + T.pt_off + nb[j]);
+                        TreePoint P = load_point(T.pts + T.pt_off + nb[j]);
                         c0 += P.x; c1 += P.y; c2 += P.z;
                     }
                     double md = (double)m;
                     c0 /= md; c1 /= md; c2 /= md;
                     double C00 = 0, C01 = 0, C02 = 0, C11 = 0, C12 = 0, C22 = 0;
                     for (int j = 0; j < m; ++j) {  // icp.hpp:47-52
-                        TreePoint P = load_point(F.pts + T.pt_off + nb[j]);
+                        TreePoint P = load_point(T.pts + T.pt_off + nb[j]);
                         double d0 = P.x - c0, d1 = P.y - c1, d2 = P.z - c2;
                         C00 += d0 * d0; C01 += d0 * d1; C02 += d0 * d2;
                         C11 += d1 * d1; C12 += d1 * d2; C22 += d2 * d2;
@@ -519,7 +551,7 @@ __global__ void __launch_bounds__(QWARPS * 32) k_knn(ForestView F, const double*
                 TreeNormal Nn;
                 Nn.x = n0; Nn.y = n1; Nn.z = n2; Nn.pad = 0.0;
                 nrm_sorted[ps] = Nn;
-                i64 po = T.pt_off + F.pts[ps].idx;
+                i64 po = T.out_off + T.pts[ps].idx;
                 if (nrm_orig) { nrm_orig[3 * po + 0] = n0; nrm_orig[3 * po + 1] = n1; nrm_orig[3 * po + 2] = n2; }
                 if (evals_orig) { evals_orig[3 * po + 0] = e0; evals_orig[3 * po + 1] = e1; evals_orig[3 * po + 2] = e2; }
             }
@@ -551,12 +583,12 @@ __global__ void __launch_bounds__(256) k_grid_build(ForestView F, const i64* __r
     const TreeDesc& T = F.trees[t];
     const int pos = (int)(it - tio[t]) * 32 + lane;
     if (pos >= T.n) return;
-    TreePoint P = load_point(F.pts + T.pt_off + pos);
+    TreePoint P = load_point(T.pts + T.pt_off + pos);
     int ix, iy, iz;
     if (!grid_cell(T, P.x, P.y, P.z, ix, iy, iz)) return;  // NaN coordinates: not a seed
     const unsigned long long key = grid_key(ix, iy, iz);
     const unsigned mask = (unsigned)(((i64)1 << (64 - T.tab_shift)) - 1);
-    GridSlot* tab = grid + T.tab_off;
+    GridSlot* tab = T.grid + T.tab_off;
     unsigned slot = grid_hash(key, T.tab_shift);
     while (true) {
         unsigned long long prev = atomicCAS(&tab[slot].key, SB_GRID_EMPTY, key);
@@ -568,10 +600,19 @@ __global__ void __launch_bounds__(256) k_grid_build(ForestView F, const i64* __r
     }
 }
 
-static ForestView view_of(const Forest* f) {
+static ForestView view_of(const Forest* f, int t0 = 0) {
     ForestView v;
-    v.pts = f->pts; v.boxes = f->boxes; v.trees = f->d_trees;
+    v.trees = f->d_trees + t0;
     return v;
+}
+
+// pointers to the arrays forest_normals allocates, into the descriptors of one batch of trees
+__global__ void k_tree_attach(TreeDesc* __restrict__ trees, int n_trees, TreeNormal* nrm, NbrEntry* nbr, GridSlot* grid) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_trees) return;
+    trees[t].nrm = nrm;
+    trees[t].nbr = nbr;
+    trees[t].grid = grid;
 }
 
 static int query_grid(Ctx* ctx, i64 n_items) {
@@ -596,42 +637,58 @@ int forest_knn(Ctx* ctx, const Forest* f, const double* d_q, const QueryItem* d_
     return SB_OK;
 }
 
-int forest_normals(Ctx* ctx, Forest* f, int k, double* d_out_normals, double* d_out_evals) {
-    const size_t npa = (size_t)(f->n_points > 0 ? f->n_points : 1);
+int forest_normals(Ctx* ctx, Forest* f, int k, double* d_out_normals, double* d_out_evals, int batch) {
+    if (f->batches.empty()) return SB_OK;
+    if (batch < 0) batch = (int)f->batches.size() - 1;
+    if (batch >= (int)f->batches.size()) return fail(ctx, SB_ERR_INVALID_ARG, "normals: no such batch of trees");
+    ForestBatch& B = f->batches[(size_t)batch];
+    if (f->batches.size() > 1 && f->normals_k != 0 && f->normals_k != k)
+        return fail(ctx, SB_ERR_INVALID_ARG, "normals: every batch of a forest must use the same k");
+    const size_t npa = (size_t)(B.n_points > 0 ? B.n_points : 1);
+    const size_t nsa = (size_t)(B.n_slots > 0 ? B.n_slots : 1);
     if (f->in_arena) {
-        SB_TRY(arena_get(ctx, npa, &f->normals));
-        SB_TRY(arena_get(ctx, npa * (size_t)k, &f->nbr));
-        SB_TRY(arena_get(ctx, (size_t)(f->n_slots > 0 ? f->n_slots : 1), &f->grid));
+        SB_TRY(arena_get(ctx, npa, &B.normals));
+        SB_TRY(arena_get(ctx, npa * (size_t)k, &B.nbr));
+        SB_TRY(arena_get(ctx, nsa, &B.grid));
     } else {
-        if (!f->grid) SB_CUDA(ctx, cudaMalloc(&f->grid, sizeof(GridSlot) * (size_t)(f->n_slots > 0 ? f->n_slots : 1)));
-        if (!f->normals) SB_CUDA(ctx, cudaMalloc(&f->normals, sizeof(TreeNormal) * npa));
-        if (f->nbr && f->normals_k != k) {
+        if (!B.grid) SB_CUDA(ctx, cudaMalloc(&B.grid, sizeof(GridSlot) * nsa));
+        if (!B.normals) SB_CUDA(ctx, cudaMalloc(&B.normals, sizeof(TreeNormal) * npa));
+        if (B.nbr && f->normals_k != k) {
             SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            cudaFree(f->nbr);
-            f->nbr = nullptr;
+            cudaFree(B.nbr);
+            B.nbr = nullptr;
         }
-        if (!f->nbr) SB_CUDA(ctx, cudaMalloc(&f->nbr, sizeof(NbrEntry) * npa * (size_t)k));
+        if (!B.nbr) SB_CUDA(ctx, cudaMalloc(&B.nbr, sizeof(NbrEntry) * npa * (size_t)k));
     }
     f->normals_k = k;
+    TreeDesc* d_bt = f->d_trees + B.t0;
+    for (int t = 0; t < B.n_trees; ++t) {
+        TreeDesc& T = f->h_trees[(size_t)(B.t0 + t)];
+        T.nrm = B.normals; T.nbr = B.nbr; T.grid = B.grid;
+    }
+    if (B.n_trees > 0)
+        SB_LAUNCH(ctx, k_tree_attach, ceil_div(B.n_trees, 128), 128, 0, d_bt, B.n_trees, B.normals, B.nbr, B.grid);
     // implicit work items: chunk c of tree t is item tree_item_off[t] + c (no per-item table to build or upload)
-    std::vector<i64> tio((size_t)f->n_trees + 1, 0);
-    for (int t = 0; t < f->n_trees; ++t) tio[t + 1] = tio[t] + (f->h_trees[t].n + 31) / 32;
-    i64 n_items = tio[f->n_trees];
+    std::vector<i64> tio((size_t)B.n_trees + 1, 0);
+    for (int t = 0; t < B.n_trees; ++t) tio[t + 1] = tio[t] + (f->h_trees[(size_t)(B.t0 + t)].n + 31) / 32;
+    i64 n_items = tio[B.n_trees];
     if (n_items == 0) return SB_OK;
+    const ArenaMark mark = arena_mark(ctx);
     i64* d_tio;
     unsigned long long* d_spacing;
     SB_TRY(arena_get(ctx, tio.size(), &d_tio));
-    SB_TRY(arena_get(ctx, (size_t)f->n_trees, &d_spacing));
+    SB_TRY(arena_get(ctx, (size_t)B.n_trees, &d_spacing));
     SB_CUDA(ctx, cudaMemcpyAsync(d_tio, tio.data(), sizeof(i64) * tio.size(), cudaMemcpyHostToDevice, ctx->stream));
-    SB_CUDA(ctx, cudaMemsetAsync(d_spacing, 0, sizeof(unsigned long long) * (size_t)f->n_trees, ctx->stream));
-    SB_CUDA(ctx, cudaMemsetAsync(f->grid, 0xff, sizeof(GridSlot) * (size_t)f->n_slots, ctx->stream));
-    SB_LAUNCH(ctx, k_knn<1>, query_grid(ctx, n_items), QWARPS * 32, 0, view_of(f), nullptr,
-              reinterpret_cast<const QueryItem*>(d_tio), n_items, k, nullptr, nullptr, f->normals, f->nbr, d_out_normals,
-              d_out_evals, f->n_trees, d_spacing);
+    SB_CUDA(ctx, cudaMemsetAsync(d_spacing, 0, sizeof(unsigned long long) * (size_t)B.n_trees, ctx->stream));
+    SB_CUDA(ctx, cudaMemsetAsync(B.grid, 0xff, sizeof(GridSlot) * (size_t)B.n_slots, ctx->stream));
+    SB_LAUNCH(ctx, k_knn<1>, query_grid(ctx, n_items), QWARPS * 32, 0, view_of(f, B.t0), nullptr,
+              reinterpret_cast<const QueryItem*>(d_tio), n_items, k, nullptr, nullptr, B.normals, B.nbr, d_out_normals,
+              d_out_evals, B.n_trees, d_spacing);
     // seed grid for icp.cu (cell size from the measured point spacing)
-    SB_LAUNCH(ctx, k_grid_params, ceil_div(f->n_trees, 128), 128, 0, f->d_trees, d_spacing, f->n_trees);
-    SB_LAUNCH(ctx, k_grid_build, (unsigned)((n_items * 32 + 255) / 256), 256, 0, view_of(f), d_tio, n_items, f->n_trees,
-              f->grid);
+    SB_LAUNCH(ctx, k_grid_params, ceil_div(B.n_trees, 128), 128, 0, d_bt, d_spacing, B.n_trees);
+    SB_LAUNCH(ctx, k_grid_build, (unsigned)((n_items * 32 + 255) / 256), 256, 0, view_of(f, B.t0), d_tio, n_items,
+              B.n_trees, B.grid);
+    arena_release(ctx, mark);
     return SB_OK;
 }
 

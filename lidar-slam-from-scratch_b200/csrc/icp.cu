@@ -38,9 +38,6 @@ struct FallbackEntry {   // a source point whose walk did not end with a proof
 
 struct IcpJob {
     ForestView F;
-    const TreeNormal* normals;  // per sorted target point
-    const NbrEntry* nbr;        // nbr_k entries per sorted target point (forest_normals)
-    const GridSlot* grid;       // seed grid (forest_normals)
     const double* src;          // source rows, fp64 xyz
     int* match;                 // n_items x ITEM_Q: correspondence of every source point (seed of the next pass)
     i64 n_items;
@@ -195,11 +192,10 @@ __device__ __forceinline__ int grid_find(const GridSlot* __restrict__ tab, unsig
 
 // A target point near the query: the representative of the query's grid cell, else the nearest representative of
 // the 26 surrounding cells (fp32: a starting point, never an answer).  -1 if all 27 cells are empty.
-__device__ __forceinline__ int grid_seed(const ForestView& F, const GridSlot* __restrict__ grid, const TreeDesc& T,
-                                         double qx, double qy, double qz) {
+__device__ __forceinline__ int grid_seed(const TreeDesc& T, double qx, double qy, double qz) {
     int ix, iy, iz;
     if (!grid_cell(T, qx, qy, qz, ix, iy, iz)) return -1;
-    const GridSlot* tab = grid + T.tab_off;
+    const GridSlot* tab = T.grid + T.tab_off;
     const unsigned mask = (unsigned)(((i64)1 << (64 - T.tab_shift)) - 1);
     int pos = grid_find(tab, mask, T.tab_shift, ix, iy, iz);
     if (pos >= 0) return pos;
@@ -209,7 +205,7 @@ __device__ __forceinline__ int grid_seed(const ForestView& F, const GridSlot* __
         if (c == 13) continue;
         int p = grid_find(tab, mask, T.tab_shift, ix + c % 3 - 1, iy + (c / 3) % 3 - 1, iz + c / 9 - 1);
         if (p < 0) continue;
-        const double* P = reinterpret_cast<const double*>(F.pts + T.pt_off + p);
+        const double* P = reinterpret_cast<const double*>(T.pts + T.pt_off + p);
         const double2 xy = __ldg(reinterpret_cast<const double2*>(P));
         const double z = __ldg(P + 2);
         float dx = (float)xy.x - fx, dy = (float)xy.y - fy, dz = (float)z - fz;
@@ -219,8 +215,8 @@ __device__ __forceinline__ int grid_seed(const ForestView& F, const GridSlot* __
     return pos;
 }
 
-__device__ __forceinline__ void accumulate_item(const IcpJob* __restrict__ job, const ForestView& F, i64 it, i64 pt_off,
-                                                int lane, int my_pos, double cx, double cy, double cz);
+__device__ __forceinline__ void accumulate_item(const IcpJob* __restrict__ job, const TreeDesc& T, i64 it, int lane,
+                                                int my_pos, double cx, double cy, double cz);
 
 // Works on the pairs listed in job->act_pair: the ST_ACTIVE ones inside the loop, the ST_EXHAUSTED ones in the final
 // error pass (icp.hpp:235-252).  Work item = ITEM_Q consecutive source points of one pair (implicit: binary search
@@ -254,10 +250,10 @@ __global__ void __launch_bounds__(IWARPS * 32) k_icp_match(IcpJob* __restrict__ 
         if (lane < count) {
             transform_point(Tm, job->src + 3 * (P.src_off + s0 + lane), cx, cy, cz);
             int center = job->match[it * ITEM_Q + lane];  // -1 before the first pass
-            if (center < 0 || center >= T.n) center = grid_seed(F, job->grid, T, cx, cy, cz);
+            if (center < 0 || center >= T.n) center = grid_seed(T, cx, cy, cz);
             if (center >= 0) {
-                const TreePoint* TP = F.pts + T.pt_off;
-                const NbrEntry* TN = job->nbr + T.pt_off * (i64)K;
+                const TreePoint* TP = T.pts + T.pt_off;
+                const NbrEntry* TN = T.nbr + T.pt_off * (i64)K;
                 TreePoint c = load_point(TP + center);
                 double bd = dist2_rn(c.x, c.y, c.z, cx, cy, cz);
                 int bidx = c.idx;
@@ -305,7 +301,7 @@ __global__ void __launch_bounds__(IWARPS * 32) k_icp_match(IcpJob* __restrict__ 
             }
         }
         // every point of the item has its proven correspondence: finish the item here (k_icp_accum skips it)
-        if (!todo) accumulate_item(job, F, it, T.pt_off, lane, lane < count ? bpos : -1, cx, cy, cz);
+        if (!todo) accumulate_item(job, T, it, lane, lane < count ? bpos : -1, cx, cy, cz);
         if (lane == 0) job->item_done[it] = todo ? 0 : 1;
         if (job->stats && lane == 0) {  // SB_ICP_STATS: buckets by iteration: 0, 1, 2..11, >= 12
             int bkt = job->state[pair].iter;
@@ -351,13 +347,13 @@ __global__ void __launch_bounds__(IWARPS * 32) k_icp_fallback(IcpJob* __restrict
 // Residual and the 28 sums of one work item (32 source points, one per lane; my_pos < 0: no correspondence, the lane
 // adds zeros): fixed-order butterfly, one 224-byte partial per item.  (cx, cy, cz) = the lane's transformed source
 // point.
-__device__ __forceinline__ void accumulate_item(const IcpJob* __restrict__ job, const ForestView& F, i64 it, i64 pt_off,
-                                                int lane, int my_pos, double cx, double cy, double cz) {
+__device__ __forceinline__ void accumulate_item(const IcpJob* __restrict__ job, const TreeDesc& T, i64 it, int lane,
+                                                int my_pos, double cx, double cy, double cz) {
     double tx = 0, ty = 0, tz = 0, nx = 0, ny = 0, nz = 0;
     if (my_pos >= 0) {
-        TreePoint q = load_point(F.pts + pt_off + my_pos);
+        TreePoint q = load_point(T.pts + T.pt_off + my_pos);
         tx = q.x; ty = q.y; tz = q.z;
-        const double2* np = reinterpret_cast<const double2*>(job->normals + pt_off + my_pos);
+        const double2* np = reinterpret_cast<const double2*>(T.nrm + T.pt_off + my_pos);
         double2 n01 = __ldg(np), n2 = __ldg(np + 1);
         nx = n01.x; ny = n01.y; nz = n2.x;
     } else {
@@ -413,7 +409,7 @@ __global__ void __launch_bounds__(IWARPS * 32) k_icp_accum(const IcpJob* __restr
         if (job->item_done[it]) continue;  // k_icp_match wrote this item's partial already
         const int s0 = (int)(it - P.item_off) * ITEM_Q;
         const int count = P.n_src - s0 < ITEM_Q ? P.n_src - s0 : ITEM_Q;
-        const i64 pt_off = F.trees[P.tree].pt_off;
+        const TreeDesc& T = F.trees[P.tree];
         double cx = 0, cy = 0, cz = 0;
         int my_pos = -1;
         if (lane < count) {
@@ -421,7 +417,7 @@ __global__ void __launch_bounds__(IWARPS * 32) k_icp_accum(const IcpJob* __restr
             if (my_pos >= 0)
                 transform_point(job->results[pair].transformation, job->src + 3 * (P.src_off + s0 + lane), cx, cy, cz);
         }
-        accumulate_item(job, F, it, pt_off, lane, my_pos, cx, cy, cz);
+        accumulate_item(job, T, it, lane, my_pos, cx, cy, cz);
     }
 }
 
@@ -817,7 +813,10 @@ int icp_batch(Ctx* ctx, const Forest* f, const double* d_src, const std::vector<
     if (cfg->max_iterations < 0 || cfg->max_iterations > SB_MAX_ICP_ITERATIONS)
         return fail(ctx, SB_ERR_INVALID_ARG, "icp: max_iterations %d outside [0, %d]", cfg->max_iterations,
                     SB_MAX_ICP_ITERATIONS);
-    if (!f->normals || !f->nbr || !f->grid) return fail(ctx, SB_ERR_INVALID_ARG, "icp: forest has no normals");
+    if (f->normals_k <= 0) return fail(ctx, SB_ERR_INVALID_ARG, "icp: forest has no normals");
+    for (const ForestBatch& B : f->batches)
+        if (B.n_points > 0 && (!B.normals || !B.nbr || !B.grid))
+            return fail(ctx, SB_ERR_INVALID_ARG, "icp: a batch of the forest has no normals");
     IcpGraph* G;
     SB_TRY(icp_graph_get(ctx, &G));
     std::vector<PairDesc> pairs(pairs_in);
@@ -854,11 +853,7 @@ int icp_batch(Ctx* ctx, const Forest* f, const double* d_src, const std::vector<
     SB_CUDA(ctx, cudaMemsetAsync(d_match, 0xff, sizeof(int) * ni * ITEM_Q, ctx->stream));  // -1: no correspondence yet
     IcpJob job;
     memset(&job, 0, sizeof(job));
-    job.F.pts = f->pts; job.F.boxes = f->boxes;
     job.F.trees = f->d_trees;
-    job.normals = f->normals;
-    job.nbr = f->nbr;
-    job.grid = f->grid;
     job.nbr_k = f->normals_k;
     job.stats = G->d_stats;
     job.src = d_src;

@@ -25,8 +25,6 @@ struct WarpStack {                       // shared memory, one per warp
 };
 
 struct ForestView {
-    const TreePoint* __restrict__ pts;
-    const float* __restrict__ boxes;
     const TreeDesc* __restrict__ trees;
 };
 
@@ -96,7 +94,7 @@ __device__ __forceinline__ void test_children(const ForestView& F, const TreeDes
     bool valid = ci < T.box_cnt[level];
     float dmf = __int_as_float(0x7f800000);
     if (valid) {
-        const float2* b = reinterpret_cast<const float2*>(F.boxes + 6 * (T.box_off[level] + ci));
+        const float2* b = reinterpret_cast<const float2*>(T.boxes + 6 * (T.box_off[level] + ci));
         dmf = Q.lb(b[0], b[1], b[2]);
     }
     bool pass = valid && !((double)dmf > tau);
@@ -169,7 +167,7 @@ struct NearestVisitor {
     // distance from above, so the traversal only has to visit boxes inside that ball.  Exactness is unaffected.
     __device__ __forceinline__ void seed(int pos) {
         if (pos < 0 || pos >= T.n) return;
-        TreePoint P = load_point(F.pts + T.pt_off + pos);
+        TreePoint P = load_point(T.pts + T.pt_off + pos);
         double d = dist2_rn(P.x, P.y, P.z, qx, qy, qz);
         int idx = P.idx;
         if (d < best_d || (d == best_d && idx < best_idx)) {
@@ -183,7 +181,7 @@ struct NearestVisitor {
         unsigned hi = 0xffffffffu, lo = 0xffffffffu;
         int idx = 0x7fffffff;
         if (valid) {
-            TreePoint P = load_point(F.pts + T.pt_off + p0 + lane);
+            TreePoint P = load_point(T.pts + T.pt_off + p0 + lane);
             double d = dist2_rn(P.x, P.y, P.z, qx, qy, qz);
             idx = P.idx;
             if (d == d) {  // NaN never wins (kdtree.hpp:125 strict <)
@@ -231,7 +229,7 @@ struct KnnVisitor {
     __device__ __forceinline__ void seed(int pos, WarpStack& S) {
         ld = (double)INFINITY; lidx = 0x7fffffff; lpos = -1;
         if (pos >= 0 && pos < T.n) {
-            TreePoint P = load_point(F.pts + T.pt_off + pos);
+            TreePoint P = load_point(T.pts + T.pt_off + pos);
             double d = dist2_rn(P.x, P.y, P.z, qx, qy, qz);
             if (d == d) { ld = d; lidx = P.idx; lpos = pos; }
         }
@@ -254,7 +252,7 @@ struct KnnVisitor {
         double cd = 0.0;
         int cidx = 0x7fffffff;
         if (valid) {
-            TreePoint P = load_point(F.pts + T.pt_off + p0 + lane);
+            TreePoint P = load_point(T.pts + T.pt_off + p0 + lane);
             cd = dist2_rn(P.x, P.y, P.z, qx, qy, qz);
             cidx = P.idx;
         }
