@@ -483,7 +483,7 @@ __global__ void __launch_bounds__(QWARPS * 32) k_knn(ForestView F, const double*
         for (int j = 0; j < I.count; ++j) {
             double qx = shfl_d(mx, j), qy = shfl_d(my, j), qz = shfl_d(mz, j);
             KnnVisitor V(F, T, qx, qy, qz, lane, k);
-            if (MODE == 1 || j > 0) V.seed(prev_pos, S);
+            if (MODE == 1 || j > 0) V.seed(prev_pos);
             traverse(F, T, qx, qy, qz, S, V, lane);
             prev_pos = V.lpos;
             bool have = lane < k && V.lidx != 0x7fffffff;

@@ -19,9 +19,6 @@ struct WarpStack {                       // shared memory, one per warp
     float dm[SB_MAX_LEVELS][32];         // lower-bound d^2 of "my" child at each level
     unsigned mask[SB_MAX_LEVELS];        // children still to visit at each level (warp-uniform)
     int base[SB_MAX_LEVELS];             // first child index at each level (warp-uniform)
-    double sd[32];                       // scratch of KnnVisitor::seed: the seeds in rank order
-    int si[32];
-    int sp[32];
 };
 
 struct ForestView {
@@ -223,27 +220,45 @@ struct KnnVisitor {
           lidx(0x7fffffff), lpos(-1), tau_d((double)INFINITY), tau_idx(0x7fffffff) {}
     __device__ __forceinline__ double tau() const { return tau_d; }
     // Seeds the list with up to 32 DISTINCT tree points (this lane's `pos`, cloud-local sorted position, or -1):
-    // distances to the new query are evaluated and the 32 entries are put in (d2, idx) order across the warp — every
-    // lane counts the entries that precede its own (32 broadcasts) and drops its entry at that rank through shared
-    // memory.  Any k distinct real points bound the k-th nearest distance from above, so the result stays exact.
-    __device__ __forceinline__ void seed(int pos, WarpStack& S) {
+    // distances to the new query are evaluated and the 32 entries are put in (d2, idx) order across the warp.  The
+    // seeds arrive in the order of the previous query's list, which is almost the order for this query (consecutive
+    // queries are neighbours on the Morton curve), so an odd-even transposition sort that stops as soon as a whole
+    // pass swaps nothing takes a few passes instead of the 15 stages of a full sorting network.  Any k distinct real
+    // points bound the k-th nearest distance from above, so the result stays exact.
+    __device__ __forceinline__ void seed(int pos) {
         ld = (double)INFINITY; lidx = 0x7fffffff; lpos = -1;
         if (pos >= 0 && pos < T.n) {
             TreePoint P = load_point(T.pts + T.pt_off + pos);
             double d = dist2_rn(P.x, P.y, P.z, qx, qy, qz);
             if (d == d) { ld = d; lidx = P.idx; lpos = pos; }
         }
-        int rank = 0;
-#pragma unroll 8
-        for (int j = 0; j < 32; ++j) {
-            const double od = shfl_d(ld, j);
-            const int oi = __shfl_sync(0xffffffffu, lidx, j);
-            rank += (od < ld || (od == ld && (oi < lidx || (oi == lidx && j < lane)))) ? 1 : 0;
+        // comb passes at shrinking strides move far-displaced entries cheaply before the stride-1 passes
+#pragma unroll
+        for (int stride = 16; stride >= 2; stride >>= 1) {
+            const int partner = lane ^ stride;
+            const double od = shfl_d(ld, partner);
+            const int oi = __shfl_sync(0xffffffffu, lidx, partner);
+            const int op = __shfl_sync(0xffffffffu, lpos, partner);
+            const bool other_less = lex_less(od, oi, ld, lidx);
+            const bool take = lane < partner ? other_less : (!other_less && !(od == ld && oi == lidx));
+            if (take) { ld = od; lidx = oi; lpos = op; }
         }
-        __syncwarp();
-        S.sd[rank] = ld; S.si[rank] = lidx; S.sp[rank] = lpos;
-        __syncwarp();
-        ld = S.sd[lane]; lidx = S.si[lane]; lpos = S.sp[lane];
+        bool swapped;
+        do {
+            swapped = false;
+#pragma unroll
+            for (int phase = 0; phase < 2; ++phase) {
+                const int partner = phase == 0 ? (lane ^ 1) : ((lane & 1) ? lane + 1 : lane - 1);
+                const bool valid = partner >= 0 && partner < 32;
+                const int src = valid ? partner : lane;
+                const double od = shfl_d(ld, src);
+                const int oi = __shfl_sync(0xffffffffu, lidx, src);
+                const int op = __shfl_sync(0xffffffffu, lpos, src);
+                const bool other_less = lex_less(od, oi, ld, lidx);
+                const bool take = valid && (lane < partner ? other_less : (!other_less && !(od == ld && oi == lidx)));
+                if (take) { ld = od; lidx = oi; lpos = op; swapped = true; }
+            }
+        } while (__any_sync(0xffffffffu, swapped));
         tau_d = shfl_d(ld, k - 1);
         tau_idx = __shfl_sync(0xffffffffu, lidx, k - 1);
     }
