@@ -9,6 +9,8 @@
 // integers) -> 30-bit Morton codes -> segmented radix sort -> gather into SoA + leaf boxes -> upper box levels.
 #include "traverse.cuh"
 
+#include <cstdlib>
+
 namespace sb {
 
 static constexpr int CHUNK = 1024;  // points per build work item (32 leaves)
@@ -617,7 +619,8 @@ __global__ void k_tree_attach(TreeDesc* __restrict__ trees, int n_trees, TreeNor
 
 static int query_grid(Ctx* ctx, i64 n_items) {
     i64 blocks = (n_items + QWARPS - 1) / QWARPS;
-    i64 cap = (i64)ctx->sm_count * 8;  // persistent: 8 resident 256-thread CTAs per SM
+    static const int per_sm = getenv("SB_KNN_GRID") ? atoi(getenv("SB_KNN_GRID")) : 32;
+    i64 cap = (i64)ctx->sm_count * per_sm;  // persistent grid: more CTAs than fit at once evens out uneven items
     return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
 }
 

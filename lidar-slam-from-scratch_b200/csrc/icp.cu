@@ -66,6 +66,7 @@ struct IcpJob {
 static constexpr int IWARPS = 8;
 static constexpr int NSUM = 28;
 static constexpr int ITEM_Q = 32;   // source points per warp work item: one per lane
+static constexpr int WALK_GROUP = 1;  // neighbour-list entries whose candidate points are fetched together
 static constexpr int MAX_HOPS = 6;  // re-centrings of the neighbour-graph walk before the tree takes over
 
 // -------------------------------------------------------------------------------------------------------------
@@ -264,16 +265,28 @@ __global__ void __launch_bounds__(IWARPS * 32) k_icp_match(IcpJob* __restrict__ 
                         float sb = dc;
                         const int2* L = reinterpret_cast<const int2*>(TN + (i64)center * K);
                         float rlast = 0.f;
-                        for (int j = 0; j < K; ++j) {
-                            const int2 e = __ldg(L + j);
-                            rlast = __int_as_float(e.y);
-                            if (e.x < 0 || __fsub_rd(rlast, dc) > sb) { cert = true; break; }
-                            if (e.x == center) continue;
-                            TreePoint t = load_point(TP + e.x);
-                            double d = dist2_rn(t.x, t.y, t.z, cx, cy, cz);
-                            if (d < bd || (d == bd && t.idx < bidx)) {
-                                bd = d; bidx = t.idx; bpos = e.x;
-                                sb = sqrt_up(bd);
+                        // entries WALK_GROUP at a time: their candidate points are fetched together (speculatively — the
+                        // proof may arrive before all of them are needed) so that the walk waits for one memory round
+                        // trip per group instead of one per candidate; evaluation order is unchanged
+                        for (int j0 = 0; j0 < K && !cert; j0 += WALK_GROUP) {
+                            int2 e[WALK_GROUP];
+                            TreePoint t[WALK_GROUP];
+#pragma unroll
+                            for (int u = 0; u < WALK_GROUP; ++u) {
+                                e[u] = j0 + u < K ? __ldg(L + j0 + u) : make_int2(-1, 0x7f800000);
+                                if (e[u].x >= 0 && e[u].x != center) t[u] = load_point(TP + e[u].x);
+                            }
+#pragma unroll
+                            for (int u = 0; u < WALK_GROUP; ++u) {
+                                if (cert || j0 + u >= K) break;
+                                rlast = __int_as_float(e[u].y);
+                                if (e[u].x < 0 || __fsub_rd(rlast, dc) > sb) { cert = true; break; }
+                                if (e[u].x == center) continue;
+                                double d = dist2_rn(t[u].x, t[u].y, t[u].z, cx, cy, cz);
+                                if (d < bd || (d == bd && t[u].idx < bidx)) {
+                                    bd = d; bidx = t[u].idx; bpos = e[u].x;
+                                    sb = sqrt_up(bd);
+                                }
                             }
                         }
                         if (!cert && __fsub_rd(rlast, dc) > sb) cert = true;  // list exhausted: the rest is >= r_{K-1}
@@ -776,7 +789,7 @@ static int icp_graph_get(Ctx* ctx, IcpGraph** out) {
     ctx->icp_graph = G;
     *out = G;
     SB_CUDA(ctx, cudaMalloc(&G->d_job, sizeof(IcpJob)));
-    G->iter_grid = ctx->sm_count * 8;
+    G->iter_grid = ctx->sm_count * (getenv("SB_ICP_GRID") ? atoi(getenv("SB_ICP_GRID")) : 32);
     G->solve_grid = ctx->sm_count * 4;
     if (getenv("SB_ICP_STATS")) {
         SB_CUDA(ctx, cudaMalloc(&G->d_stats, 8 * sizeof(unsigned long long)));

@@ -19,6 +19,8 @@
 // if there are too many of them, or keys do not fit 21 bits per axis, the call falls back to the sort.
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace sb {
 
 struct VoxelPack {
@@ -574,7 +576,8 @@ static int voxel_hashed_dev(Ctx* ctx, const PointSrc src, const i64* h_off, int 
     SB_CUDA(ctx, cudaMemsetAsync(ctx->d_flags, 0, sizeof(int), ctx->stream));
     i64 init[6] = {INT64_MAX, INT64_MAX, INT64_MAX, INT64_MIN, INT64_MIN, INT64_MIN};
     SB_CUDA(ctx, cudaMemcpyAsync(d_mm, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
-    const int pgrid = (int)(n_tiles < (i64)ctx->sm_count * 8 ? n_tiles : (i64)ctx->sm_count * 8);
+    static const int per_sm = getenv("SB_VOX_GRID") ? atoi(getenv("SB_VOX_GRID")) : 64;
+    const int pgrid = (int)(n_tiles < (i64)ctx->sm_count * per_sm ? n_tiles : (i64)ctx->sm_count * per_sm);
     SB_LAUNCH(ctx, k_vox_insert, pgrid, 256, 0, src, d_clouds, d_tile_cloud, n_tiles, voxel, d_table, d_slot_of, d_nvox,
               d_mm, ctx->d_flags);
     // ---- the only host round trip: flags, key range, voxels per cloud
