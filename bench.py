@@ -301,15 +301,24 @@ def main():
         N, M, T, Q = counts["raw_rows"], counts["voxel_rows"], counts["target_rows"], counts["nn_queries"]
         alg = {"voxel": 24 * N + 24 * M, "scan_context": 24 * M + 9600 * (F + 1), "index_build": 52 * T,
                "normals": 48 * T, "icp_loop": 72 * Q + 224 * F * max(counts["icp_iter_launches"], 1)}
-        kern = {"voxel": "k_sort_scatter/k_sort_hist/k_voxel_* (voxel grid)", "scan_context": "k_sc_compute",
+        kern = {"voxel": "k_vox_insert (+ clear/list/sort/finalize/collect/patch)", "scan_context": "k_sc_compute",
                 "index_build": "k_morton/k_sort_*/k_gather_leaves", "normals": "k_knn<1> (kNN + covariance + Jacobi)",
-                "icp_loop": "k_icp_iter (1-NN + 28 sums) inside the WHILE graph"}
+                "icp_loop": "k_icp_match/k_icp_fallback/k_icp_accum/k_icp_solve inside the WHILE graph"}
+        traffic = {}
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        except Exception:
+            pass
         dom = max(alg, key=lambda k: st.get(k, 0.0))
         dom_ms = st[dom]
-        launches_dom = counts["icp_iter_launches"] if dom == "icp_loop" else 1
+        launches_dom = 4 * counts["icp_iter_launches"] + 1 if dom == "icp_loop" else 1
         achieved = alg[dom] / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
         roofline = {"bound": "hbm", "kernel": kern[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "frac": achieved / peak,
+                    # DRAM bytes of one launch of that kernel from the committed ncu capture (same command, 1000 frames)
+                    "traffic": (traffic.get(dom, {}).get("dram_bytes_per_launch") if F == 1000 else None),
+                    "traffic_source": "profiles/r01_traffic.json (ncu --set full)" if dom in traffic and F == 1000 else None,
+                    "peak_source": peak_src,
                     "algorithmic_bytes_per_step": int(alg[dom]), "launches_per_step": int(launches_dom),
                     "avg_launch_ms": dom_ms / max(launches_dom, 1),
                     "stages_ms": st, "stages_host_ms": {k: v / args.steps for k, v in host_acc.items()},

@@ -598,8 +598,9 @@ static int voxel_hashed_dev(Ctx* ctx, const PointSrc src, const i64* h_off, int 
     for (int c = 0; c < n_clouds; ++c) h_out_off[c + 1] = h_out_off[c] + nvox[c];
     const i64 m = h_out_off[n_clouds];
     {  // size the next call's tables for 2 slots per voxel (before rounding up to a power of two) at this density
-        double r = 2.0 * (double)m / (double)n;
-        ctx->vox_slots_per_point = r < 0.125 ? 0.125 : (r > 2.0 ? 2.0 : r);
+        static const double per_voxel = getenv("SB_VOX_SLOTS") ? atof(getenv("SB_VOX_SLOTS")) : 2.0;
+        double r = per_voxel * (double)m / (double)n;
+        ctx->vox_slots_per_point = r < 0.0625 ? 0.0625 : (r > 2.0 ? 2.0 : r);
     }
     int bx = bits_for((u64)(mm[3] - mm[0])), by = bits_for((u64)(mm[4] - mm[1])), bz = bits_for((u64)(mm[5] - mm[2]));
     VoxelPack P;
