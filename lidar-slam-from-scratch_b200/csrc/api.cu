@@ -160,7 +160,7 @@ static int upload_voxel_pipelined(Ctx* ctx, const void* h_raw, int f32, int stri
     // round trips than they gain in overlap (measured: 24 MB 93 ms, 96 MB 64 ms, 192 MB 63 ms, 384 MB 66 ms per C2 step)
     std::vector<int> cb(1, 0);
     {
-        static const long chunk_mb = getenv("SB_CHUNK_MB") ? atol(getenv("SB_CHUNK_MB")) : 192;
+        const long chunk_mb = getenv("SB_CHUNK_MB") ? atol(getenv("SB_CHUNK_MB")) : 192;
         const i64 target_rows = (i64)(((size_t)(chunk_mb > 0 ? chunk_mb : 192) << 20) / row_bytes);
         i64 start = 0;
         for (int c = 0; c < n_clouds; ++c)

@@ -327,6 +327,31 @@ def test_register_batch_equals_single_pairs(engine, oracle, synth, scene):
         assert np.array_equal(sc[c], oracle.sc_compute(ds[c]))
 
 
+def test_chunked_upload_and_batch_composition_independence(engine, synth, scene, monkeypatch):
+    """The host entry points upload, voxelise, index and compute normals chunk by chunk (SB_CHUNK_MB); the result does
+    not depend on the chunking, nor on which other pairs share the batch (fixed summation order per pair)."""
+    s = oracle_lib.small_sensor(32, 600)
+    raws = [synth.scan(s, scene, (1.0 * i, 0.1 * (i % 3), 0.01 * i), 70 + i) for i in range(9)]
+    off = np.r_[0, np.cumsum([len(r) for r in raws])]
+    allpts = np.vstack(raws)
+    src = [1, 2, 3, 4, 5, 6, 7, 8, 0, 4]
+    tgt = [0, 1, 2, 3, 4, 5, 6, 7, 8, 2]
+    ref, sc_ref = engine.register_batch(allpts, off, src, tgt, voxel=0.5, want_sc=True)
+    monkeypatch.setenv("SB_CHUNK_MB", "1")  # ~2 clouds per chunk: 5 chunks, 5 batches of trees
+    for pts in (allpts, allpts.astype(np.float32)):
+        got, sc = engine.register_batch(pts, off, src, tgt, voxel=0.5, want_sc=True)
+        assert np.array_equal(got.transformations, ref.transformations)
+        assert np.array_equal(got.num_iterations, ref.num_iterations) and np.array_equal(sc, sc_ref)
+        assert np.array_equal(got.final_errors, ref.final_errors)
+    monkeypatch.delenv("SB_CHUNK_MB")
+    for p in (0, 4, 9):  # each pair alone gives the bits it gave inside the batch
+        a, b = src[p], tgt[p]
+        pts = np.vstack([raws[a], raws[b]])
+        one = engine.register_batch(pts, np.array([0, len(raws[a]), len(pts)]), [0], [1], voxel=0.5)
+        assert np.array_equal(one.transformations[0], ref.transformations[p])
+        assert one[0].num_iterations == ref[p].num_iterations
+
+
 def test_icp_is_deterministic(engine, small_pair):
     r1 = engine.icp_point_to_plane(small_pair["b"], small_pair["a"])
     r2 = engine.icp_point_to_plane(small_pair["b"], small_pair["a"])
@@ -367,6 +392,28 @@ def test_scan_context_random_db_topk(engine, oracle):
     assert np.max(np.abs(got - ref)) < 1e-5
     assert np.array_equal(np.lexsort((np.arange(300), got))[:10], np.lexsort((np.arange(300), ref))[:10])
     assert np.argmin(got) == 17
+
+
+def test_scan_context_4k_database_top10(engine):
+    """C4-sized search: one query against 4000 descriptors; distances vs a vectorised numpy restatement of
+    scan_context.hpp:121-142 and identical top-10 ids (ties broken by entry id like loop_closure.hpp:92)."""
+    rng = np.random.default_rng(11)
+    n = 4000
+    base = np.where(rng.uniform(size=(40, 60, 20)) < 0.35, rng.uniform(-1.7, 9.0, (40, 60, 20)), 0.0)
+    db = base[rng.integers(0, 40, n)] + np.where(rng.uniform(size=(n, 60, 20)) < 0.05, rng.normal(0, 0.5, (n, 60, 20)), 0.0)
+    db = np.stack([np.roll(d, int(sft), axis=0) for d, sft in zip(db, rng.integers(0, 60, n))])  # [sector][ring]
+    q = db[1234] + rng.normal(0, 0.02, (60, 20))
+    got = engine.sc_distance_batch(q.reshape(-1), db.reshape(n, -1))
+    ref = np.full(n, np.inf)
+    qa = np.sqrt((q * q).sum())
+    nb = np.sqrt((db * db).sum(axis=(1, 2)))
+    for sft in range(60):  # b(i, (j + shift) % 60): sector axis rolled by -shift
+        dots = np.einsum("sr,nsr->n", q, np.roll(db, -sft, axis=1))
+        norm = qa * nb
+        ref = np.minimum(ref, np.where(norm < 1e-10, 1.0, 1.0 - dots / np.where(norm < 1e-10, 1.0, norm)))
+    assert np.max(np.abs(got - ref)) < 1e-9
+    assert np.array_equal(np.lexsort((np.arange(n), got))[:10], np.lexsort((np.arange(n), ref))[:10])
+    assert np.argmin(got) == 1234
 
 
 # ------------------------------------------------------------------ loop closure
