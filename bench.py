@@ -268,6 +268,8 @@ def main():
                     gather(r2)
                 g1.record(stream)
                 barrier()
+                host_stages = eng.stage_host_ms()
+                dev_stages = eng.stage_ms()
                 wall = (time.perf_counter() - t0) / args.steps * 1e3
                 ms2 = max(g0.elapsed_time(g1) / args.steps, wall)  # host-side work (staging, result decode) counts
                 t2 = torch.tensor([ms2], device="cuda", dtype=torch.float64)
@@ -277,12 +279,16 @@ def main():
                 assert np.array_equal(sc, s2)
                 return {"value": world_size * F / (float(t2.item()) * 1e-3), "unit": "pairs/s",
                         "h2d_bytes_per_step": int(n_raw * bytes_per_row), "d2h_bytes_per_step": int(d2h),
-                        "ms_per_step": float(t2.item())}
+                        "ms_per_step": float(t2.item()),
+                        "host_ms_last_step": {k: round(v, 2) for k, v in host_stages.items()},
+                        "device_ms_last_step": {k: round(v, 2) for k, v in dev_stages.items()}}
 
+            eng.set_profiling(True)
             e2e = timed_host(h32.numpy().reshape(-1, 3), 12)
             e2e["input"] = "pinned host float32 xyz records (as read from disk), widened on the device"
             e2e_f64 = timed_host(h64.numpy().reshape(-1, 3), 24)
             e2e_f64["input"] = "pinned host fp64 rows (PointCloud::Matrix)"
+            eng.set_profiling(False)
 
         if rank != 0:
             if world_size > 1:

@@ -83,7 +83,7 @@ int arena_alloc(Ctx* ctx, size_t bytes, void** out) {
 }
 
 void stage_mark(Ctx* ctx, int stage) {
-    if (!ctx->profiling || ctx->n_ev >= 32) return;
+    if (!ctx->profiling || ctx->n_ev >= 128) return;
     while (ctx->ev_created <= ctx->n_ev) {
         if (cudaEventCreate(&ctx->ev[ctx->ev_created]) != cudaSuccess) return;
         ctx->ev_created++;
@@ -93,6 +93,37 @@ void stage_mark(Ctx* ctx, int stage) {
         std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
     ctx->ev_stage[ctx->n_ev] = stage;
     ctx->n_ev++;
+}
+
+__global__ void k_copy_words(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+int table_upload(Ctx* ctx, void* d_dst, const void* h_src, size_t bytes) {
+    if (bytes == 0) return SB_OK;
+    if (!ctx->tbuf) {
+        const size_t cap = (size_t)32 << 20;
+        if (cudaHostAlloc(&ctx->tbuf, cap, cudaHostAllocMapped) == cudaSuccess &&
+            cudaHostGetDevicePointer((void**)&ctx->tbuf_dev, ctx->tbuf, 0) == cudaSuccess) {
+            ctx->tbuf_cap = cap;
+        } else {
+            cudaGetLastError();
+            ctx->tbuf = nullptr;
+            ctx->tbuf_cap = 0;
+        }
+    }
+    const size_t need = (bytes + 15) & ~(size_t)15;
+    if ((bytes & 3) != 0 || ctx->tbuf_used + need > ctx->tbuf_cap) {  // odd size or buffer full: the copy engine
+        SB_CUDA(ctx, cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        return SB_OK;
+    }
+    memcpy(ctx->tbuf + ctx->tbuf_used, h_src, bytes);
+    const size_t words = bytes / 4;
+    const int grid = (int)((words + 255) / 256 < 64 ? (words + 255) / 256 : 64);
+    SB_LAUNCH(ctx, k_copy_words, grid, 256, 0, static_cast<uint32_t*>(d_dst),
+              reinterpret_cast<const uint32_t*>(ctx->tbuf_dev + ctx->tbuf_used), words);
+    ctx->tbuf_used += need;
+    return SB_OK;
 }
 
 int pinned_reserve(Ctx* ctx, size_t bytes) {
@@ -113,6 +144,7 @@ struct Enter {
     explicit Enter(Ctx* ctx) : c(ctx) {
         cudaSetDevice(c->device);
         arena_reset(c);
+        c->tbuf_used = 0;  // everything the previous call enqueued has completed
         c->err.clear();
         c->n_ev = 0;
     }
@@ -194,6 +226,7 @@ static int upload_voxel_pipelined(Ctx* ctx, const void* h_raw, int f32, int stri
         src.f32 = f32;
         src.stride = stride;
         const ArenaMark mark = arena_mark(ctx);
+        stage_mark(ctx, STAGE_VOXEL);
         SB_TRY(voxel_downsample_src(ctx, src, in_off.data(), nc, voxel, d_ds + 3 * off_ds[c0], out_off.data(), nullptr));
         arena_release(ctx, mark);
         for (int i = 1; i <= nc; ++i) off_ds[c0 + i] = off_ds[c0] + out_off[i];
@@ -229,9 +262,9 @@ static int register_batch_impl(Ctx* ctx, PointSrc src, const void* h_raw, const 
         for (int c = c0; c < c1; ++c)
             if (tree_of[c] >= 0) ids.push_back(c);
         if (ids.empty()) return SB_OK;
-        if (!h_raw) stage_mark(ctx, STAGE_INDEX);
+        stage_mark(ctx, STAGE_INDEX);
         SB_TRY(forest_append(ctx, &F, d_pts, off.data(), ids.data(), (int)ids.size()));
-        if (!h_raw) stage_mark(ctx, STAGE_NORMALS);
+        stage_mark(ctx, STAGE_NORMALS);
         return forest_normals(ctx, &F, cfg->normals_k, nullptr, nullptr);
     };
     // 1. voxel grid (slam_node.cpp:122)
@@ -369,6 +402,7 @@ void sb_ctx_destroy(sb_ctx* ctx) {
     cudaFree(c->d_flags);
     for (int i = 0; i < c->ev_created; ++i) cudaEventDestroy(c->ev[i]);
     if (c->pinned) cudaFreeHost(c->pinned);
+    if (c->tbuf) cudaFreeHost(c->tbuf);
     for (int i = 0; i < 2; ++i)
         if (c->copy_ev[i]) cudaEventDestroy(c->copy_ev[i]);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);

@@ -61,6 +61,12 @@ struct Ctx {
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    // Small host tables (tile lists, offsets, descriptors) reach the device through a mapped pinned buffer and a copy
+    // KERNEL, not through the copy engine: while a bulk upload is in flight the engine's queue is minutes of PCIe
+    // time deep, and every small cudaMemcpyAsync of the stages running meanwhile would wait behind it.
+    char* tbuf = nullptr;        // host address (cudaHostAllocMapped)
+    char* tbuf_dev = nullptr;    // device address of the same buffer
+    size_t tbuf_cap = 0, tbuf_used = 0;
     cudaStream_t copy_stream = nullptr;   // host-to-device chunks of the pipelined entry points (api.cu)
     cudaEvent_t copy_ev[2] = {nullptr, nullptr};
     Arena arena;
@@ -79,9 +85,9 @@ struct Ctx {
     int vox_last_path = 0;
     // optional per-stage CUDA-event timing of the last pipeline call (bench.py's roofline figures)
     bool profiling = false;
-    cudaEvent_t ev[32];
-    int ev_stage[32];
-    double ev_host[32];  // host steady_clock milliseconds at the same marks
+    cudaEvent_t ev[128];
+    int ev_stage[128];
+    double ev_host[128];  // host steady_clock milliseconds at the same marks
     int n_ev = 0, ev_created = 0;
     i64 last_icp_iterations = 0;   // max history length of the last icp_batch (launches of k_icp_iter)
     i64 last_counts[4] = {0, 0, 0, 0};  // raw rows, downsampled rows, target rows, sum over pairs of n_src * passes
@@ -99,6 +105,8 @@ ArenaMark arena_mark(Ctx* ctx);
 void arena_release(Ctx* ctx, ArenaMark m);
 int arena_alloc(Ctx* ctx, size_t bytes, void** out);
 int pinned_reserve(Ctx* ctx, size_t bytes);
+// host table -> device memory (4-byte granularity), ordered on the context's stream; h_src may be reused on return
+int table_upload(Ctx* ctx, void* d_dst, const void* h_src, size_t bytes);
 
 template <typename T>
 inline int arena_get(Ctx* ctx, size_t count, T** out) {

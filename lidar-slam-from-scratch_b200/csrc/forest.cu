@@ -292,8 +292,7 @@ int forest_append(Ctx* ctx, Forest* f, const double* d_xyz, const i64* h_off, co
     f->n_points += np;
     TreeDesc* d_new = f->d_trees + t0;
     if (n_new > 0)
-        SB_CUDA(ctx, cudaMemcpyAsync(d_new, f->h_trees.data() + t0, sizeof(TreeDesc) * (size_t)n_new, cudaMemcpyHostToDevice,
-                                     ctx->stream));
+        SB_TRY(table_upload(ctx, d_new, f->h_trees.data() + t0, sizeof(TreeDesc) * (size_t)n_new));
     if (np == 0) return SB_OK;
 
     const ArenaMark mark = arena_mark(ctx);  // everything below is scratch of this build
@@ -309,14 +308,13 @@ int forest_append(Ctx* ctx, Forest* f, const double* d_xyz, const i64* h_off, co
     SB_TRY(arena_get(ctx, (size_t)np, &kb));
     SB_TRY(arena_get(ctx, (size_t)np, &va));
     SB_TRY(arena_get(ctx, (size_t)np, &vb));
-    SB_CUDA(ctx, cudaMemcpyAsync(d_src_off, src_off.data(), sizeof(i64) * (size_t)n_new, cudaMemcpyHostToDevice, ctx->stream));
-    SB_CUDA(ctx, cudaMemcpyAsync(d_chunks, chunks.data(), sizeof(Chunk) * chunks.size(), cudaMemcpyHostToDevice, ctx->stream));
+    SB_TRY(table_upload(ctx, d_src_off, src_off.data(), sizeof(i64) * (size_t)n_new));
+    SB_TRY(table_upload(ctx, d_chunks, chunks.data(), sizeof(Chunk) * chunks.size()));
     {
         std::vector<long long> init((size_t)6 * n_new);
         for (int t = 0; t < n_new; ++t)
             for (int a = 0; a < 3; ++a) { init[6 * t + a] = INT64_MAX; init[6 * t + 3 + a] = INT64_MIN; }
-        SB_CUDA(ctx, cudaMemcpyAsync(d_bb, init.data(), sizeof(long long) * init.size(), cudaMemcpyHostToDevice, ctx->stream));
-        SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the host vectors above go out of scope
+        SB_TRY(table_upload(ctx, d_bb, init.data(), sizeof(long long) * init.size()));
     }
     unsigned nch = (unsigned)chunks.size();
     SB_LAUNCH(ctx, k_bbox, nch, 256, 0, d_xyz, d_src_off, d_chunks, d_bb);
@@ -681,7 +679,7 @@ int forest_normals(Ctx* ctx, Forest* f, int k, double* d_out_normals, double* d_
     unsigned long long* d_spacing;
     SB_TRY(arena_get(ctx, tio.size(), &d_tio));
     SB_TRY(arena_get(ctx, (size_t)B.n_trees, &d_spacing));
-    SB_CUDA(ctx, cudaMemcpyAsync(d_tio, tio.data(), sizeof(i64) * tio.size(), cudaMemcpyHostToDevice, ctx->stream));
+    SB_TRY(table_upload(ctx, d_tio, tio.data(), sizeof(i64) * tio.size()));
     SB_CUDA(ctx, cudaMemsetAsync(d_spacing, 0, sizeof(unsigned long long) * (size_t)B.n_trees, ctx->stream));
     SB_CUDA(ctx, cudaMemsetAsync(B.grid, 0xff, sizeof(GridSlot) * (size_t)B.n_slots, ctx->stream));
     SB_LAUNCH(ctx, k_knn<1>, query_grid(ctx, n_items), QWARPS * 32, 0, view_of(f, B.t0), nullptr,

@@ -219,10 +219,8 @@ int segmented_sort_pairs(Ctx* ctx, u64* keys_a, u64* keys_b, uint32_t* vals_a, u
     // tile table (host-built, staged through pinned memory)
     i64 n_tiles = 0;
     for (int s = 0; s < n_seg; ++s) n_tiles += (h_seg_off[s + 1] - h_seg_off[s] + SORT_TILE - 1) / SORT_TILE;
-    SB_TRY(pinned_reserve(ctx, (size_t)n_tiles * sizeof(SortTile)));
-    // make sure an earlier async copy out of the pinned buffer has completed before we overwrite it
-    SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    SortTile* ht = reinterpret_cast<SortTile*>(ctx->pinned);
+    std::vector<SortTile> ht_vec((size_t)n_tiles);
+    SortTile* ht = ht_vec.data();
     i64 ti = 0;
     for (int s = 0; s < n_seg; ++s) {
         i64 n = h_seg_off[s + 1] - h_seg_off[s];
@@ -244,7 +242,7 @@ int segmented_sort_pairs(Ctx* ctx, u64* keys_a, u64* keys_b, uint32_t* vals_a, u
     uint32_t* H;
     SB_TRY(arena_get(ctx, (size_t)n_tiles, &d_tiles));
     SB_TRY(arena_get(ctx, (size_t)n_tiles * RADIX, &H));
-    SB_CUDA(ctx, cudaMemcpyAsync(d_tiles, ht, (size_t)n_tiles * sizeof(SortTile), cudaMemcpyHostToDevice, ctx->stream));
+    SB_TRY(table_upload(ctx, d_tiles, ht, (size_t)n_tiles * sizeof(SortTile)));
     u64* kin = keys_a; u64* kout = keys_b;
     uint32_t* vin = vals_a; uint32_t* vout = vals_b;
     for (int shift = 0; shift < key_bits; shift += 8) {

@@ -374,8 +374,11 @@ __global__ void __launch_bounds__(256) k_vox_insert(const PointSrc src, const Vo
         const int a = threadIdx.x;
         i64 v = s_red[0][a];
         for (int w = 1; w < 8; ++w) v = a < 3 ? min(v, s_red[w][a]) : max(v, s_red[w][a]);
-        if (a < 3) { if (v != INT64_MAX) atomicMin(&mm[a], v); }
-        else if (v != INT64_MIN) atomicMax(&mm[a], v);
+        // thousands of blocks end here and all of them would hit the same six words: look first, only a block that
+        // improves the bound pays for the atomic
+        const i64 cur = *reinterpret_cast<volatile i64*>(&mm[a]);
+        if (a < 3) { if (v != INT64_MAX && v < cur) atomicMin(&mm[a], v); }
+        else if (v != INT64_MIN && v > cur) atomicMax(&mm[a], v);
     }
 }
 
@@ -568,9 +571,8 @@ static int voxel_hashed_dev(Ctx* ctx, const PointSrc src, const i64* h_off, int 
     SB_TRY(arena_get(ctx, (size_t)PATCH_CAP, &d_list));
     d_cursor = d_nvox + n_clouds;
     d_list_n = d_nvox + 2 * n_clouds;
-    SB_CUDA(ctx, cudaMemcpyAsync(d_clouds, hc.data(), sizeof(VoxCloud) * n_clouds, cudaMemcpyHostToDevice, ctx->stream));
-    SB_CUDA(ctx, cudaMemcpyAsync(d_tile_cloud, h_tile_cloud.data(), sizeof(int) * (size_t)n_tiles, cudaMemcpyHostToDevice,
-                                 ctx->stream));
+    SB_TRY(table_upload(ctx, d_clouds, hc.data(), sizeof(VoxCloud) * n_clouds));
+    SB_TRY(table_upload(ctx, d_tile_cloud, h_tile_cloud.data(), sizeof(int) * (size_t)n_tiles));
     SB_LAUNCH(ctx, k_vox_clear, ceil_div(n_slots, 256), 256, 0, d_table, n_slots);
     SB_CUDA(ctx, cudaMemsetAsync(d_nvox, 0, sizeof(int) * (2 * (size_t)n_clouds + 1), ctx->stream));
     SB_CUDA(ctx, cudaMemsetAsync(ctx->d_flags, 0, sizeof(int), ctx->stream));
@@ -618,7 +620,7 @@ static int voxel_hashed_dev(Ctx* ctx, const PointSrc src, const i64* h_off, int 
     SB_TRY(arena_get(ctx, (size_t)m, &va));
     SB_TRY(arena_get(ctx, (size_t)m, &vb));
     SB_TRY(arena_get(ctx, (size_t)n_clouds + 1, &d_out_off));
-    SB_CUDA(ctx, cudaMemcpyAsync(d_out_off, h_out_off, sizeof(i64) * (n_clouds + 1), cudaMemcpyHostToDevice, ctx->stream));
+    SB_TRY(table_upload(ctx, d_out_off, h_out_off, sizeof(i64) * (n_clouds + 1)));
     SB_LAUNCH(ctx, k_vox_list, ceil_div(n_slots, 256), 256, 0, d_clouds, n_clouds, n_slots, d_table, d_out_off, d_cursor, P,
               ka, va);
     SB_TRY(segmented_sort_pairs(ctx, ka, kb, va, vb, h_out_off, n_clouds, bx + by + bz, &ks, &vs));
