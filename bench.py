@@ -353,13 +353,58 @@ def main():
                                   "(NN search twice per iteration); reference binary not buildable (no Eigen)",
                         "parity_max_translation_diff_m": max_dt}
 
+        # ---- the other metrics BASELINE.json names, on their own configurations (short, device-resident, untimed
+        # by the driver): C3 = k-NN (k=10) + normals on 128-beam scans at voxel 0.2; C4 = Scan Context search over a
+        # 4000-keyframe database
+        extras = {}
+        try:
+            s128 = dict(SENSOR, beams=128, azimuth_steps=2048)
+            n3 = 48
+            d3 = torch.empty(n3 * 128 * 2048 * 3, dtype=torch.float64, device="cuda")
+            off3 = eng.synth_scans_dev(s128, world, poses[:n3], 5000, d3.data_ptr())
+            cfg3 = eng.icp_config(max_iterations=0, normals_k=10)   # index + normals only; no ICP iterations
+            p3s, p3t = np.arange(1, n3, dtype=np.int32), np.arange(0, n3 - 1, dtype=np.int32)
+            for _ in range(3):
+                eng.register_batch(None, off3, p3s, p3t, voxel=0.2, cfg=cfg3, device_ptr=d3.data_ptr())
+            eng.set_profiling(True)
+            eng.register_batch(None, off3, p3s, p3t, voxel=0.2, cfg=cfg3, device_ptr=d3.data_ptr())
+            st3, c3 = eng.stage_ms(), eng.last_counts()
+            eng.set_profiling(False)
+            extras["c3_knn_normals"] = {
+                "workload": "128 beams x 2048 az, voxel 0.2 m, k = 10, %d indexed clouds of %.0f points" %
+                            (n3 - 1, c3["target_rows"] / (n3 - 1)),
+                "knn_plus_normals_queries_per_s": c3["target_rows"] / (st3["normals"] * 1e-3),
+                "ms": st3["normals"], "index_build_ms": st3["index_build"], "voxel_ms": st3["voxel"],
+                "raw_points_per_s_voxel_grid": c3["raw_rows"] / (st3["voxel"] * 1e-3)}
+            del d3
+            rng = np.random.default_rng(3)
+            det = slam_b200.LoopClosureDetector(eng, frame_gap=50, sc_distance_threshold=0.25)
+            tiny = np.zeros((4, 3))
+            base = np.where(rng.uniform(size=(64, 1200)) < 0.35, rng.uniform(-1.7, 9.0, (64, 1200)), 0.0)
+            for i in range(4001):
+                det.addFrame(tiny, i, desc=base[i % 64] + 0.01 * (i // 64))
+            for _ in range(3):
+                det.candidates_local()
+            t0 = time.perf_counter()
+            reps = 20
+            for _ in range(reps):
+                cd, ce = det.candidates_local()
+            dt4 = (time.perf_counter() - t0) / reps
+            extras["c4_scan_context_search"] = {
+                "workload": "1 query vs 4000 descriptors (20x60, 60 column shifts), host call incl. result copy",
+                "ms_per_query": dt4 * 1e3, "descriptor_pairs_per_s": 4000 / dt4,
+                "db_bytes": 4000 * 9600, "gflops_fp64": 2 * 60 * 1200 * 4000 / dt4 / 1e9}
+            det.close()
+        except Exception as ex:  # the headline line must still be printed
+            extras["error"] = repr(ex)
+
         iters = res.num_iterations
         out = {
             "metric": "ICP scan-pairs/s", "value": value, "unit": "pairs/s", "n_gpus": world_size, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_max, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(F),
             "ms_per_frame": ms_max / F, "clocks": clocks, "e2e": e2e, "e2e_f64": e2e_f64, "gpu_launches": int(launches),
-            "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "extras": extras,
             "workload_stats": {"raw_points_per_scan": n_raw / (F + 1), "voxel_points_per_scan": M / (F + 1),
                                "icp_iterations_mean": float(iters.mean()), "icp_iterations_max": int(iters.max()),
                                "converged_frac": float(res.converged.mean())},
