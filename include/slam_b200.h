@@ -216,6 +216,31 @@ int sb_loop_candidates_local(sb_loop* loop, double* dist, int32_t* entry, int32_
 int sb_loop_verify_entries(sb_loop* loop, const int32_t* entry, const double* dist, int32_t n, sb_loop_result* results,
                            int32_t* converged);
 
+/* ---------------------------------------------------------------- after the path: world frame, map -------- */
+/* The data-parallel steps that follow registration in slam_node.cpp.  poses16: n_clouds
+ * row-major 4x4 transforms (Transformation::matrix()), cloud c is rows [offsets[c], offsets[c+1]). */
+typedef struct sb_grid_config {   /* slam::OccupancyGridConfig, slam_viz/include/slam_viz/ros/slam_node.hpp:35-40 */
+    double resolution;            /* 0.2  */
+    double height_min;            /* 0.3  */
+    double height_max;            /* 2.0  */
+    double max_range;             /* 40.0 */
+} sb_grid_config;
+void sb_default_grid_config(sb_grid_config* cfg);
+/* world = cloud * R^T + t for every cloud (slam_node.cpp:147, 189, 201-203). out_xyz: offsets[n_clouds]*3 doubles. */
+int sb_transform_clouds(sb_ctx* ctx, const double* xyz, const int64_t* offsets, int32_t n_clouds, const double* poses16,
+                        double* out_xyz);
+/* rebuild_occupancy_grid (slam_node.cpp:211-229): transforms every (sensor-frame) cloud with its pose, keeps points
+ * with height_min <= z <= height_max and 0.5 <= horizontal range from the pose's translation <= max_range, and
+ * returns the set of cells (floor(x/res), floor(y/res)), ascending in (x, y) (the reference's unordered_set has no
+ * order).  out_cells: 2 ints per cell, up to `capacity` cells; *out_count = number of cells found. */
+int sb_occupancy_cells(sb_ctx* ctx, const double* xyz, const int64_t* offsets, int32_t n_clouds, const double* poses16,
+                       const sb_grid_config* cfg, int32_t* out_cells, int64_t capacity, int64_t* out_count);
+/* build_final_global_map + the voxel grid publish_global_map applies to it (slam_node.cpp:196-209, 235-238): all
+ * clouds in the world frame as one cloud, voxel-downsampled with `voxel` (the node passes 2 * voxel_size);
+ * voxel <= 0 returns the concatenation.  out_xyz: offsets[n_clouds]*3 doubles. */
+int sb_global_map(sb_ctx* ctx, const double* xyz, const int64_t* offsets, int32_t n_clouds, const double* poses16,
+                  double voxel, double* out_xyz, int64_t* out_m);
+
 /* ---------------------------------------------------------------- bench/test input generator --------------- */
 /* Synthetic 64/128-beam raycast straight into device memory (synth/lidar_synth.h).  boxes: host, n_boxes*6 floats;
  * poses: host, n_scans*3 doubles (x, y, yaw); d_xyz: device, n_scans*beams*azimuth_steps*3 doubles capacity;

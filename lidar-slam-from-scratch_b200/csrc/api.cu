@@ -914,6 +914,98 @@ int sb_loop_detect(sb_loop* loop, sb_loop_result* results, int32_t capacity, int
     return SB_OK;
 }
 
+// ---------------------------------------------------------------- after the path: world frame, map
+void sb_default_grid_config(sb_grid_config* cfg) {  // slam_node.hpp:35-40
+    cfg->resolution = 0.2;
+    cfg->height_min = 0.3;
+    cfg->height_max = 2.0;
+    cfg->max_range = 40.0;
+}
+
+static int check_clouds(Ctx* c, const double* xyz, const int64_t* offsets, int32_t n_clouds, const double* poses16) {
+    if (offsets[0] != 0) return fail(c, SB_ERR_INVALID_ARG, "offsets must start at 0");
+    for (int i = 0; i < n_clouds; ++i)
+        if (offsets[i + 1] < offsets[i]) return fail(c, SB_ERR_INVALID_ARG, "offsets must be non-decreasing");
+    if (offsets[n_clouds] > 0 && (!xyz || !poses16)) return fail(c, SB_ERR_INVALID_ARG, "null buffer");
+    return SB_OK;
+}
+
+// uploads clouds, offsets and poses and transforms the clouds into the world frame
+static int world_clouds(Ctx* c, const double* xyz, const int64_t* offsets, int32_t n_clouds, const double* poses16,
+                        double** d_world, i64** d_off, double** d_poses) {
+    const i64 n = offsets[n_clouds];
+    double* d_in;
+    SB_TRY(upload(c, xyz, sizeof(double) * 3 * n, (void**)&d_in));
+    SB_TRY(upload(c, offsets, sizeof(i64) * (n_clouds + 1), (void**)d_off));
+    SB_TRY(upload(c, poses16, sizeof(double) * 16 * (size_t)(n_clouds > 0 ? n_clouds : 0), (void**)d_poses));
+    SB_TRY(arena_get(c, (size_t)3 * (n > 0 ? n : 1), d_world));
+    return transform_clouds_dev(c, d_in, *d_off, n_clouds, *d_poses, n, *d_world);
+}
+
+int sb_transform_clouds(sb_ctx* ctx, const double* xyz, const int64_t* offsets, int32_t n_clouds, const double* poses16,
+                        double* out_xyz) {
+    if (!ctx || !offsets || n_clouds < 0) return SB_ERR_INVALID_ARG;
+    Ctx* c = &ctx->c;
+    Enter g(c);
+    SB_TRY(check_clouds(c, xyz, offsets, n_clouds, poses16));
+    const i64 n = offsets[n_clouds];
+    if (n == 0) return SB_OK;
+    if (!out_xyz) return fail(c, SB_ERR_INVALID_ARG, "null output buffer");
+    double *d_world, *d_poses;
+    i64* d_off;
+    SB_TRY(world_clouds(c, xyz, offsets, n_clouds, poses16, &d_world, &d_off, &d_poses));
+    SB_TRY(download(c, out_xyz, d_world, sizeof(double) * 3 * n));
+    SB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return SB_OK;
+}
+
+int sb_occupancy_cells(sb_ctx* ctx, const double* xyz, const int64_t* offsets, int32_t n_clouds, const double* poses16,
+                       const sb_grid_config* cfg, int32_t* out_cells, int64_t capacity, int64_t* out_count) {
+    if (!ctx || !offsets || n_clouds < 0 || !cfg || !out_count || capacity < 0 || (capacity > 0 && !out_cells))
+        return SB_ERR_INVALID_ARG;
+    Ctx* c = &ctx->c;
+    Enter g(c);
+    *out_count = 0;
+    SB_TRY(check_clouds(c, xyz, offsets, n_clouds, poses16));
+    if (!(cfg->resolution > 0)) return fail(c, SB_ERR_INVALID_ARG, "grid resolution must be positive");
+    const i64 n = offsets[n_clouds];
+    if (n == 0) return SB_OK;
+    double *d_world, *d_poses;
+    i64* d_off;
+    int* d_cells;
+    SB_TRY(world_clouds(c, xyz, offsets, n_clouds, poses16, &d_world, &d_off, &d_poses));
+    SB_TRY(arena_get(c, (size_t)2 * (capacity > 0 ? capacity : 1), &d_cells));
+    i64 count = 0;
+    SB_TRY(occupancy_cells_dev(c, d_world, d_off, n_clouds, d_poses, n, cfg, d_cells, capacity, &count));
+    *out_count = count;
+    const i64 m = count < capacity ? count : capacity;
+    SB_TRY(download(c, out_cells, d_cells, sizeof(int) * 2 * (size_t)m));
+    SB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return SB_OK;
+}
+
+int sb_global_map(sb_ctx* ctx, const double* xyz, const int64_t* offsets, int32_t n_clouds, const double* poses16,
+                  double voxel, double* out_xyz, int64_t* out_m) {
+    if (!ctx || !offsets || n_clouds < 0 || !out_m) return SB_ERR_INVALID_ARG;
+    Ctx* c = &ctx->c;
+    Enter g(c);
+    *out_m = 0;
+    SB_TRY(check_clouds(c, xyz, offsets, n_clouds, poses16));
+    const i64 n = offsets[n_clouds];
+    if (n == 0) return SB_OK;
+    if (!out_xyz) return fail(c, SB_ERR_INVALID_ARG, "null output buffer");
+    double *d_world, *d_poses, *d_out;
+    i64* d_off;
+    SB_TRY(world_clouds(c, xyz, offsets, n_clouds, poses16, &d_world, &d_off, &d_poses));
+    SB_TRY(arena_get(c, (size_t)3 * n, &d_out));
+    i64 one[2] = {0, n}, out_off[2] = {0, 0};
+    SB_TRY(voxel_downsample_dev(c, d_world, one, 1, voxel, d_out, out_off, nullptr));
+    *out_m = out_off[1];
+    SB_TRY(download(c, out_xyz, d_out, sizeof(double) * 3 * (size_t)out_off[1]));
+    SB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return SB_OK;
+}
+
 // ---------------------------------------------------------------- synthetic input generator
 int sb_synth_scans_dev(sb_ctx* ctx, int32_t beams, int32_t azimuth_steps, float elev_top_deg, float elev_bot_deg,
                        float max_range, float noise_sigma, float sensor_height, const float* boxes, int32_t n_boxes,

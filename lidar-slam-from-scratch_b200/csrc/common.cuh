@@ -325,6 +325,11 @@ int sc_keys_dev(Ctx* ctx, const double* d_desc, double* d_ring, double* d_sector
 // icp.cu
 int solve_point_to_plane_dev(Ctx* ctx, const double* d_src, const double* d_tgt, const double* d_nrm, i64 n,
                              double* d_out_T);
+// mapping.cu
+int transform_clouds_dev(Ctx* ctx, const double* d_xyz, const i64* d_off, int n_clouds, const double* d_poses, i64 n,
+                         double* d_out);
+int occupancy_cells_dev(Ctx* ctx, const double* d_world, const i64* d_off, int n_clouds, const double* d_poses, i64 n,
+                        const sb_grid_config* cfg, int* d_cells, i64 capacity, i64* count);
 // synth.cu
 int synth_scans_dev(Ctx* ctx, int beams, int azimuth_steps, float elev_top_deg, float elev_bot_deg, float max_range,
                     float noise_sigma, float sensor_height, const float* boxes6, int n_boxes, const double* poses,

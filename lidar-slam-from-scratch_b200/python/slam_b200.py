@@ -112,6 +112,10 @@ SYMBOLS = {
     "sb_loop_detect": (C.c_int, [_P, C.POINTER(LoopResultC), C.c_int32, _I32]),
     "sb_loop_candidates_local": (C.c_int, [_P, _D, _I32, C.c_int32, _I32]),
     "sb_loop_verify_entries": (C.c_int, [_P, _I32, _D, C.c_int32, C.POINTER(LoopResultC), _I32]),
+    "sb_default_grid_config": (None, [_P]),
+    "sb_transform_clouds": (C.c_int, [_P, _D, _I64, C.c_int32, _D, _D]),
+    "sb_occupancy_cells": (C.c_int, [_P, _D, _I64, C.c_int32, _D, _P, _I32, C.c_int64, _I64]),
+    "sb_global_map": (C.c_int, [_P, _D, _I64, C.c_int32, _D, C.c_double, _D, _I64]),
     "sb_synth_scans_dev": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                                      C.POINTER(C.c_float), C.c_int32, _D, C.c_int32, C.c_uint64, _P, _I64]),
 }
@@ -310,6 +314,36 @@ class Engine:
         self._check(s)
         out = ICPResultBatch(res[:npairs])
         return (out, sc) if want_sc else out
+
+    # ---- after the path: world-frame clouds, occupancy cells, global map (slam_node.cpp:147-152, 196-238)
+    def transform_clouds(self, points, offsets, poses):
+        pts, off = _f64(points, 3), np.ascontiguousarray(offsets, dtype=np.int64)
+        T = np.ascontiguousarray(poses, dtype=np.float64).reshape(-1, 16)
+        out = np.empty_like(pts)
+        self._check(self.lib.sb_transform_clouds(self.h, _dp(pts), off.ctypes.data_as(_I64), off.shape[0] - 1, _dp(T),
+                                                 _dp(out)))
+        return out
+
+    def occupancy_cells(self, points, offsets, poses, resolution=0.2, height_min=0.3, height_max=2.0, max_range=40.0,
+                        capacity=None):
+        pts, off = _f64(points, 3), np.ascontiguousarray(offsets, dtype=np.int64)
+        T = np.ascontiguousarray(poses, dtype=np.float64).reshape(-1, 16)
+        cfg = (C.c_double * 4)(resolution, height_min, height_max, max_range)
+        cap = int(capacity if capacity is not None else max(pts.shape[0], 1))
+        cells = np.empty((max(cap, 1), 2), dtype=np.int32)
+        cnt = C.c_int64(0)
+        self._check(self.lib.sb_occupancy_cells(self.h, _dp(pts), off.ctypes.data_as(_I64), off.shape[0] - 1, _dp(T),
+                                                C.cast(cfg, _P), cells.ctypes.data_as(_I32), cap, C.byref(cnt)))
+        return cells[:min(cnt.value, cap)].copy(), int(cnt.value)
+
+    def global_map(self, points, offsets, poses, voxel):
+        pts, off = _f64(points, 3), np.ascontiguousarray(offsets, dtype=np.int64)
+        T = np.ascontiguousarray(poses, dtype=np.float64).reshape(-1, 16)
+        out = np.empty((max(pts.shape[0], 1), 3))
+        m = C.c_int64(0)
+        self._check(self.lib.sb_global_map(self.h, _dp(pts), off.ctypes.data_as(_I64), off.shape[0] - 1, _dp(T),
+                                           float(voxel), _dp(out), C.byref(m)))
+        return out[:m.value].copy()
 
     # ---- Scan Context (scan_context.hpp)
     def sc_compute(self, cloud):

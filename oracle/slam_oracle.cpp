@@ -617,6 +617,30 @@ struct LoopDetector {
     }
 };
 
+// ===========================================================================
+// The steps right after the path in slam_node.cpp: world-frame clouds, occupancy cells, global map
+// ===========================================================================
+// world = cloud * R^T + t, row by row (slam_viz/src/ros/slam_node.cpp:147, 189, 201-203)
+static void transform_cloud(const double* xyz, i64 n, const double T[16], double* out) {
+    for (i64 i = 0; i < n; ++i) {
+        const double x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+        for (int a = 0; a < 3; ++a) out[3 * i + a] = ((x * T[4 * a] + y * T[4 * a + 1]) + z * T[4 * a + 2]) + T[4 * a + 3];
+    }
+}
+
+// update_occupancy_grid (slam_node.cpp:211-221) into an ordered set of (x, y) cells
+static void occupancy_insert(const double* world, i64 n, const double sensor[3], double res, double hmin, double hmax,
+                             double max_range, std::vector<std::pair<int, int>>& cells) {
+    for (i64 i = 0; i < n; ++i) {
+        const double x = world[3 * i], y = world[3 * i + 1], z = world[3 * i + 2];
+        if (z < hmin || z > hmax) continue;
+        const double dx = x - sensor[0], dy = y - sensor[1];
+        const double r = std::sqrt(dx * dx + dy * dy);
+        if (r > max_range || r < 0.5) continue;
+        cells.emplace_back(static_cast<int>(std::floor(x / res)), static_cast<int>(std::floor(y / res)));
+    }
+}
+
 }  // namespace orc
 
 // ===========================================================================
@@ -681,6 +705,34 @@ int orc_icp_point_to_plane(const double* src, int ns, const double* tgt, int nt,
     *final_error = o.final_error;
     if (history) std::memcpy(history, o.history.data(), sizeof(double) * o.history.size());
     return static_cast<int>(o.history.size());
+}
+void orc_transform_cloud(const double* xyz, long long n, const double* T16, double* out) {
+    orc::transform_cloud(xyz, n, T16, out);
+}
+// rebuild_occupancy_grid (slam_node.cpp:223-229): all clouds (sensor frame, CSR) with their poses -> unique cells in
+// ascending (x, y) order (the reference's unordered_set has no order).  Returns the number of cells; out_cells may
+// be null to count only.
+long long orc_occupancy_cells(const double* xyz, const long long* offsets, int n_clouds, const double* poses16,
+                              double res, double hmin, double hmax, double max_range, int* out_cells,
+                              long long capacity) {
+    std::vector<std::pair<int, int>> cells;
+    std::vector<double> w;
+    for (int c = 0; c < n_clouds; ++c) {
+        const long long n = offsets[c + 1] - offsets[c];
+        w.resize((size_t)(3 * n));
+        const double* T = poses16 + 16 * c;
+        orc::transform_cloud(xyz + 3 * offsets[c], n, T, w.data());
+        const double sensor[3] = {T[3], T[7], T[11]};
+        orc::occupancy_insert(w.data(), n, sensor, res, hmin, hmax, max_range, cells);
+    }
+    std::sort(cells.begin(), cells.end());
+    cells.erase(std::unique(cells.begin(), cells.end()), cells.end());
+    if (out_cells)
+        for (size_t i = 0; i < cells.size() && (long long)i < capacity; ++i) {
+            out_cells[2 * i] = cells[i].first;
+            out_cells[2 * i + 1] = cells[i].second;
+        }
+    return (long long)cells.size();
 }
 void orc_sc_compute(const double* xyz, long long n, double* desc1200) { orc::sc_compute(xyz, n, desc1200); }
 double orc_sc_distance(const double* a, const double* b) { return orc::sc_distance(a, b); }

@@ -57,6 +57,10 @@ class Oracle:
         lib.orc_icp_point_to_plane.restype = C.c_int
         lib.orc_icp_point_to_plane.argtypes = [_D, C.c_int, _D, C.c_int, C.c_int, C.c_double, C.c_double, _D, C.c_int,
                                                C.c_int, _D, _I, _I, _D, _D]
+        lib.orc_transform_cloud.argtypes = [_D, C.c_longlong, _D, _D]
+        lib.orc_occupancy_cells.restype = C.c_longlong
+        lib.orc_occupancy_cells.argtypes = [_D, _LL, C.c_int, _D, C.c_double, C.c_double, C.c_double, C.c_double, _I,
+                                            C.c_longlong]
         lib.orc_sc_compute.argtypes = [_D, C.c_longlong, _D]
         lib.orc_sc_distance.restype = C.c_double
         lib.orc_sc_distance.argtypes = [_D, _D]
@@ -153,6 +157,21 @@ class Oracle:
                                              _dp(T), C.byref(conv), C.byref(nit), C.byref(fe), _dp(hist))
         return dict(transformation=T.reshape(4, 4), converged=bool(conv.value), num_iterations=nit.value,
                     final_error=fe.value, error_history=hist[:hl].copy())
+
+    def transform_cloud(self, pts, T):
+        p, T = _f64(pts), np.ascontiguousarray(T, dtype=np.float64).reshape(16)
+        out = np.empty_like(p)
+        self.lib.orc_transform_cloud(_dp(p), p.shape[0], _dp(T), _dp(out))
+        return out
+
+    def occupancy_cells(self, pts, offsets, poses, res=0.2, hmin=0.3, hmax=2.0, max_range=40.0):
+        p = _f64(pts)
+        off = np.ascontiguousarray(offsets, dtype=np.int64)
+        T = np.ascontiguousarray(poses, dtype=np.float64).reshape(-1, 16)
+        cells = np.empty((max(p.shape[0], 1), 2), dtype=np.int32)
+        n = self.lib.orc_occupancy_cells(_dp(p), off.ctypes.data_as(_LL), off.shape[0] - 1, _dp(T), res, hmin, hmax,
+                                         max_range, cells.ctypes.data_as(_I), cells.shape[0])
+        return cells[:n].copy()
 
     def sc_compute(self, pts):
         p = _f64(pts)

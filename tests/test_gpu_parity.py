@@ -485,3 +485,34 @@ def test_golden_fixtures_gpu(engine):
     dT = r.transformation @ np.linalg.inv(g["icp_T"])
     assert np.linalg.norm(dT[:3, 3]) < 1e-4 and rot_angle(dT[:3, :3]) < 1e-5
     assert r.converged == bool(g["icp_converged"]) and np.allclose(r.error_history, g["icp_history"], atol=1e-6)
+
+
+# ------------------------------------------------------------------ after the path: world frame, occupancy, map
+def test_world_frame_occupancy_and_global_map(engine, oracle, synth, scene):
+    """slam_node.cpp:147 (world clouds, bit-exact), :211-229 (occupancy cell set, identical) and
+    :196-209 + :237 (global map = world clouds voxel-downsampled at 2 * voxel_size, bit-exact vs the oracle)."""
+    s = oracle_lib.small_sensor(32, 600)
+    poses = [(2.0 * i, 0.3 * i, 0.05 * i) for i in range(6)]
+    clouds = [oracle.voxel_downsample(synth.scan(s, scene, p, 80 + i), 0.5)[0] for i, p in enumerate(poses)]
+    off = np.r_[0, np.cumsum([len(c) for c in clouds])]
+    Ts = []
+    for x, y, yaw in poses:
+        T = np.eye(4)
+        T[:3, :3] = [[np.cos(yaw), -np.sin(yaw), 0], [np.sin(yaw), np.cos(yaw), 0], [0, 0, 1]]
+        T[:3, 3] = [x, y, 1.73]
+        Ts.append(T)
+    Ts = np.stack(Ts)
+    allpts = np.vstack(clouds)
+    world = engine.transform_clouds(allpts, off, Ts)
+    ref_world = np.vstack([oracle.transform_cloud(c, T) for c, T in zip(clouds, Ts)])
+    assert np.array_equal(world, ref_world)
+    cells, count = engine.occupancy_cells(allpts, off, Ts)
+    ref_cells = oracle.occupancy_cells(allpts, off, Ts)
+    assert count == len(ref_cells) and np.array_equal(cells, ref_cells) and count > 100
+    few, count2 = engine.occupancy_cells(allpts, off, Ts, capacity=10)
+    assert count2 == count and np.array_equal(few, ref_cells[:10])
+    gm = engine.global_map(allpts, off, Ts, 1.0)
+    ref_gm, _ = oracle.voxel_downsample(ref_world, 1.0)
+    assert np.array_equal(gm, ref_gm)
+    assert np.array_equal(engine.global_map(allpts, off, Ts, 0.0), ref_world)
+    assert engine.occupancy_cells(np.zeros((0, 3)), [0], np.zeros((0, 16)))[1] == 0

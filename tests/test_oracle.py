@@ -283,3 +283,20 @@ def test_golden_fixtures(oracle):
     assert np.allclose(r["transformation"], g["icp_T"], atol=1e-9)
     assert np.allclose(r["error_history"], g["icp_history"], atol=1e-10)
     assert r["converged"] == bool(g["icp_converged"])
+
+
+def test_transform_and_occupancy_match_numpy(oracle):
+    """slam_node.cpp:147 (world = cloud * R^T + t) and :211-229 (occupancy cells) vs a numpy restatement."""
+    rng = np.random.default_rng(4)
+    pts = rng.uniform(-30, 30, (5000, 3)) * [1, 1, 0.1]
+    th = 0.3
+    T = np.eye(4)
+    T[:3, :3] = [[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1]]
+    T[:3, 3] = [5.0, -2.0, 0.4]
+    w = oracle.transform_cloud(pts, T)
+    assert np.allclose(w, pts @ T[:3, :3].T + T[:3, 3], rtol=0, atol=1e-12)
+    cells = oracle.occupancy_cells(pts, [0, len(pts)], T[None])
+    r = np.hypot(w[:, 0] - T[0, 3], w[:, 1] - T[1, 3])
+    keep = (w[:, 2] >= 0.3) & (w[:, 2] <= 2.0) & (r <= 40.0) & (r >= 0.5)
+    ref = np.unique(np.floor(w[keep, :2] / 0.2).astype(np.int32), axis=0)
+    assert np.array_equal(cells, ref)
