@@ -188,12 +188,12 @@ static int upload_voxel_pipelined(Ctx* ctx, const void* h_raw, int f32, int stri
         SB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
         for (int i = 0; i < 2; ++i) SB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->copy_ev[i], cudaEventDisableTiming));
     }
-    // chunk boundaries: whole clouds, about 192 MB each (SB_CHUNK_MB): smaller chunks pay more per-chunk host
-    // round trips than they gain in overlap (measured: 24 MB 93 ms, 96 MB 64 ms, 192 MB 63 ms, 384 MB 66 ms per C2 step)
+    // chunk boundaries: whole clouds, about 384 MB each (SB_CHUNK_MB): smaller chunks pay more per-chunk host
+    // round trips than they gain in overlap (measured per C2 step from float32 records: 128 MB 57.9 ms, 256 MB 55.5 ms, 384 MB 54.4 ms, 512 MB 55.7 ms)
     std::vector<int> cb(1, 0);
     {
-        const long chunk_mb = getenv("SB_CHUNK_MB") ? atol(getenv("SB_CHUNK_MB")) : 192;
-        const i64 target_rows = (i64)(((size_t)(chunk_mb > 0 ? chunk_mb : 192) << 20) / row_bytes);
+        const long chunk_mb = getenv("SB_CHUNK_MB") ? atol(getenv("SB_CHUNK_MB")) : 384;
+        const i64 target_rows = (i64)(((size_t)(chunk_mb > 0 ? chunk_mb : 384) << 20) / row_bytes);
         i64 start = 0;
         for (int c = 0; c < n_clouds; ++c)
             if (offsets[c + 1] - start >= target_rows || c == n_clouds - 1) {

@@ -582,14 +582,24 @@ static int voxel_hashed_dev(Ctx* ctx, const PointSrc src, const i64* h_off, int 
     const int pgrid = (int)(n_tiles < (i64)ctx->sm_count * per_sm ? n_tiles : (i64)ctx->sm_count * per_sm);
     SB_LAUNCH(ctx, k_vox_insert, pgrid, 256, 0, src, d_clouds, d_tile_cloud, n_tiles, voxel, d_table, d_slot_of, d_nvox,
               d_mm, ctx->d_flags);
-    // ---- the only host round trip: flags, key range, voxels per cloud
+    // ---- the only host round trip: flags, key range, voxels per cloud (into pinned memory: a pageable target would
+    // make the driver stage the copies)
     std::vector<int> nvox((size_t)n_clouds);
     i64 mm[6];
     int flags = 0;
-    SB_CUDA(ctx, cudaMemcpyAsync(nvox.data(), d_nvox, sizeof(int) * n_clouds, cudaMemcpyDeviceToHost, ctx->stream));
-    SB_CUDA(ctx, cudaMemcpyAsync(mm, d_mm, sizeof(mm), cudaMemcpyDeviceToHost, ctx->stream));
-    SB_CUDA(ctx, cudaMemcpyAsync(&flags, ctx->d_flags, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    {
+        const size_t nv_bytes = sizeof(int) * (size_t)n_clouds;
+        SB_TRY(pinned_reserve(ctx, nv_bytes + sizeof(mm) + 64));
+        char* hp = ctx->pinned;
+        const size_t o_mm = (nv_bytes + 15) & ~(size_t)15, o_fl = o_mm + sizeof(mm);
+        SB_CUDA(ctx, cudaMemcpyAsync(hp, d_nvox, nv_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        SB_CUDA(ctx, cudaMemcpyAsync(hp + o_mm, d_mm, sizeof(mm), cudaMemcpyDeviceToHost, ctx->stream));
+        SB_CUDA(ctx, cudaMemcpyAsync(hp + o_fl, ctx->d_flags, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        memcpy(nvox.data(), hp, nv_bytes);
+        memcpy(mm, hp + o_mm, sizeof(mm));
+        memcpy(&flags, hp + o_fl, sizeof(int));
+    }
     if (flags & FLAG_NONFINITE) return fail(ctx, SB_ERR_RANGE, "voxel: non-finite coordinate or |coord/voxel| >= 4e18");
     if (flags & FLAG_TABLE_FULL) {  // more voxels per point than the tables were sized for: this call takes the
         ctx->vox_slots_per_point = 2.0;  // sort, the next one gets worst-case tables (one voxel per point)
@@ -629,8 +639,9 @@ static int voxel_hashed_dev(Ctx* ctx, const PointSrc src, const i64* h_off, int 
     SB_LAUNCH(ctx, k_vox_collect, pgrid, 256, 0, d_clouds, d_tile_cloud, n_tiles, d_slot_of, d_table, d_list, d_list_n,
               ctx->d_flags);
     SB_LAUNCH(ctx, k_vox_patch, 1, 1024, 0, src, d_list, d_list_n, d_out_xyz);
-    SB_CUDA(ctx, cudaMemcpyAsync(&flags, ctx->d_flags, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, ctx->d_flags, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    memcpy(&flags, ctx->pinned, sizeof(int));
     if (flags & FLAG_PATCH_OVERFLOW) return SB_OK;  // e.g. arbitrary fp64 input: the sort handles it
     *done = 1;
     return SB_OK;
