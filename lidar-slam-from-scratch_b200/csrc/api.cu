@@ -245,27 +245,37 @@ static int register_batch_impl(Ctx* ctx, PointSrc src, const void* h_raw, const 
             return fail(ctx, SB_ERR_INVALID_ARG, "register_batch: pair %d references a cloud outside [0, %d)", p, n_clouds);
     if (cfg->normals_k < 1 || cfg->normals_k > SB_MAX_K)
         return fail(ctx, SB_ERR_INVALID_ARG, "normals_k %d outside [1, %d]", cfg->normals_k, SB_MAX_K);
-    // one tree + normals per distinct target cloud (icp.hpp:166-171), numbered in cloud order
+    // one tree + normals per distinct target cloud (icp.hpp:166-171); clouds that are only sources get a tree too
+    // (no normals): the ICP passes read every source in its own Morton order (PairDesc::src_pts)
+    std::vector<char> is_tgt((size_t)n_clouds, 0), is_src((size_t)n_clouds, 0);
+    for (int p = 0; p < n_pairs; ++p) { is_tgt[pair_tgt[p]] = 1; is_src[pair_src[p]] = 1; }
     std::vector<int> tree_of((size_t)n_clouds, -1);
-    int n_targets = 0;
-    for (int p = 0; p < n_pairs; ++p) tree_of[pair_tgt[p]] = 0;
-    for (int c = 0; c < n_clouds; ++c)
-        if (tree_of[c] == 0) tree_of[c] = n_targets++;
+    int n_index = 0;
+    for (int c = 0; c < n_clouds; ++c) n_index += (is_tgt[c] || is_src[c]) ? 1 : 0;
     Forest F;
     F.in_arena = true;
-    SB_TRY(forest_reserve(ctx, &F, n_targets));
+    SB_TRY(forest_reserve(ctx, &F, n_index));
     std::vector<i64> off(offsets, offsets + n_clouds + 1);
     const double* d_pts = nullptr;
-    // index + normals of the target clouds in [c0, c1) (their downsampled rows are final)
+    // index (+ normals for targets) of the clouds in [c0, c1) (their downsampled rows are final)
     auto index_clouds = [&](int c0, int c1) -> int {
-        std::vector<int> ids;
-        for (int c = c0; c < c1; ++c)
-            if (tree_of[c] >= 0) ids.push_back(c);
-        if (ids.empty()) return SB_OK;
-        stage_mark(ctx, STAGE_INDEX);
-        SB_TRY(forest_append(ctx, &F, d_pts, off.data(), ids.data(), (int)ids.size()));
-        stage_mark(ctx, STAGE_NORMALS);
-        return forest_normals(ctx, &F, cfg->normals_k, nullptr, nullptr);
+        std::vector<int> ids_t, ids_s;
+        for (int c = c0; c < c1; ++c) {
+            if (is_tgt[c]) ids_t.push_back(c);
+            else if (is_src[c]) ids_s.push_back(c);
+        }
+        if (!ids_t.empty()) {
+            if (!h_raw) stage_mark(ctx, STAGE_INDEX);
+            for (size_t i = 0; i < ids_t.size(); ++i) tree_of[ids_t[i]] = F.n_trees + (int)i;
+            SB_TRY(forest_append(ctx, &F, d_pts, off.data(), ids_t.data(), (int)ids_t.size()));
+            if (!h_raw) stage_mark(ctx, STAGE_NORMALS);
+            SB_TRY(forest_normals(ctx, &F, cfg->normals_k, nullptr, nullptr));
+        }
+        if (!ids_s.empty()) {
+            for (size_t i = 0; i < ids_s.size(); ++i) tree_of[ids_s[i]] = F.n_trees + (int)i;
+            SB_TRY(forest_append(ctx, &F, d_pts, off.data(), ids_s.data(), (int)ids_s.size()));
+        }
+        return SB_OK;
     };
     // 1. voxel grid (slam_node.cpp:122)
     stage_mark(ctx, STAGE_VOXEL);
@@ -331,13 +341,12 @@ static int register_batch_impl(Ctx* ctx, PointSrc src, const void* h_raw, const 
     if (s == SB_OK) {
         std::vector<PairDesc> pairs((size_t)n_pairs);
         for (int p = 0; p < n_pairs; ++p) {
-            int c = pair_src[p];
-            pairs[p].src_off = off[c];
-            pairs[p].n_src = (int)(off[c + 1] - off[c]);
+            memset(&pairs[p], 0, sizeof(PairDesc));
             pairs[p].tree = tree_of[pair_tgt[p]];
-            pairs[p].item_off = 0; pairs[p].n_items = 0; pairs[p].pad = 0;
+            pairs[p].src_tree = tree_of[pair_src[p]];
+            pairs[p].n_src = (int)(off[pair_src[p] + 1] - off[pair_src[p]]);
         }
-        s = icp_batch(ctx, &F, d_pts, pairs, cfg, results);
+        s = icp_batch(ctx, &F, pairs, cfg, results);
         if (s == SB_OK) {
             i64 q = 0;
             for (int p = 0; p < n_pairs; ++p) q += (i64)pairs[p].n_src * results[p].history_len;

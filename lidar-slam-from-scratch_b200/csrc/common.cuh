@@ -301,17 +301,20 @@ int make_items_dev(Ctx* ctx, const std::vector<QueryItem>& items, QueryItem** d_
 // icp.cu
 // ---------------------------------------------------------------------------------------------------------------
 struct PairDesc {      // device-resident, one per scan pair
-    i64 src_off;       // first source row in d_src
+    const TreePoint* src_pts;  // the source cloud in ITS OWN Morton order (it is indexed too: forest tree src_tree):
+                               // neighbouring lanes then work on neighbouring points, and the order — hence the
+                               // summation order — does not depend on what else is in the batch
     int n_src;
-    int tree;          // target tree id in the forest
-    i64 item_off;      // first 64-query work item of this pair
+    int tree;          // target tree id in the forest (needs normals)
+    i64 item_off;      // first 32-point work item of this pair
     int n_items;
-    int pad;
+    int src_tree;      // source tree id in the forest (no normals needed)
 };
 
-// Registers n_pairs pairs; d_src rows fp64.  results: host array.
-int icp_batch(Ctx* ctx, const Forest* f, const double* d_src, const std::vector<PairDesc>& pairs,
-              const sb_icp_config* cfg, sb_icp_result* results);
+// Registers n_pairs pairs of trees of the forest (PairDesc::tree / src_tree; src_pts, item_off and n_items are filled
+// in here).  results: host array.
+int icp_batch(Ctx* ctx, const Forest* f, const std::vector<PairDesc>& pairs, const sb_icp_config* cfg,
+              sb_icp_result* results);
 void icp_graph_free(Ctx* ctx);
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -38,7 +38,6 @@ struct FallbackEntry {   // a source point whose walk did not end with a proof
 
 struct IcpJob {
     ForestView F;
-    const double* src;          // source rows, fp64 xyz
     int* match;                 // n_items x ITEM_Q: correspondence of every source point (seed of the next pass)
     i64 n_items;
     const PairDesc* pairs;
@@ -249,7 +248,7 @@ __global__ void __launch_bounds__(IWARPS * 32) k_icp_match(IcpJob* __restrict__ 
         bool cert = false;
         double cx = 0, cy = 0, cz = 0;
         if (lane < count) {
-            transform_point(Tm, job->src + 3 * (P.src_off + s0 + lane), cx, cy, cz);
+            transform_point(Tm, reinterpret_cast<const double*>(P.src_pts + s0 + lane), cx, cy, cz);
             int center = job->match[it * ITEM_Q + lane];  // -1 before the first pass
             if (center < 0 || center >= T.n) center = grid_seed(T, cx, cy, cz);
             if (center >= 0) {
@@ -348,8 +347,8 @@ __global__ void __launch_bounds__(IWARPS * 32) k_icp_fallback(IcpJob* __restrict
         }
         const TreeDesc& T = s_tree[warp];
         double qx, qy, qz;
-        transform_point(job->results[pair].transformation, job->src + 3 * (P.src_off + (E.q - P.item_off * ITEM_Q)), qx,
-                        qy, qz);
+        transform_point(job->results[pair].transformation,
+                        reinterpret_cast<const double*>(P.src_pts + (E.q - P.item_off * ITEM_Q)), qx, qy, qz);
         NearestVisitor V(F, T, qx, qy, qz, lane);
         V.seed(E.seed);
         traverse(F, T, qx, qy, qz, S, V, lane);
@@ -428,7 +427,7 @@ __global__ void __launch_bounds__(IWARPS * 32) k_icp_accum(const IcpJob* __restr
         if (lane < count) {
             my_pos = job->match[it * ITEM_Q + lane];
             if (my_pos >= 0)
-                transform_point(job->results[pair].transformation, job->src + 3 * (P.src_off + s0 + lane), cx, cy, cz);
+                transform_point(job->results[pair].transformation, reinterpret_cast<const double*>(P.src_pts + s0 + lane), cx, cy, cz);
         }
         accumulate_item(job, T, it, lane, my_pos, cx, cy, cz);
     }
@@ -819,17 +818,14 @@ static int icp_graph_get(Ctx* ctx, IcpGraph** out) {
     return SB_OK;
 }
 
-int icp_batch(Ctx* ctx, const Forest* f, const double* d_src, const std::vector<PairDesc>& pairs_in,
-              const sb_icp_config* cfg, sb_icp_result* results) {
+int icp_batch(Ctx* ctx, const Forest* f, const std::vector<PairDesc>& pairs_in, const sb_icp_config* cfg,
+              sb_icp_result* results) {
     const int n_pairs = (int)pairs_in.size();
     if (n_pairs == 0) return SB_OK;
     if (cfg->max_iterations < 0 || cfg->max_iterations > SB_MAX_ICP_ITERATIONS)
         return fail(ctx, SB_ERR_INVALID_ARG, "icp: max_iterations %d outside [0, %d]", cfg->max_iterations,
                     SB_MAX_ICP_ITERATIONS);
     if (f->normals_k <= 0) return fail(ctx, SB_ERR_INVALID_ARG, "icp: forest has no normals");
-    for (const ForestBatch& B : f->batches)
-        if (B.n_points > 0 && (!B.normals || !B.nbr || !B.grid))
-            return fail(ctx, SB_ERR_INVALID_ARG, "icp: a batch of the forest has no normals");
     IcpGraph* G;
     SB_TRY(icp_graph_get(ctx, &G));
     std::vector<PairDesc> pairs(pairs_in);
@@ -837,6 +833,14 @@ int icp_batch(Ctx* ctx, const Forest* f, const double* d_src, const std::vector<
     i64 n_items = 0;
     for (int p = 0; p < n_pairs; ++p) {
         PairDesc& P = pairs[p];
+        if (P.tree < 0 || P.tree >= f->n_trees || P.src_tree < 0 || P.src_tree >= f->n_trees)
+            return fail(ctx, SB_ERR_INVALID_ARG, "icp: pair %d names a tree outside the forest", p);
+        const TreeDesc& Tt = f->h_trees[(size_t)P.tree];
+        const TreeDesc& Ts = f->h_trees[(size_t)P.src_tree];
+        if (Tt.n > 0 && (!Tt.nrm || !Tt.nbr || !Tt.grid))
+            return fail(ctx, SB_ERR_INVALID_ARG, "icp: target tree %d has no normals", P.tree);
+        P.src_pts = Ts.pts + Ts.pt_off;
+        P.n_src = Ts.n;
         P.item_off = n_items;
         P.n_items = P.n_src > 0 ? (P.n_src + ITEM_Q - 1) / ITEM_Q : 0;
         n_items += P.n_items;
@@ -869,7 +873,6 @@ int icp_batch(Ctx* ctx, const Forest* f, const double* d_src, const std::vector<
     job.F.trees = f->d_trees;
     job.nbr_k = f->normals_k;
     job.stats = G->d_stats;
-    job.src = d_src;
     job.match = d_match;
     job.n_items = n_items;
     job.pairs = d_pairs;

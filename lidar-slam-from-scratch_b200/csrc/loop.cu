@@ -106,8 +106,10 @@ int loop_verify(sb_loop* L, const int* entries, const double* dist, int n, sb_lo
     }
     Forest F;
     F.in_arena = true;
-    int s = forest_build(ctx, L->d_clouds, L->cloud_off.data(), slots.data(), n, &F);
+    int s = forest_reserve(ctx, &F, n + 1);
+    if (s == SB_OK) s = forest_append(ctx, &F, L->d_clouds, L->cloud_off.data(), slots.data(), n);   // candidates
     if (s == SB_OK) s = forest_normals(ctx, &F, L->cfg.normals_k, nullptr, nullptr);
+    if (s == SB_OK) s = forest_append(ctx, &F, L->d_clouds, L->cloud_off.data(), &qslot, 1);         // the query
     std::vector<sb_icp_result> res((size_t)n);
     if (s == SB_OK) {
         sb_icp_config cfg;
@@ -117,12 +119,12 @@ int loop_verify(sb_loop* L, const int* entries, const double* dist, int n, sb_lo
         cfg.normals_k = L->cfg.normals_k;
         std::vector<PairDesc> pairs((size_t)n);
         for (int i = 0; i < n; ++i) {
-            pairs[i].src_off = L->cloud_off[qslot];  // source = query cloud (loop_closure.hpp:102)
+            memset(&pairs[i], 0, sizeof(PairDesc));
+            pairs[i].src_tree = n;                   // source = query cloud (loop_closure.hpp:102)
             pairs[i].n_src = (int)(L->cloud_off[qslot + 1] - L->cloud_off[qslot]);
             pairs[i].tree = i;                       // target = candidate cloud (loop_closure.hpp:103)
-            pairs[i].item_off = 0; pairs[i].n_items = 0; pairs[i].pad = 0;
         }
-        s = icp_batch(ctx, &F, L->d_clouds, pairs, &cfg, res.data());
+        s = icp_batch(ctx, &F, pairs, &cfg, res.data());
     }
     cudaStreamSynchronize(ctx->stream);
     forest_free(&F);
