@@ -352,6 +352,26 @@ def test_chunked_upload_and_batch_composition_independence(engine, synth, scene,
         assert one[0].num_iterations == ref[p].num_iterations
 
 
+def test_register_batch_odd_pair_lists(engine, oracle, synth, scene):
+    """Pair lists the odometry chain never produces: a cloud registered onto itself, a cloud that is only a source,
+    one that is only a target, one that is in no pair, an empty cloud in the batch, and no pairs at all."""
+    s = oracle_lib.small_sensor(32, 600)
+    raws = [synth.scan(s, scene, (0.5 * i, 0.0, 0.01 * i), 90 + i) for i in range(4)]
+    clouds = [raws[0], raws[1], np.zeros((0, 3)), raws[2], raws[3]]
+    off = np.r_[0, np.cumsum([len(c) for c in clouds])]
+    allpts = np.vstack(clouds)
+    src, tgt = [0, 1, 3, 2], [0, 0, 1, 1]   # 0 onto itself; 1 is source and target; 3 only source; 4 unused; 2 is empty
+    res, sc = engine.register_batch(allpts, off, src, tgt, voxel=0.5, want_sc=True)
+    ds = [oracle.voxel_downsample(c, 0.5)[0] if len(c) else np.zeros((0, 3)) for c in clouds]
+    assert np.allclose(res[0].transformation, np.eye(4), atol=1e-12) and res[0].final_error < 1e-12
+    check_icp(res[1], oracle.icp_point_to_plane(ds[1], ds[0]))
+    check_icp(res[2], oracle.icp_point_to_plane(ds[3], ds[1]))
+    assert res[3].status == 2 and res[0].status == 0            # empty source: SB_ERR_EMPTY for that pair only
+    assert np.array_equal(sc[2], np.zeros(1200)) and np.array_equal(sc[4], oracle.sc_compute(ds[4]))
+    none, sc2 = engine.register_batch(allpts, off, [], [], voxel=0.5, want_sc=True)
+    assert len(none) == 0 and np.array_equal(sc2, sc)
+
+
 def test_icp_is_deterministic(engine, small_pair):
     r1 = engine.icp_point_to_plane(small_pair["b"], small_pair["a"])
     r2 = engine.icp_point_to_plane(small_pair["b"], small_pair["a"])
