@@ -174,6 +174,14 @@ static std::vector<QueryItem> items_for(i64 nq) {
     return items;
 }
 
+int ensure_copy_stream(Ctx* ctx) {
+    if (!ctx->copy_stream) {
+        SB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) SB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->copy_ev[i], cudaEventDisableTiming));
+    }
+    return SB_OK;
+}
+
 // Host clouds -> device, voxel grid.  The raw rows are copied in chunks of whole clouds on a second stream and the
 // voxel grid of chunk c runs while chunk c+1 is in flight (pinned host memory; pageable memory still works, without
 // the overlap).  d_ds receives the downsampled rows of all clouds, off_ds their CSR offsets.
@@ -184,10 +192,7 @@ static int upload_voxel_pipelined(Ctx* ctx, const void* h_raw, int f32, int stri
     const i64 n = offsets[n_clouds];
     char* d_raw;
     SB_TRY(arena_get(ctx, (size_t)(n > 0 ? n : 1) * row_bytes, &d_raw));
-    if (!ctx->copy_stream) {
-        SB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; ++i) SB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->copy_ev[i], cudaEventDisableTiming));
-    }
+    SB_TRY(ensure_copy_stream(ctx));
     // chunk boundaries: whole clouds, about 384 MB each (SB_CHUNK_MB): smaller chunks pay more per-chunk host
     // round trips than they gain in overlap (measured per C2 step from float32 records: 128 MB 57.9 ms, 256 MB 55.5 ms, 384 MB 54.4 ms, 512 MB 55.7 ms)
     std::vector<int> cb(1, 0);
@@ -318,15 +323,27 @@ static int register_batch_impl(Ctx* ctx, PointSrc src, const void* h_raw, const 
     stage_mark(ctx, STAGE_SC);
     ctx->last_counts[0] = n_raw;
     ctx->last_counts[1] = off[n_clouds];
+    double* d_desc = nullptr;
+    // the descriptors go back to the host on the copy stream while the ICP loop runs (or right away without pairs)
+    std::function<int()> fetch_sc = [&]() -> int {
+        if (!sc_desc) return SB_OK;
+        SB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_ev[0], 0));
+        SB_CUDA(ctx, cudaMemcpyAsync(sc_desc, d_desc, sizeof(double) * SB_SC_SIZE * n_clouds, cudaMemcpyDeviceToHost,
+                                     ctx->copy_stream));
+        SB_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+        return SB_OK;
+    };
     if (sc_desc) {
         i64* d_off;
-        double* d_desc;
-        SB_TRY(upload(ctx, off.data(), sizeof(i64) * (n_clouds + 1), (void**)&d_off));
+        SB_TRY(ensure_copy_stream(ctx));
+        SB_TRY(arena_get(ctx, (size_t)n_clouds + 1, &d_off));
+        SB_TRY(table_upload(ctx, d_off, off.data(), sizeof(i64) * (n_clouds + 1)));
         SB_TRY(arena_get(ctx, (size_t)n_clouds * SB_SC_SIZE, &d_desc));
         SB_TRY(sc_compute_dev(ctx, d_pts, d_off, n_clouds, d_desc));
-        SB_TRY(download(ctx, sc_desc, d_desc, sizeof(double) * SB_SC_SIZE * n_clouds));
+        SB_CUDA(ctx, cudaEventRecord(ctx->copy_ev[0], ctx->stream));  // the upload pipeline is done with its events
     }
     if (n_pairs == 0) {
+        SB_TRY(fetch_sc());
         stage_mark(ctx, STAGE_END);
         SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         forest_free(&F);
@@ -346,7 +363,7 @@ static int register_batch_impl(Ctx* ctx, PointSrc src, const void* h_raw, const 
             pairs[p].src_tree = tree_of[pair_src[p]];
             pairs[p].n_src = (int)(off[pair_src[p] + 1] - off[pair_src[p]]);
         }
-        s = icp_batch(ctx, &F, pairs, cfg, results);
+        s = icp_batch(ctx, &F, pairs, cfg, results, &fetch_sc);
         if (s == SB_OK) {
             i64 q = 0;
             for (int p = 0; p < n_pairs; ++p) q += (i64)pairs[p].n_src * results[p].history_len;

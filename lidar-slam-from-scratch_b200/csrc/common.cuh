@@ -9,6 +9,7 @@
 
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <string>
 #include <utility>
 #include <vector>
@@ -313,8 +314,11 @@ struct PairDesc {      // device-resident, one per scan pair
 
 // Registers n_pairs pairs of trees of the forest (PairDesc::tree / src_tree; src_pts, item_off and n_items are filled
 // in here).  results: host array.
+// after_launch (optional) runs on the host right after the loop has been enqueued: host work or copies on another
+// stream placed there overlap with the iterations.
 int icp_batch(Ctx* ctx, const Forest* f, const std::vector<PairDesc>& pairs, const sb_icp_config* cfg,
-              sb_icp_result* results);
+              sb_icp_result* results, const std::function<int()>* after_launch = nullptr);
+int ensure_copy_stream(Ctx* ctx);
 void icp_graph_free(Ctx* ctx);
 
 // ---------------------------------------------------------------------------------------------------------------

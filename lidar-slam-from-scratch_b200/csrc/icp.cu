@@ -819,7 +819,7 @@ static int icp_graph_get(Ctx* ctx, IcpGraph** out) {
 }
 
 int icp_batch(Ctx* ctx, const Forest* f, const std::vector<PairDesc>& pairs_in, const sb_icp_config* cfg,
-              sb_icp_result* results) {
+              sb_icp_result* results, const std::function<int()>* after_launch) {
     const int n_pairs = (int)pairs_in.size();
     if (n_pairs == 0) return SB_OK;
     if (cfg->max_iterations < 0 || cfg->max_iterations > SB_MAX_ICP_ITERATIONS)
@@ -914,6 +914,7 @@ int icp_batch(Ctx* ctx, const Forest* f, const std::vector<PairDesc>& pairs_in, 
         SB_LAUNCH(ctx, k_icp_accum, G->iter_grid, IWARPS * 32, 0, G->d_job);
         SB_LAUNCH(ctx, k_icp_solve, G->solve_grid, 256, 0, G->d_job, 1, none, 0);
     }
+    if (after_launch && *after_launch) SB_TRY((*after_launch)());
     SB_CUDA(ctx, cudaMemcpyAsync(results, d_res, sizeof(sb_icp_result) * n_pairs, cudaMemcpyDeviceToHost, ctx->stream));
     SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     int max_hist = 1;
