@@ -190,14 +190,25 @@ def main():
             return res, sc
 
         gathered = None
+        # exchange buffers of the sharded path: one 160-byte record per pair and rank, gathered on every rank
+        if world_size > 1:
+            g_host = torch.empty((F, 20), dtype=torch.float64, pin_memory=True)
+            g_dev = torch.empty((F, 20), dtype=torch.float64, device="cuda")
+            g_all = torch.empty((world_size * F, 20), dtype=torch.float64, device="cuda")
+        g_work = [None]
 
         def gather(res):
+            """NCCL all-gather of the result records: the only exchange of the sharded path.  It is
+            queued behind the step on the engine's stream and overlaps the next step; the closing barrier +
+            synchronize waits for the last one, so every step's records have arrived inside the timed region."""
             if world_size == 1:
                 return
-            t = torch.from_numpy(res.records20()).cuda()
-            out = [torch.empty_like(t) for _ in range(world_size)]
-            dist.all_gather(out, t)  # NCCL: the only exchange of the sharded path
-            return out
+            if g_work[0] is not None:
+                g_work[0].wait()   # stream-level wait: the previous gather must have read g_dev before it is rewritten
+            g_host.numpy()[...] = res.records20()
+            g_dev.copy_(g_host, non_blocking=True)
+            g_work[0] = dist.all_gather_into_tensor(g_all, g_dev, async_op=True)
+            return g_all
 
         def barrier():
             if world_size > 1:
@@ -212,7 +223,8 @@ def main():
         eng.set_profiling(True)
         sampler = ClockSampler(local_rank)
         barrier()
-        sampler.start()
+        if rank == 0:  # one sampler per node: nvidia-smi from every rank perturbs the run it is meant to watch
+            sampler.start()
         l0 = eng.launch_count
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         stage_acc, host_acc = {}, {}
@@ -228,6 +240,8 @@ def main():
         barrier()
         clocks = sampler.stop()
         launches = eng.launch_count - l0
+        if gathered is not None:  # the exchange really delivered this rank's records
+            assert np.array_equal(gathered[rank * F:(rank + 1) * F].cpu().numpy(), res.records20())
         ms = e0.elapsed_time(e1) / args.steps
         counts = eng.last_counts()
         eng.set_profiling(False)
@@ -236,6 +250,15 @@ def main():
             dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
         ms_max = float(t_ms.item())
         value = world_size * F / (ms_max * 1e-3)
+        # per-rank view: own elapsed time and device-busy time (sum of the stage events) -- tells a slow GPU
+        # (busy grows) from host-side gaps or waiting in the gather (busy flat, elapsed grows)
+        per_rank = None
+        if world_size > 1:
+            mine = torch.tensor([ms, sum(stage_acc.values()) / args.steps], device="cuda", dtype=torch.float64)
+            allr = [torch.empty_like(mine) for _ in range(world_size)]
+            dist.all_gather(allr, mine)
+            per_rank = {"step_ms": [round(float(a[0]), 2) for a in allr],
+                        "device_busy_ms": [round(float(a[1]), 2) for a in allr]}
 
         # ---- e2e: host (pinned) scans through the public entry points, H2D + D2H inside the timed region.
         # "e2e" takes the scans the way the reference's loader gets them from disk: float32 x, y, z records
@@ -403,7 +426,7 @@ def main():
             "metric": "ICP scan-pairs/s", "value": value, "unit": "pairs/s", "n_gpus": world_size, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_max, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(F),
-            "ms_per_frame": ms_max / F, "clocks": clocks, "e2e": e2e, "e2e_f64": e2e_f64, "gpu_launches": int(launches),
+            "ms_per_frame": ms_max / F, "clocks": clocks, "e2e": e2e, "e2e_f64": e2e_f64, "gpu_launches": int(launches), "per_rank": per_rank,
             "roofline": roofline, "cpu_baseline": cpu_baseline, "extras": extras,
             "workload_stats": {"raw_points_per_scan": n_raw / (F + 1), "voxel_points_per_scan": M / (F + 1),
                                "icp_iterations_mean": float(iters.mean()), "icp_iterations_max": int(iters.max()),
