@@ -418,6 +418,13 @@ def main():
                 "ms_per_query": dt4 * 1e3, "descriptor_pairs_per_s": 4000 / dt4,
                 "db_bytes": 4000 * 9600, "gflops_fp64": 2 * 60 * 1200 * 4000 / dt4 / 1e9}
             det.close()
+            # C2 as the reference runs it: one frame per call (SURVEY.md 8d "ms/frame odometry")
+            sys.path.insert(0, os.path.join(ROOT, "scripts"))
+            import stream_latency
+            n_s = min(F, 150) + 1
+            h_s = d_raw[:int(off[n_s]) * 3].cpu().numpy().reshape(-1, 3)
+            scans_s = [np.ascontiguousarray(h_s[off[i]:off[i + 1]]) for i in range(n_s)]
+            extras["c2_streaming"] = stream_latency.process_frames(eng, slam_b200, scans_s, VOXEL)
         except Exception as ex:  # the headline line must still be printed
             extras["error"] = repr(ex)
 

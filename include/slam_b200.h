@@ -200,6 +200,9 @@ int sb_sc_keys(sb_ctx* ctx, const double* desc, double* ring_key20, double* sect
  * part of the candidate list; the caller gathers (NCCL) and passes the merged list to sb_loop_verify. */
 int sb_loop_create(sb_ctx* ctx, const sb_loop_config* cfg, int32_t rank, int32_t world, sb_loop** out);
 void sb_loop_free(sb_loop* loop);
+/* Optional: size the device pools for n_entries descriptors and total_rows cloud rows (what this rank will own) so
+ * that no later addFrame allocates.  Without it the pools start at 4096 descriptors / 11 M rows and double. */
+int sb_loop_reserve(sb_loop* loop, int64_t n_entries, int64_t total_rows);
 int sb_loop_add_frame(sb_loop* loop, const double* xyz, int64_t n, int32_t frame_idx);      /* addFrame, :53-59  */
 /* Adds a frame whose Scan Context is already known (database bulk load; the cloud is still copied). */
 int sb_loop_add_frame_desc(sb_loop* loop, const double* xyz, int64_t n, int32_t frame_idx, const double* desc);

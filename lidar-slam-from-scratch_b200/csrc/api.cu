@@ -33,11 +33,17 @@ int arena_reset(Ctx* ctx) {
         for (void* p : A.overflow) cudaFree(p);
         A.overflow.clear();
     }
-    if (A.high > A.cap) {  // regrow the slab to the high-water mark (+25 %)
+    if (A.high > A.cap) {
+        // regrow the slab to the high-water mark (+25 %), never below 64 MB and at least doubling while it is small:
+        // cudaMalloc / cudaFree cost up to hundreds of ms on this pool, a streaming caller whose frames vary by a few
+        // per cent must stop reaching them after the first frames
         cudaStreamSynchronize(ctx->stream);
         cudaFree(A.base);
         A.base = nullptr;
         size_t ncap = A.high + A.high / 4 + (1u << 20);
+        const size_t floor_cap = (size_t)64 << 20, dbl = A.cap < ((size_t)1 << 30) ? 2 * A.cap : 0;
+        if (ncap < floor_cap) ncap = floor_cap;
+        if (ncap < dbl) ncap = dbl;
         if (cudaMalloc(&A.base, ncap) != cudaSuccess) {
             cudaGetLastError();
             A.cap = 0;
@@ -864,7 +870,14 @@ void sb_loop_free(sb_loop* loop) {
     cudaStreamSynchronize(loop->ctx->stream);
     cudaFree(loop->d_desc);
     cudaFree(loop->d_clouds);
+    for (double* p : loop->retired) cudaFree(p);
     delete loop;
+}
+
+int sb_loop_reserve(sb_loop* loop, int64_t n_entries, int64_t total_rows) {
+    if (!loop || n_entries < 0 || total_rows < 0) return SB_ERR_INVALID_ARG;
+    Enter g(loop->ctx);
+    return loop_reserve(loop, n_entries, total_rows);
 }
 
 int sb_loop_add_frame_desc(sb_loop* loop, const double* xyz, int64_t n, int32_t frame_idx, const double* desc) {

@@ -364,10 +364,12 @@ struct sb_loop {
     size_t desc_cap = 0;             // in descriptors
     double* d_clouds = nullptr;      // rows x 3
     size_t cloud_cap = 0;            // in rows
+    std::vector<double*> retired;    // outgrown pools, released with the detector (loop.cu: grow)
 };
 
 namespace sb {
 int loop_add(sb_loop* L, const double* xyz, i64 n, int frame_idx, const double* desc);
+int loop_reserve(sb_loop* L, i64 n_entries, i64 total_rows);
 int loop_candidates(sb_loop* L, std::vector<std::pair<double, int>>& cand);
 int loop_verify(sb_loop* L, const int* entries, const double* dist, int n, sb_loop_result* results, int* converged);
 }  // namespace sb

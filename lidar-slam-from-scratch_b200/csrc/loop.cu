@@ -13,17 +13,34 @@
 
 namespace sb {
 
-static int grow(Ctx* ctx, double** buf, size_t* cap, size_t need, size_t used, size_t unit) {
+// Pools only ever grow, by doubling, and the outgrown buffer is retired (freed with the detector) rather than
+// released: cudaMalloc / cudaFree stall the calling thread for up to hundreds of milliseconds (measured on the B200
+// pool: 100 ms / 580 ms worst case) while a frame takes 1.7 ms, so the streaming path must not reach them in steady
+// state.  The first allocation holds ~1300 voxel-downsampled scans / 4096 descriptors; sb_loop_reserve sizes the
+// pools for a known sequence length up front.
+static const size_t FIRST_CLOUD_ROWS = (size_t)11 << 20;   // 264 MB of fp64 xyz rows
+static const size_t FIRST_DESC_SLOTS = 4096;               // 39 MB
+
+static int grow(sb_loop* L, double** buf, size_t* cap, size_t need, size_t used, size_t unit, size_t first) {
     if (need <= *cap) return SB_OK;
-    size_t ncap = *cap ? *cap : 256;
+    Ctx* ctx = L->ctx;
+    size_t ncap = *cap ? *cap : first;
     while (ncap < need) ncap *= 2;
     double* nb;
     SB_CUDA(ctx, cudaMalloc(&nb, ncap * unit * sizeof(double)));
     if (used) SB_CUDA(ctx, cudaMemcpyAsync(nb, *buf, used * unit * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-    SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaFree(*buf);
+    if (*buf) L->retired.push_back(*buf);
     *buf = nb;
     *cap = ncap;
+    return SB_OK;
+}
+
+int loop_reserve(sb_loop* L, i64 n_entries, i64 total_rows) {
+    size_t slots = L->entry_id.size();
+    i64 rows = L->cloud_off.empty() ? 0 : L->cloud_off.back();
+    if (n_entries > 0) SB_TRY(grow(L, &L->d_desc, &L->desc_cap, (size_t)n_entries, slots, SB_SC_SIZE, (size_t)n_entries));
+    if (total_rows > 0) SB_TRY(grow(L, &L->d_clouds, &L->cloud_cap, (size_t)total_rows, (size_t)rows, 3, (size_t)total_rows));
+    SB_CUDA(L->ctx, cudaStreamSynchronize(L->ctx->stream));
     return SB_OK;
 }
 
@@ -40,8 +57,8 @@ int loop_add(sb_loop* L, const double* xyz, i64 n, int frame_idx, const double* 
     size_t slots = L->entry_id.size();
     i64 rows = L->cloud_off.empty() ? 0 : L->cloud_off.back();
     if (L->cloud_off.empty()) L->cloud_off.push_back(0);
-    SB_TRY(grow(ctx, &L->d_desc, &L->desc_cap, slots + 1, slots, SB_SC_SIZE));
-    SB_TRY(grow(ctx, &L->d_clouds, &L->cloud_cap, (size_t)(rows + n), (size_t)rows, 3));
+    SB_TRY(grow(L, &L->d_desc, &L->desc_cap, slots + 1, slots, SB_SC_SIZE, FIRST_DESC_SLOTS));
+    SB_TRY(grow(L, &L->d_clouds, &L->cloud_cap, (size_t)(rows + n), (size_t)rows, 3, FIRST_CLOUD_ROWS));
     if (n > 0)
         SB_CUDA(ctx, cudaMemcpyAsync(L->d_clouds + 3 * rows, xyz, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, ctx->stream));
     double* d_slot = L->d_desc + slots * SB_SC_SIZE;

@@ -62,6 +62,10 @@ public:
 
     size_t size() const { return (size_t)sb_loop_size(loop_.get()); }                // loop_closure.hpp:131
     void clear() { b200::check(sb_loop_clear(loop_.get()), "clear"); }               // loop_closure.hpp:136-141
+    // extension: size the device pools for a known sequence (frames, total downsampled rows) before streaming
+    void reserve(size_t frames, size_t total_rows) {
+        b200::check(sb_loop_reserve(loop_.get(), (int64_t)frames, (int64_t)total_rows), "reserve");
+    }
 
 private:
     LoopClosureConfig config_;

@@ -105,6 +105,7 @@ SYMBOLS = {
     "sb_sc_keys": (C.c_int, [_P, _D, _D, _D]),
     "sb_loop_create": (C.c_int, [_P, C.POINTER(LoopConfigC), C.c_int32, C.c_int32, C.POINTER(_P)]),
     "sb_loop_free": (None, [_P]),
+    "sb_loop_reserve": (C.c_int, [_P, C.c_int64, C.c_int64]),
     "sb_loop_add_frame": (C.c_int, [_P, _D, C.c_int64, C.c_int32]),
     "sb_loop_add_frame_desc": (C.c_int, [_P, _D, C.c_int64, C.c_int32, _D]),
     "sb_loop_size": (C.c_int64, [_P]),
@@ -564,6 +565,10 @@ class LoopClosureDetector:
         else:
             d = _f64(desc).reshape(-1)
             self.e._check(self.e.lib.sb_loop_add_frame_desc(self.h, _dp(p), p.shape[0], frame_idx, _dp(d)))
+
+    def reserve(self, n_entries, total_rows):
+        """Size the device pools up front (no counterpart in the reference: its std::vectors grow on the host)."""
+        self.e._check(self.e.lib.sb_loop_reserve(self.h, int(n_entries), int(total_rows)))
 
     def size(self):
         return int(self.e.lib.sb_loop_size(self.h))

@@ -487,6 +487,29 @@ def test_loop_sharded_candidates_merge(engine, oracle, synth, scene):
         assert conv[0] == rconv[j] and np.array_equal(res[0]["transform"], ref[j]["transform"])
 
 
+def test_loop_pools_grow_without_changing_results(engine, oracle, synth, scene):
+    """A detector whose pools were reserved far too small outgrows them several times (copy into the doubled pool,
+    old pool retired); candidates and verified loops must equal those of a detector with the default pools."""
+    import slam_b200
+    s = oracle_lib.small_sensor(16, 360)
+    small = slam_b200.LoopClosureDetector(engine, frame_gap=2, sc_distance_threshold=0.6, icp_fitness_threshold=0.5)
+    small.reserve(1, 64)
+    big = slam_b200.LoopClosureDetector(engine, frame_gap=2, sc_distance_threshold=0.6, icp_fitness_threshold=0.5)
+    for i in range(12):
+        c = oracle.voxel_downsample(synth.scan(s, scene, (1.5 * (i % 4), 0.0, 0.0), 80 + i), 0.5)[0]
+        small.addFrame(c, i)
+        big.addFrame(c, i)
+        if i >= 3:
+            ds, es = small.candidates_local()
+            db, eb = big.candidates_local()
+            assert np.array_equal(es, eb) and np.array_equal(ds, db)
+    gs, gb = small.detect(), big.detect()
+    assert len(gs) == len(gb) and len(gb) > 0
+    for a, b in zip(gs, gb):
+        assert a["match_frame"] == b["match_frame"] and np.array_equal(a["transform"], b["transform"])
+    assert small.size() == big.size() == 12
+
+
 # ------------------------------------------------------------------ committed golden fixtures (independent numpy)
 def test_golden_fixtures_gpu(engine):
     import slam_b200
