@@ -559,3 +559,56 @@ def test_world_frame_occupancy_and_global_map(engine, oracle, synth, scene):
     assert np.array_equal(gm, ref_gm)
     assert np.array_equal(engine.global_map(allpts, off, Ts, 0.0), ref_world)
     assert engine.occupancy_cells(np.zeros((0, 3)), [0], np.zeros((0, 16)))[1] == 0
+
+
+# ------------------------------------------------------------------ fixtures produced by the reference's own sources
+def test_reference_golden_gpu(engine):
+    """CUDA path against tests/golden/reference_small.npz = outputs of the reference's own sources (compiled against the
+    Eigen stand-in, tests/golden/make_reference_golden.py).  Tolerances are north_star's: voxel keys / centroids and
+    neighbour indices bit-exact, normals 1e-4 (sign-canonical), pose 1e-4 m / 1e-5 rad, Scan Context distance 1e-5."""
+    import slam_b200
+    g = np.load(os.path.join(GOLDEN, "reference_small.npz"))
+
+    def sort_rows(x):
+        return x[np.lexsort((x[:, 2], x[:, 1], x[:, 0]))]
+
+    for raw, v, key in ((g["raw_a"], 0.5, "voxel_a"), (g["raw_b"], 0.5, "voxel_b"), (g["raw_a"], 0.2, "voxel_a_02")):
+        assert np.array_equal(sort_rows(engine.voxel_downsample(raw.astype(np.float64), v)), g[key])
+        out32, off32 = engine.voxel_downsample_batch_f32(raw, np.array([0, len(raw)], dtype=np.int64), v)[:2]
+        assert np.array_equal(sort_rows(out32[off32[0]:off32[1]]), g[key])       # float32 records, widened on the device
+    a, b = g["voxel_a"], g["voxel_b"]
+    tree = slam_b200.KDTree(engine, a)
+    assert np.array_equal(tree.k_nearest_batch(a, 20)[0], g["knn20_a"])
+    assert np.array_equal(tree.k_nearest_batch(a, 10)[0], g["knn10_a"])
+    idx, d2 = tree.nearest_batch(b)
+    assert np.array_equal(idx, g["nn_b_in_a"]) and np.array_equal(d2, g["nn_b_in_a_d2"])
+    for k, key in ((20, "normals20_a"), (10, "normals10_a")):
+        n = tree.estimate_normals(k)
+        dots = np.sum(n * g[key], axis=1)
+        ok = dots > 1 - 1e-6                       # elsewhere the two smallest eigenvalues coincide: direction undefined
+        assert ok.mean() > 0.999 and np.max(np.abs(n[ok] - g[key][ok])) < 1e-4
+    assert np.array_equal(engine.sc_compute(a), g["sc_a"]) and np.array_equal(engine.sc_compute(b), g["sc_b"])
+    assert abs(engine.sc_distance(g["sc_a"], g["sc_b"]) - float(g["sc_dist_ab"])) < 1e-5
+    ring, sector = engine.sc_keys(g["sc_a"])
+    assert np.allclose(ring, g["sc_ring_key_a"], atol=1e-12) and np.allclose(sector, g["sc_sector_key_a"], atol=1e-12)
+    T = engine.solve_point_to_plane(b, a[g["nn_b_in_a"]], g["normals20_a"][g["nn_b_in_a"]])
+    assert np.max(np.abs(T - g["solve_T"])) < 1e-9
+    for name, it in (("icp50", 50), ("icp3", 3), ("icp30", 30)):
+        r = engine.icp_point_to_plane(b, a, engine.icp_config(max_iterations=it))
+        assert [r.num_iterations, int(r.converged)] == g[name + "_meta"].tolist()
+        assert np.allclose(r.error_history, g[name + "_history"], rtol=0, atol=1e-6)
+        dT = r.transformation @ np.linalg.inv(g[name + "_T"])
+        assert np.linalg.norm(dT[:3, 3]) < 1e-4 and rot_angle(dT[:3, :3]) < 1e-5
+    det = slam_b200.LoopClosureDetector(engine, frame_gap=3, sc_distance_threshold=0.5, icp_fitness_threshold=0.5,
+                                        max_candidates=2)
+    off, found = g["loop_offsets"], []
+    for i in range(len(off) - 1):
+        det.addFrame(g["loop_clouds"][off[i]:off[i + 1]], i)
+        found += det.detect()
+    want = g["loop_results"]
+    assert len(found) == len(want)
+    for x, w in zip(found, want):
+        assert (x["query_frame"], x["match_frame"]) == (int(w[0]), int(w[1]))
+        assert abs(x["scan_context_distance"] - w[2]) < 1e-5 and abs(x["icp_fitness"] - w[3]) < 1e-6
+        dT = x["transform"] @ np.linalg.inv(w[4:].reshape(4, 4))
+        assert np.linalg.norm(dT[:3, 3]) < 1e-4 and rot_angle(dT[:3, :3]) < 1e-5

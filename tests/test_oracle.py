@@ -1,8 +1,10 @@
 """CPU tests of the oracle (oracle/slam_oracle.cpp) against INDEPENDENT implementations.
 
-The reference ships no tests or golden vectors and cannot be built here (Eigen absent), so the oracle is pinned
-against brute force, numpy and scipy, against analytic cases, and against the committed fixtures in tests/golden/
-(produced by tests/golden/make_golden.py, a pure-numpy restatement that shares no code with the C++ oracle).
+The reference ships no tests or golden vectors, so the oracle is pinned against brute force, numpy and scipy,
+against analytic cases, against tests/golden/golden_small.npz (tests/golden/make_golden.py, a pure-numpy restatement
+that shares no code with the C++ oracle) and against tests/golden/reference_small.npz, produced by the reference's own
+sources compiled over an Eigen stand-in (tests/golden/make_reference_golden.py; live comparison in
+tests/test_reference_build.py).
 """
 import os
 
@@ -300,3 +302,59 @@ def test_transform_and_occupancy_match_numpy(oracle):
     keep = (w[:, 2] >= 0.3) & (w[:, 2] <= 2.0) & (r <= 40.0) & (r >= 0.5)
     ref = np.unique(np.floor(w[keep, :2] / 0.2).astype(np.int32), axis=0)
     assert np.array_equal(cells, ref)
+
+
+# ------------------------------------------------------------------ fixtures produced by the reference's own sources
+# tests/golden/reference_small.npz: outputs of /root/reference/slam_viz compiled against oracle/eigen_standin
+# (tests/golden/make_reference_golden.py).  The tolerances cover only the stand-in's replacement of Eigen's kernels.
+def _sort_rows(x):
+    return x[np.lexsort((x[:, 2], x[:, 1], x[:, 0]))]
+
+
+@pytest.fixture(scope="module")
+def refgold():
+    return np.load(os.path.join(GOLDEN, "reference_small.npz"))
+
+
+def test_reference_golden_voxel_knn_normals(oracle, refgold):
+    g = refgold
+    for raw, v, key in ((g["raw_a"], 0.5, "voxel_a"), (g["raw_b"], 0.5, "voxel_b"), (g["raw_a"], 0.2, "voxel_a_02")):
+        out, _ = oracle.voxel_downsample(raw.astype(np.float64), v)
+        assert np.array_equal(_sort_rows(out), g[key])
+    a, b = g["voxel_a"], g["voxel_b"]
+    t = oracle.tree(a)
+    assert np.array_equal(t.k_nearest_batch(a, 20)[0], g["knn20_a"])
+    assert np.array_equal(t.k_nearest_batch(a, 10)[0], g["knn10_a"])
+    idx, d2 = t.nearest_batch(b)
+    assert np.array_equal(idx, g["nn_b_in_a"]) and np.array_equal(d2, g["nn_b_in_a_d2"])
+    for k, key in ((20, "normals20_a"), (10, "normals10_a")):
+        n = t.estimate_normals(k)[0]
+        dots = np.sum(n * g[key], axis=1)
+        assert np.mean(dots > 1 - 1e-9) > 0.999
+        assert np.max(np.abs(n[dots > 1 - 1e-9] - g[key][dots > 1 - 1e-9])) < 1e-7
+
+
+def test_reference_golden_scan_context_icp_loop(oracle, refgold):
+    g = refgold
+    a, b = g["voxel_a"], g["voxel_b"]
+    assert np.array_equal(oracle.sc_compute(a), g["sc_a"]) and np.array_equal(oracle.sc_compute(b), g["sc_b"])
+    assert oracle.sc_distance(g["sc_a"], g["sc_b"]) == float(g["sc_dist_ab"])
+    T = oracle.solve_point_to_plane(b, a[g["nn_b_in_a"]], g["normals20_a"][g["nn_b_in_a"]])
+    assert np.max(np.abs(T - g["solve_T"])) < 1e-10
+    for name, cfg in (("icp50", dict()), ("icp3", dict(max_iterations=3)), ("icp30", dict(max_iterations=30))):
+        r = oracle.icp_point_to_plane(b, a, **cfg)
+        assert [r["num_iterations"], int(r["converged"])] == g[name + "_meta"].tolist()
+        assert np.allclose(r["error_history"], g[name + "_history"], rtol=0, atol=1e-9)
+        assert abs(r["final_error"] - float(g[name + "_final_error"])) < 1e-9
+        assert np.max(np.abs(r["transformation"] - g[name + "_T"])) < 1e-8
+    det = oracle.loop(frame_gap=3, sc_thr=0.5, icp_thr=0.5, max_candidates=2)
+    off, found = g["loop_offsets"], []
+    for i in range(len(off) - 1):
+        det.add(g["loop_clouds"][off[i]:off[i + 1]], i)
+        found += det.detect()
+    want = g["loop_results"]
+    assert len(found) == len(want) > 0
+    for x, w in zip(found, want):
+        assert (x["query_frame"], x["match_frame"]) == (int(w[0]), int(w[1]))
+        assert x["scan_context_distance"] == w[2] and abs(x["icp_fitness"] - w[3]) < 1e-9
+        assert np.max(np.abs(x["transform"].reshape(-1) - w[4:])) < 1e-8
