@@ -101,6 +101,28 @@ void stage_mark(Ctx* ctx, int stage) {
     ctx->n_ev++;
 }
 
+void trace_mark(Ctx* ctx, const char* name) {
+    static const bool on = getenv("SB_PIPE_TRACE") != nullptr;
+    if (!on) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, ctx->stream);
+    ctx->trace.push_back({name, e});
+}
+
+void trace_dump(Ctx* ctx) {
+    if (ctx->trace.empty()) return;
+    cudaStreamSynchronize(ctx->stream);
+    for (size_t i = 1; i < ctx->trace.size(); ++i) {
+        float ms = 0.f, d = 0.f;
+        cudaEventElapsedTime(&ms, ctx->trace[0].second, ctx->trace[i].second);
+        cudaEventElapsedTime(&d, ctx->trace[i - 1].second, ctx->trace[i].second);
+        fprintf(stderr, "[slam_b200]   %-18s at %8.3f ms (+%.3f)\n", ctx->trace[i].first, ms, d);
+    }
+    for (auto& t : ctx->trace) cudaEventDestroy(t.second);
+    ctx->trace.clear();
+}
+
 __global__ void k_copy_words(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, size_t n) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
 }
@@ -199,18 +221,37 @@ static int upload_voxel_pipelined(Ctx* ctx, const void* h_raw, int f32, int stri
     char* d_raw;
     SB_TRY(arena_get(ctx, (size_t)(n > 0 ? n : 1) * row_bytes, &d_raw));
     SB_TRY(ensure_copy_stream(ctx));
-    // chunk boundaries: whole clouds, about 384 MB each (SB_CHUNK_MB): smaller chunks pay more per-chunk host
-    // round trips than they gain in overlap (measured per C2 step from float32 records: 128 MB 57.9 ms, 256 MB 55.5 ms, 384 MB 54.4 ms, 512 MB 55.7 ms)
+    // chunk boundaries: whole clouds.  The body of the transfer goes in chunks of about 384 MB (SB_CHUNK_MB): smaller
+    // chunks pay more per-chunk host round trips than they gain in overlap (measured per C2 step from float32
+    // records: 128 MB 57.9 ms, 256 MB 55.5 ms, 384 MB 54.4 ms, 512 MB 55.7 ms).  The first two and the last two chunks
+    // are smaller (1/6 and 1/2.4 of that): the device idles while the first chunk arrives and the copy engine idles
+    // while the last one is processed, so the pipeline fills and drains on small pieces (SB_CHUNK_RAMP=0: off).
     std::vector<int> cb(1, 0);
     {
         const long chunk_mb = getenv("SB_CHUNK_MB") ? atol(getenv("SB_CHUNK_MB")) : 384;
-        const i64 target_rows = (i64)(((size_t)(chunk_mb > 0 ? chunk_mb : 384) << 20) / row_bytes);
+        const double body = (double)((size_t)(chunk_mb > 0 ? chunk_mb : 384) << 20);
+        const double total = (double)n * (double)row_bytes;
+        static const bool ramp = !(getenv("SB_CHUNK_RAMP") && atoi(getenv("SB_CHUNK_RAMP")) == 0);
+        std::vector<double> sizes;
+        const double edge = body / 6.0 + body / 2.4;
+        if (ramp && total > 2.0 * edge + 0.5 * body) {
+            const int k = (int)ceil((total - 2.0 * edge) / body);
+            sizes.push_back(body / 6.0);
+            sizes.push_back(body / 2.4);
+            for (int i = 0; i < k; ++i) sizes.push_back((total - 2.0 * edge) / k);
+            sizes.push_back(body / 2.4);
+            sizes.push_back(body / 6.0);
+        }
         i64 start = 0;
-        for (int c = 0; c < n_clouds; ++c)
-            if (offsets[c + 1] - start >= target_rows || c == n_clouds - 1) {
+        size_t si = 0;
+        for (int c = 0; c < n_clouds; ++c) {
+            const double want = si < sizes.size() ? sizes[si] : body;
+            if ((double)(offsets[c + 1] - start) * (double)row_bytes >= want || c == n_clouds - 1) {
                 cb.push_back(c + 1);
                 start = offsets[c + 1];
+                ++si;
             }
+        }
         if (cb.back() != n_clouds) cb.push_back(n_clouds);
     }
     const int n_chunks = (int)cb.size() - 1;
@@ -223,11 +264,25 @@ static int upload_voxel_pipelined(Ctx* ctx, const void* h_raw, int f32, int stri
         return SB_OK;
     };
     off_ds[0] = 0;
+    // SB_PIPE_TRACE=1: device timeline of the pipeline (copy done / voxel grid / index + normals per chunk) on stderr
+    static const bool trace = getenv("SB_PIPE_TRACE") != nullptr;
+    std::vector<cudaEvent_t> tev;
+    auto tmark = [&](cudaStream_t st) {
+        if (!trace) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        tev.push_back(e);
+    };
+    tmark(ctx->stream);
     if (n_chunks > 0) SB_TRY(enqueue_copy(0));
+    tmark(ctx->copy_stream);
     std::vector<i64> in_off, out_off;
     for (int k = 0; k < n_chunks; ++k) {
         SB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[k & 1], 0));
         if (k + 1 < n_chunks) SB_TRY(enqueue_copy(k + 1));  // in flight while chunk k is voxelised
+        tmark(ctx->copy_stream);
+        tmark(ctx->stream);
         const int c0 = cb[k], nc = cb[k + 1] - cb[k];
         in_off.assign((size_t)nc + 1, 0);
         out_off.assign((size_t)nc + 1, 0);
@@ -240,8 +295,24 @@ static int upload_voxel_pipelined(Ctx* ctx, const void* h_raw, int f32, int stri
         stage_mark(ctx, STAGE_VOXEL);
         SB_TRY(voxel_downsample_src(ctx, src, in_off.data(), nc, voxel, d_ds + 3 * off_ds[c0], out_off.data(), nullptr));
         arena_release(ctx, mark);
+        tmark(ctx->stream);
         for (int i = 1; i <= nc; ++i) off_ds[c0 + i] = off_ds[c0] + out_off[i];
         if (after_chunk) SB_TRY(after_chunk(c0, c0 + nc));  // more device work on these clouds while the next chunk copies
+        tmark(ctx->stream);
+    }
+    if (trace) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamSynchronize(ctx->copy_stream);
+        auto at = [&](size_t i) { float ms = 0.f; cudaEventElapsedTime(&ms, tev[0], tev[i]); return ms; };
+        fprintf(stderr, "[slam_b200] pipeline: first copy done %.2f ms\n", at(1));
+        for (int k = 0; k < n_chunks; ++k) {
+            const size_t b = 2 + 4 * (size_t)k;
+            fprintf(stderr, "[slam_b200]  chunk %d (%d clouds, %.0f MB): next copy done %.2f | compute start %.2f, voxel done %.2f, "
+                    "index+normals done %.2f ms\n", k, cb[k + 1] - cb[k],
+                    (double)(offsets[cb[k + 1]] - offsets[cb[k]]) * row_bytes / 1048576.0, at(b), at(b + 1), at(b + 2), at(b + 3));
+        }
+        for (cudaEvent_t e : tev) cudaEventDestroy(e);
+        trace_dump(ctx);
     }
     return SB_OK;
 }
@@ -278,9 +349,12 @@ static int register_batch_impl(Ctx* ctx, PointSrc src, const void* h_raw, const 
         if (!ids_t.empty()) {
             if (!h_raw) stage_mark(ctx, STAGE_INDEX);
             for (size_t i = 0; i < ids_t.size(); ++i) tree_of[ids_t[i]] = F.n_trees + (int)i;
+            trace_mark(ctx, "index:begin");
             SB_TRY(forest_append(ctx, &F, d_pts, off.data(), ids_t.data(), (int)ids_t.size()));
+            trace_mark(ctx, "index:append");
             if (!h_raw) stage_mark(ctx, STAGE_NORMALS);
             SB_TRY(forest_normals(ctx, &F, cfg->normals_k, nullptr, nullptr));
+            trace_mark(ctx, "index:normals");
         }
         if (!ids_s.empty()) {
             for (size_t i = 0; i < ids_s.size(); ++i) tree_of[ids_s[i]] = F.n_trees + (int)i;

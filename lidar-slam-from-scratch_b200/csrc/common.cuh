@@ -90,6 +90,8 @@ struct Ctx {
     int ev_stage[128];
     double ev_host[128];  // host steady_clock milliseconds at the same marks
     int n_ev = 0, ev_created = 0;
+    // SB_PIPE_TRACE=1: named device-time marks on the main stream (trace_mark / trace_dump), a debugging aid
+    std::vector<std::pair<const char*, cudaEvent_t>> trace;
     i64 last_icp_iterations = 0;   // max history length of the last icp_batch (launches of k_icp_iter)
     i64 last_counts[4] = {0, 0, 0, 0};  // raw rows, downsampled rows, target rows, sum over pairs of n_src * passes
 };
@@ -98,6 +100,8 @@ struct Ctx {
 enum { STAGE_H2D = 0, STAGE_VOXEL = 1, STAGE_SC = 2, STAGE_INDEX = 3, STAGE_NORMALS = 4, STAGE_ICP = 5, STAGE_D2H = 6,
        STAGE_COUNT = 7, STAGE_END = -1 };
 void stage_mark(Ctx* ctx, int stage);
+void trace_mark(Ctx* ctx, const char* name);
+void trace_dump(Ctx* ctx);
 
 int arena_reset(Ctx* ctx);
 // Temporaries of one pipeline stage: everything allocated after arena_mark is handed back by arena_release.  Safe

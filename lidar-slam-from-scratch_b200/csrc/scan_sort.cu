@@ -208,6 +208,93 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(const u64* __rest
     }
 }
 
+
+// =============================================================================================================
+// one-CTA-per-segment sort in shared memory (segments of up to SEG_CAP rows, keys of up to 32 bits)
+// =============================================================================================================
+// A downsampled scan is 7-10 k rows: the tiled sort above spends five launches per digit on it (20 for a Morton
+// code) and all of them are latency.  Here a CTA keeps the segment's keys and a 16-bit permutation in shared memory
+// and does every digit pass there: rank by __match_any inside each warp's contiguous block of rows (stable), one
+// block scan over the [digit][warp] counters, scatter of the permutation; keys and values move once, at the end.
+static constexpr int SEG_CAP = 12288;
+static constexpr int SEG_THREADS = 1024;
+static constexpr int SEG_EPT = SEG_CAP / SEG_THREADS;   // batches of 32 rows per warp, at most
+static constexpr size_t SEG_SMEM = (size_t)SEG_CAP * 4 + (size_t)SEG_CAP * 2 * 2 + (size_t)RADIX * 32 * 2;
+
+__global__ void __launch_bounds__(SEG_THREADS) k_seg_sort_smem(const u64* __restrict__ kin, const uint32_t* __restrict__ vin,
+                                                               u64* __restrict__ kout, uint32_t* __restrict__ vout,
+                                                               const i64* __restrict__ seg_off, int key_bits) {
+    extern __shared__ __align__(16) unsigned char seg_sm[];
+    uint32_t* keys = reinterpret_cast<uint32_t*>(seg_sm);
+    unsigned short* pin = reinterpret_cast<unsigned short*>(keys + SEG_CAP);
+    unsigned short* pout = pin + SEG_CAP;
+    unsigned short* cnt = pout + SEG_CAP;  // [digit][warp]: rows of this digit in this warp's block, then their base
+    __shared__ uint32_t s_scan[33];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const i64 base = seg_off[blockIdx.x];
+    const int n = (int)(seg_off[blockIdx.x + 1] - base);
+    if (n <= 0) return;
+    for (int i = tid; i < n; i += SEG_THREADS) {
+        keys[i] = (uint32_t)kin[base + i];
+        pin[i] = (unsigned short)i;
+    }
+    const int per = (((n + 31) / 32) + 31) & ~31;  // rows per warp: a multiple of 32, 32 * per >= n
+    const int w0 = warp * per, w1 = min(n, w0 + per);
+    for (int shift = 0; shift < key_bits; shift += 8) {
+        for (int i = tid; i < RADIX * 32; i += SEG_THREADS) cnt[i] = 0;
+        __syncthreads();
+        unsigned short rank[SEG_EPT];
+#pragma unroll
+        for (int j = 0; j < SEG_EPT; ++j) {
+            rank[j] = 0;
+            if (j * 32 < per) {  // warp-uniform
+                const int i = w0 + j * 32 + lane;
+                const bool act = i < w1;
+                const unsigned d = act ? ((keys[pin[i]] >> shift) & (RADIX - 1)) : (unsigned)RADIX + lane;
+                const unsigned m = __match_any_sync(0xffffffffu, d);
+                unsigned short old = 0;
+                if (act) old = cnt[d * 32 + warp];
+                __syncwarp();
+                if (act) {
+                    rank[j] = (unsigned short)(old + __popc(m & lanemask_lt()));
+                    if ((int)(__ffs(m) - 1) == lane) cnt[d * 32 + warp] = (unsigned short)(old + __popc(m));
+                }
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        {   // exclusive scan over the 8192 counters in [digit][warp] order: 8 consecutive counters per thread
+            unsigned short* c8 = cnt + tid * 8;
+            uint32_t loc[8], sum = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { loc[q] = sum; sum += c8[q]; }
+            uint32_t total;
+            const uint32_t off = block_exclusive_scan_1024(sum, s_scan, &total);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) c8[q] = (unsigned short)(off + loc[q]);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < SEG_EPT; ++j) {
+            if (j * 32 < per) {
+                const int i = w0 + j * 32 + lane;
+                if (i < w1) {
+                    const unsigned short idx = pin[i];
+                    const unsigned d = (keys[idx] >> shift) & (RADIX - 1);
+                    pout[cnt[d * 32 + warp] + rank[j]] = idx;
+                }
+            }
+        }
+        __syncthreads();
+        unsigned short* t = pin; pin = pout; pout = t;
+    }
+    for (int i = tid; i < n; i += SEG_THREADS) {
+        const unsigned short idx = pin[i];
+        kout[base + i] = (u64)keys[idx];
+        vout[base + i] = vin[base + idx];
+    }
+}
+
 int segmented_sort_pairs(Ctx* ctx, u64* keys_a, u64* keys_b, uint32_t* vals_a, uint32_t* vals_b,
                          const i64* h_seg_off, int n_seg, int key_bits, u64** out_keys, uint32_t** out_vals) {
     *out_keys = keys_a;
@@ -216,6 +303,24 @@ int segmented_sort_pairs(Ctx* ctx, u64* keys_a, u64* keys_b, uint32_t* vals_a, u
     if (h_seg_off[0] != 0) return fail(ctx, SB_ERR_INVALID_ARG, "sort: offsets must start at 0");
     if (n_total <= 0 || key_bits <= 0) return SB_OK;
     if (h_seg_off[n_seg] >= (i64)0xffffffffLL) return fail(ctx, SB_ERR_RANGE, "sort: more than 2^32-1 rows in one call");
+    // short segments with short keys: one CTA per segment, everything in shared memory
+    {
+        i64 longest = 0;
+        for (int s = 0; s < n_seg; ++s) longest = std::max(longest, h_seg_off[s + 1] - h_seg_off[s]);
+        static const bool no_smem_sort = getenv("SB_SORT_TILED") != nullptr;
+        if (!no_smem_sort && key_bits <= 32 && longest <= SEG_CAP) {
+            // per device, and cheap: set on every call rather than tracked per context
+            SB_CUDA(ctx, cudaFuncSetAttribute(k_seg_sort_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEG_SMEM));
+            i64* d_seg;
+            SB_TRY(arena_get(ctx, (size_t)n_seg + 1, &d_seg));
+            SB_TRY(table_upload(ctx, d_seg, h_seg_off, sizeof(i64) * ((size_t)n_seg + 1)));
+            SB_LAUNCH(ctx, k_seg_sort_smem, (unsigned)n_seg, SEG_THREADS, SEG_SMEM, keys_a, vals_a, keys_b, vals_b, d_seg,
+                      key_bits);
+            *out_keys = keys_b;
+            *out_vals = vals_b;
+            return SB_OK;
+        }
+    }
     // tile table (host-built, staged through pinned memory)
     i64 n_tiles = 0;
     for (int s = 0; s < n_seg; ++s) n_tiles += (h_seg_off[s + 1] - h_seg_off[s] + SORT_TILE - 1) / SORT_TILE;
