@@ -284,6 +284,7 @@ __global__ void __launch_bounds__(256) k_vox_insert(const PointSrc src, const Vo
         const VoxCloud C = clouds[c];
         const i64 t0 = (tile - C.tile_off) * VTILE;
         VoxSlot* tab = table + C.tab_off;
+        int claimed = 0;  // voxels this thread created in this tile: one counter update per warp and tile
 #pragma unroll
         for (int r = 0; r < VROWS; ++r) {
             const i64 i = t0 + r * 256 + threadIdx.x;  // row inside the cloud
@@ -314,7 +315,7 @@ __global__ void __launch_bounds__(256) k_vox_insert(const PointSrc src, const Vo
                         if (cur == VOX_EMPTY) {
                             cur = atomicCAS(&tab[s].key, VOX_EMPTY, key);
                             if (cur == VOX_EMPTY) {
-                                atomicAdd(&n_vox[c], 1);
+                                ++claimed;
                                 cur = key;
                             }
                         }
@@ -353,6 +354,8 @@ __global__ void __launch_bounds__(256) k_vox_insert(const PointSrc src, const Vo
                 if (fl) atomicOr(&S->flags, fl);
             }
         }
+        claimed = __reduce_add_sync(0xffffffffu, claimed);
+        if (lane == 0 && claimed) atomicAdd(&n_vox[c], claimed);
     }
     // key range + flags of this block
 #pragma unroll
