@@ -54,6 +54,33 @@ class ClockSampler:
         self._t = None
 
     def _run(self):
+        # NVML in-process (a sample costs microseconds, so a 0.2 s timed region still gets ~10 of them); nvidia-smi
+        # as a subprocess only if the binding is missing
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            try:  # the CUDA ordinal need not be the NVML index (CUDA_VISIBLE_DEVICES): go by PCI address
+                import torch
+                pr = torch.cuda.get_device_properties(self.device)
+                h = pynvml.nvmlDeviceGetHandleByPciBusId(
+                    ("%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)).encode())
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.device)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            bits = {"hw_slowdown": pynvml.nvmlClocksThrottleReasonHwSlowdown,
+                    "hw_thermal_slowdown": pynvml.nvmlClocksThrottleReasonHwThermalSlowdown,
+                    "sw_thermal_slowdown": pynvml.nvmlClocksThrottleReasonSwThermalSlowdown,
+                    "sw_power_cap": pynvml.nvmlClocksThrottleReasonSwPowerCap}
+            while not self._stop.is_set():
+                self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for n, b in bits.items():
+                    if r & b:
+                        self.reasons.add(n)
+                self._stop.wait(0.02)
+            return
+        except Exception:
+            pass
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
