@@ -180,6 +180,34 @@ def test_knn_adversarial_bit_exact(engine, oracle, kind):
     assert np.array_equal(ni, bi[:, 0]) and np.array_equal(nd, bd[:, 0])
 
 
+def test_index_sort_paths_around_the_shared_memory_capacity(engine, oracle):
+    """Morton sort of the index build: segments up to 12288 points are sorted by one CTA in shared memory, longer ones
+    by the tiled device-wide sort; both sides of the boundary, odd sizes, and a batch that mixes them (then every
+    segment takes the tiled path).  Also the voxel key sort of a cloud with > 12288 voxels."""
+    import slam_b200
+    for n in (12287, 12288, 12289, 4097):
+        rng = np.random.default_rng(n)
+        pts = rng.uniform(-40, 40, (n, 3))
+        q = np.vstack([pts[:64], rng.uniform(-40, 40, (64, 3))])
+        gi, gd = slam_b200.KDTree(engine, pts).k_nearest_batch(q, 7)
+        bi, bd = oracle.brute_knn(pts, q, 7)
+        assert np.array_equal(gi, bi) and np.array_equal(gd, bd), n
+    rng = np.random.default_rng(5)
+    sizes = [100, 12288, 12289, 1, 33, 5000]
+    clouds = [np.round(rng.uniform(-60, 60, (m, 3)).astype(np.float32), 2).astype(np.float64) for m in sizes]
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    res = engine.register_batch(np.vstack(clouds), off, [0, 2, 5], [1, 1, 2], voxel=0.0,
+                                cfg=engine.icp_config(max_iterations=2))
+    assert len(res) == 3
+    for (s_, t_), r in zip(((0, 1), (2, 1), (5, 2)), res):
+        o = oracle.icp_point_to_plane(clouds[s_], clouds[t_], max_iterations=2)
+        assert r.num_iterations == o["num_iterations"] and np.allclose(r.error_history, o["error_history"], atol=1e-6)
+    big = np.round(rng.uniform(-30, 30, (40000, 3)).astype(np.float32), 3).astype(np.float64)   # ~40 k voxels at 0.5 m
+    out, keys = engine.voxel_downsample(big, 0.5, return_keys=True)
+    oo, ok = oracle.voxel_downsample(big, 0.5)
+    assert len(out) > 12288 and np.array_equal(keys, ok) and np.array_equal(out, oo)
+
+
 def test_knn_tiny_and_empty(engine, oracle):
     import slam_b200
     for n in (1, 2, 3, 31, 32, 33, 1024, 1025):
