@@ -148,6 +148,7 @@ int main() {
     lc.frame_gap = 2;
     lc.sc_distance_threshold = 0.5;
     slam::LoopClosureDetector det(lc);
+    det.reserve(8, 100000);  // extension: size the device pools up front (must not change any result)
     det.addFrame(prev, 1);
     det.addFrame(curr, 2);
     det.addFrame(slam::voxel_downsample(scan(boxes, 30.0, 0.0, 0.0, 9), 0.5), 3);
