@@ -68,6 +68,21 @@ def main():
     out["loop_clouds"] = np.concatenate(clouds)
     out["loop_offsets"] = np.array(offs, dtype=np.int64)
     out["loop_results"] = np.array(found)  # rows: query, match, sc_distance, icp_fitness, T[16]
+    # config C1 itself (BASELINE.json configs[0]): 64 beams x 1875 steps, poses (0,0,0) and (1.0, 0.1, 0.01), voxel 0.5,
+    # ICPConfig defaults.  The raw scans (2 x 1.4 MB) are not stored: the raycaster is deterministic, the fixture keeps
+    # their SHA-256 so that a test knows it regenerated the same input, and the reference's outputs.
+    import hashlib
+    c1a = syn.scan(oracle_lib.SENSOR64, scene, (0.0, 0.0, 0.0), 7)
+    c1b = syn.scan(oracle_lib.SENSOR64, scene, (1.0, 0.1, 0.01), 8)
+    out["c1_sha256"] = np.frombuffer(hashlib.sha256(c1a.tobytes() + c1b.tobytes()).digest(), dtype=np.uint8)
+    va = sort_rows(ref.voxel_downsample(c1a, 0.5))
+    vb = sort_rows(ref.voxel_downsample(c1b, 0.5))
+    out["c1_voxel_counts"] = np.array([len(c1a), len(c1b), len(va), len(vb)], dtype=np.int64)
+    out["c1_voxel_a_sum"], out["c1_voxel_b_sum"] = va.sum(axis=0), vb.sum(axis=0)
+    c1 = ref.icp_point_to_plane(vb, va)
+    out["c1_T"], out["c1_history"] = c1["transformation"], c1["error_history"]
+    out["c1_meta"] = np.array([c1["num_iterations"], int(c1["converged"])], dtype=np.int32)
+    out["c1_final_error"] = np.float64(c1["final_error"])
     path = os.path.join(HERE, "reference_small.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes;", len(a), "and", len(b), "voxel points;",

@@ -640,3 +640,31 @@ def test_reference_golden_gpu(engine):
         assert abs(x["scan_context_distance"] - w[2]) < 1e-5 and abs(x["icp_fitness"] - w[3]) < 1e-6
         dT = x["transform"] @ np.linalg.inv(w[4:].reshape(4, 4))
         assert np.linalg.norm(dT[:3, 3]) < 1e-4 and rot_angle(dT[:3, :3]) < 1e-5
+
+
+def test_reference_golden_config_c1_gpu(engine, synth, scene):
+    """BASELINE.json configs[0] through the CUDA path against the reference's own result for it (fixture made by
+    tests/golden/make_reference_golden.py; the raw scans are regenerated and checked by SHA-256)."""
+    import hashlib
+    g = np.load(os.path.join(GOLDEN, "reference_small.npz"))
+    a = synth.scan(oracle_lib.SENSOR64, scene, (0.0, 0.0, 0.0), 7)
+    b = synth.scan(oracle_lib.SENSOR64, scene, (1.0, 0.1, 0.01), 8)
+    sha = np.frombuffer(hashlib.sha256(a.tobytes() + b.tobytes()).digest(), dtype=np.uint8)
+    assert np.array_equal(sha, g["c1_sha256"])
+
+    def sort_rows(x):
+        return x[np.lexsort((x[:, 2], x[:, 1], x[:, 0]))]
+
+    va, vb = sort_rows(engine.voxel_downsample(a, 0.5)), sort_rows(engine.voxel_downsample(b, 0.5))
+    assert [len(a), len(b), len(va), len(vb)] == g["c1_voxel_counts"].tolist()
+    assert np.array_equal(va.sum(axis=0), g["c1_voxel_a_sum"]) and np.array_equal(vb.sum(axis=0), g["c1_voxel_b_sum"])
+    r = engine.icp_point_to_plane(vb, va)
+    assert [r.num_iterations, int(r.converged)] == g["c1_meta"].tolist()
+    assert np.allclose(r.error_history, g["c1_history"], rtol=0, atol=1e-6)
+    dT = r.transformation @ np.linalg.inv(g["c1_T"])
+    assert np.linalg.norm(dT[:3, 3]) < 1e-4 and rot_angle(dT[:3, :3]) < 1e-5
+    # the same pair through the batch entry point (voxel grid + index + normals + ICP in one call, key-ordered rows)
+    off = np.array([0, len(a), len(a) + len(b)], dtype=np.int64)
+    rb = engine.register_batch(np.vstack([a, b]), off, [1], [0], voxel=0.5)[0]
+    dT = rb.transformation @ np.linalg.inv(g["c1_T"])
+    assert rb.num_iterations == int(g["c1_meta"][0]) and np.linalg.norm(dT[:3, 3]) < 1e-4 and rot_angle(dT[:3, :3]) < 1e-5

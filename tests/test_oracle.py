@@ -358,3 +358,26 @@ def test_reference_golden_scan_context_icp_loop(oracle, refgold):
         assert (x["query_frame"], x["match_frame"]) == (int(w[0]), int(w[1]))
         assert x["scan_context_distance"] == w[2] and abs(x["icp_fitness"] - w[3]) < 1e-9
         assert np.max(np.abs(x["transform"].reshape(-1) - w[4:])) < 1e-8
+
+
+def _c1_inputs(synth, scene, g):
+    import hashlib
+    a = synth.scan(oracle_lib.SENSOR64, scene, (0.0, 0.0, 0.0), 7)
+    b = synth.scan(oracle_lib.SENSOR64, scene, (1.0, 0.1, 0.01), 8)
+    sha = np.frombuffer(hashlib.sha256(a.tobytes() + b.tobytes()).digest(), dtype=np.uint8)
+    assert np.array_equal(sha, g["c1_sha256"]), "the raycaster no longer reproduces the scans the fixture was made from"
+    return a, b
+
+
+def test_reference_golden_config_c1(oracle, synth, scene, refgold):
+    """BASELINE.json configs[0] (one 64-beam pair, voxel 0.5, ICPConfig defaults): the oracle against what the
+    reference's own sources produced for it."""
+    g = refgold
+    a, b = _c1_inputs(synth, scene, g)
+    va, vb = _sort_rows(oracle.voxel_downsample(a, 0.5)[0]), _sort_rows(oracle.voxel_downsample(b, 0.5)[0])
+    assert [len(a), len(b), len(va), len(vb)] == g["c1_voxel_counts"].tolist()
+    assert np.array_equal(va.sum(axis=0), g["c1_voxel_a_sum"]) and np.array_equal(vb.sum(axis=0), g["c1_voxel_b_sum"])
+    r = oracle.icp_point_to_plane(vb, va)
+    assert [r["num_iterations"], int(r["converged"])] == g["c1_meta"].tolist()
+    assert np.allclose(r["error_history"], g["c1_history"], rtol=0, atol=1e-9)
+    assert np.max(np.abs(r["transformation"] - g["c1_T"])) < 1e-8
