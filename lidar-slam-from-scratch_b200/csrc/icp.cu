@@ -743,8 +743,7 @@ void icp_graph_free(Ctx* ctx) {
 
 static int add_kernel(Ctx* ctx, cudaGraph_t g, cudaGraphNode_t* node, const cudaGraphNode_t* dep, void* fn, int grid,
                       int block, void** args) {
-    cudaKernelNodeParams kp;
-    memset(&kp, 0, sizeof(kp));
+    cudaKernelNodeParams kp = {};
     kp.func = fn;
     kp.gridDim = dim3((unsigned)grid, 1, 1);
     kp.blockDim = dim3((unsigned)block, 1, 1);

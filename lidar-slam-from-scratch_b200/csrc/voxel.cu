@@ -216,8 +216,7 @@ static int voxel_sorted_dev(Ctx* ctx, const double* d_xyz, const i64* h_off, int
 // =============================================================================================================
 // fast path
 // =============================================================================================================
-static constexpr int VQ_BITS = 44;                     // fixed-point fraction bits
-static constexpr double VQ_SCALE = 17592186044416.0;   // 2^44
+static constexpr double VQ_SCALE = 17592186044416.0;   // 2^44: the sums carry 44 fixed-point fraction bits
 static constexpr int VQ_COARSE_TZ = 11;                // a coordinate is "coarse" if it is a multiple of 2^(11-44)
 static constexpr double VQ_LIMIT_COARSE = 524288.0;    // 2^19: sum|v| below this -> no wrap, fp64 loop exact (coarse)
 static constexpr double VQ_LIMIT_FINE = 512.0;         // 2^(53-44): sum|v| bound when some member is finer

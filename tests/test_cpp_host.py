@@ -8,6 +8,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EXE = os.path.join(ROOT, "tests", "cpp", "host_api_test")
+EXE_EIGEN_API = EXE + "_eigenapi"  # the headers' Eigen branch, compiled against oracle/eigen_standin
 
 
 def build():
@@ -25,14 +26,16 @@ def test_cpp_host_api_compiles_and_has_no_cpu_fallback():
     import torch
     if torch.cuda.is_available():
         pytest.skip("GPU present: covered by the gpu test")
-    p = subprocess.run([EXE], capture_output=True, text=True)
-    assert p.returncode != 0
-    assert "no usable sm_100a device" in p.stderr
+    for exe in (EXE, EXE_EIGEN_API):
+        p = subprocess.run([exe], capture_output=True, text=True)
+        assert p.returncode != 0
+        assert "no usable sm_100a device" in p.stderr
 
 
 @pytest.mark.gpu
 def test_cpp_host_api_matches_oracle():
     build()
-    p = subprocess.run([EXE], capture_output=True, text=True, timeout=600)
-    assert p.returncode == 0, p.stdout + p.stderr
-    assert "all checks passed" in p.stdout
+    for exe in (EXE, EXE_EIGEN_API):
+        p = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0, exe + "\n" + p.stdout + p.stderr
+        assert "all checks passed" in p.stdout
