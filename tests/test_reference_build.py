@@ -213,3 +213,61 @@ def test_loop_detector_sequence(oracle, ref, synth, scene):
     assert found > 0 and rd.size() == len(poses)
     rd.clear()
     assert rd.size() == 0 and rd.detect() == []
+
+
+# ------------------------------------------------------------------ exact ties and many random shapes
+def test_exact_ties_on_a_lattice(oracle, ref):
+    """On exact distance ties the reference returns whichever minimiser its traversal meets first (kdtree.hpp:125,160
+    with nth_element's unspecified partition); the oracle and the engine return the smallest index.  Both must agree
+    on the DISTANCES bit for bit, the reference's pick must be a true minimiser, and the oracle's the first of them."""
+    rng = np.random.default_rng(9)
+    g = np.arange(-4, 5, dtype=np.float64)
+    pts = np.stack(np.meshgrid(g, g, g, indexing="ij"), axis=-1).reshape(-1, 3)
+    pts = pts[rng.permutation(len(pts))]
+    q = np.concatenate([rng.integers(-5, 6, (200, 3)).astype(np.float64) + 0.5, pts[:50]])  # cell centres: 8-way ties
+    ot, rt = oracle.tree(pts), ref.tree(pts)
+    oi, od = ot.nearest_batch(q)
+    ri, rd = rt.nearest_batch(q)
+    assert np.array_equal(od, rd)
+    d_all = ((pts[None, :, :] - q[:, None, :]) ** 2).sum(axis=2)
+    assert np.array_equal(d_all[np.arange(len(q)), ri], rd)                    # the reference's pick is a minimiser
+    assert np.array_equal(oi, np.argmax(d_all == d_all.min(axis=1, keepdims=True), axis=1))  # oracle: first minimiser
+    for k in (4, 20):
+        ok, okd = ot.k_nearest_batch(q, k)
+        rk = rt.k_nearest_batch(q, k)
+        rkd = d_all[np.arange(len(q))[:, None], rk]
+        assert np.array_equal(okd, rkd)                                         # same multiset of distances, ascending
+        inside = okd[:, -1:] > okd                                              # strictly inside the k-th distance:
+        for row in range(len(q)):                                               # those neighbours are forced
+            assert set(ok[row][inside[row]]) <= set(rk[row])
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_shapes_nearest_and_knn(oracle, ref, seed):
+    rng = np.random.default_rng(100 + seed)
+    for _ in range(12):
+        n = int(rng.integers(1, 400))
+        kind = rng.integers(0, 3)
+        if kind == 0:
+            pts = rng.normal(size=(n, 3)) * rng.uniform(0.1, 50)
+        elif kind == 1:   # thin slab: one axis nearly degenerate (the split axis cycles regardless, kdtree.hpp:90)
+            pts = rng.uniform(-30, 30, (n, 3)) * np.array([1.0, 1.0, 1e-6])
+        else:             # clustered
+            pts = rng.normal(size=(n, 3)) * 0.05 + rng.integers(-3, 4, (n, 1)) * 10.0
+        q = np.concatenate([pts[rng.integers(0, n, 20)] + rng.normal(size=(20, 3)) * 0.3, rng.uniform(-60, 60, (20, 3))])
+        ot, rt = oracle.tree(pts), ref.tree(pts)
+        oi, od = ot.nearest_batch(q)
+        ri, rd = rt.nearest_batch(q)
+        assert np.array_equal(oi, ri) and np.array_equal(od, rd)
+        k = int(rng.choice([1, 3, 10, 20, 32]))
+        assert np.array_equal(ot.k_nearest_batch(q, k)[0], rt.k_nearest_batch(q, k))
+
+
+@pytest.mark.parametrize("voxel,scale", [(0.01, 5.0), (2.0, 500.0), (0.3, 80.0)])
+def test_voxel_grid_scales_and_signs(oracle, ref, voxel, scale):
+    rng = np.random.default_rng(int(voxel * 1000))
+    pts = (rng.uniform(-scale, scale, (5000, 3))).astype(np.float32).astype(np.float64)
+    pts[:50] = pts[50:100] + np.float32(1e-4)     # near-duplicates share voxels
+    o, _ = oracle.voxel_downsample(pts, voxel)
+    r = ref.voxel_downsample(pts, voxel)
+    assert np.array_equal(sort_rows(o), sort_rows(r))
