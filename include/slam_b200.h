@@ -244,6 +244,14 @@ int sb_occupancy_cells(sb_ctx* ctx, const double* xyz, const int64_t* offsets, i
 int sb_global_map(sb_ctx* ctx, const double* xyz, const int64_t* offsets, int32_t n_clouds, const double* poses16,
                   double voxel, double* out_xyz, int64_t* out_m);
 
+/* The pose chain of process_frame (slam_node.cpp:139-145), for a sequence registered as one batch: results[i] is the
+ * registration of frame i+1 against frame i; delta_i = identity if !converged or final_error > max_error (the node
+ * uses 1.0), else the result's transformation; poses16_out[0] = initial_pose16 (NULL: identity) and
+ * poses16_out[i+1] = poses16_out[i] * delta_i.  poses16_out: (n+1)*16 doubles, row-major 4x4 — the `poses16` the three
+ * entry points above take.  Host arithmetic (n 4x4 products, a serial recurrence); ctx may be NULL. */
+int sb_odometry_poses(sb_ctx* ctx, const sb_icp_result* results, int32_t n, double max_error,
+                      const double* initial_pose16, double* poses16_out);
+
 /* ---------------------------------------------------------------- bench/test input generator --------------- */
 /* Synthetic 64/128-beam raycast straight into device memory (synth/lidar_synth.h).  boxes: host, n_boxes*6 floats;
  * poses: host, n_scans*3 doubles (x, y, yaw); d_xyz: device, n_scans*beams*azimuth_steps*3 doubles capacity;

@@ -1097,6 +1097,29 @@ int sb_occupancy_cells(sb_ctx* ctx, const double* xyz, const int64_t* offsets, i
     return SB_OK;
 }
 
+// slam_node.cpp:139-145: delta = identity unless the registration converged with final_error <= max_error;
+// new_pose = poses_.back() * delta (Transformation::operator*, types.hpp:118-125: plain 4x4 product, k ascending)
+int sb_odometry_poses(sb_ctx*, const sb_icp_result* results, int32_t n, double max_error, const double* initial_pose16,
+                      double* poses16_out) {
+    if (n < 0 || !poses16_out || (n > 0 && !results)) return SB_ERR_INVALID_ARG;
+    static const double I16[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    memcpy(poses16_out, initial_pose16 ? initial_pose16 : I16, sizeof(I16));
+    for (int32_t f = 0; f < n; ++f) {
+        const sb_icp_result& R = results[f];
+        const bool keep = R.status == SB_OK && R.converged && !(R.final_error > max_error);
+        const double* D = keep ? R.transformation : I16;
+        const double* P = poses16_out + 16 * (size_t)f;
+        double* O = poses16_out + 16 * ((size_t)f + 1);
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 4; ++j) {
+                double acc = 0.0;
+                for (int k = 0; k < 4; ++k) acc += P[4 * i + k] * D[4 * k + j];
+                O[4 * i + j] = acc;
+            }
+    }
+    return SB_OK;
+}
+
 int sb_global_map(sb_ctx* ctx, const double* xyz, const int64_t* offsets, int32_t n_clouds, const double* poses16,
                   double voxel, double* out_xyz, int64_t* out_m) {
     if (!ctx || !offsets || n_clouds < 0 || !out_m) return SB_ERR_INVALID_ARG;

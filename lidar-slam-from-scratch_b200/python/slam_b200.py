@@ -113,6 +113,7 @@ SYMBOLS = {
     "sb_loop_detect": (C.c_int, [_P, C.POINTER(LoopResultC), C.c_int32, _I32]),
     "sb_loop_candidates_local": (C.c_int, [_P, _D, _I32, C.c_int32, _I32]),
     "sb_loop_verify_entries": (C.c_int, [_P, _I32, _D, C.c_int32, C.POINTER(LoopResultC), _I32]),
+    "sb_odometry_poses": (C.c_int, [_P, C.POINTER(ICPResultC), C.c_int32, C.c_double, _D, _D]),
     "sb_default_grid_config": (None, [_P]),
     "sb_transform_clouds": (C.c_int, [_P, _D, _I64, C.c_int32, _D, _D]),
     "sb_occupancy_cells": (C.c_int, [_P, _D, _I64, C.c_int32, _D, _P, _I32, C.c_int64, _I64]),
@@ -317,6 +318,16 @@ class Engine:
         return (out, sc) if want_sc else out
 
     # ---- after the path: world-frame clouds, occupancy cells, global map (slam_node.cpp:147-152, 196-238)
+    def odometry_poses(self, results, max_error=1.0, initial_pose=None):
+        """slam_node.cpp:139-145: absolute poses (n + 1, 4, 4) of a sequence from its frame-to-frame registrations."""
+        rec = np.ascontiguousarray(results.rec)
+        n = rec.shape[0]
+        out = np.empty((n + 1, 16))
+        p0 = None if initial_pose is None else np.ascontiguousarray(initial_pose, dtype=np.float64).reshape(16)
+        self._check(self.lib.sb_odometry_poses(self.h, rec.ctypes.data_as(C.POINTER(ICPResultC)), n, float(max_error),
+                                               _dp(p0) if p0 is not None else None, _dp(out)))
+        return out.reshape(n + 1, 4, 4)
+
     def transform_clouds(self, points, offsets, poses):
         pts, off = _f64(points, 3), np.ascontiguousarray(offsets, dtype=np.int64)
         T = np.ascontiguousarray(poses, dtype=np.float64).reshape(-1, 16)

@@ -79,3 +79,37 @@ def test_defaults_match_reference():
     lib.sb_default_loop_config(C.byref(lc))
     assert (lc.frame_gap, lc.sc_distance_threshold, lc.icp_fitness_threshold, lc.max_candidates) == (50, 0.25, 0.3, 3)
     assert (lc.icp_max_iterations, lc.icp_tolerance) == (30, 1e-6)  # loop_closure.hpp:106-107
+
+
+def test_odometry_pose_chain_host_only():
+    """sb_odometry_poses is host arithmetic (slam_node.cpp:139-145) and needs no device: identity for the frames whose
+    registration did not converge or ended above the error limit, otherwise pose <- pose * delta."""
+    import numpy as np
+    lib = slam_b200.load_library()
+    rng = np.random.default_rng(4)
+    n = 9
+    rec = np.zeros(n, dtype=slam_b200.ICP_DTYPE)
+    Ts = []
+    for i in range(n):
+        a = rng.uniform(-0.05, 0.05)
+        T = np.eye(4)
+        T[:2, :2] = [[np.cos(a), -np.sin(a)], [np.sin(a), np.cos(a)]]
+        T[:3, 3] = rng.uniform(-1, 1, 3)
+        Ts.append(T)
+        rec[i]["transformation"] = T.reshape(-1)
+        rec[i]["converged"] = 0 if i == 3 else 1
+        rec[i]["final_error"] = 1.5 if i == 5 else (1.0 if i == 6 else 0.2)   # > 1.0 is dropped, == 1.0 is kept
+        rec[i]["status"] = 0
+    out = np.empty((n + 1, 16))
+    D = C.POINTER(C.c_double)
+    s = lib.sb_odometry_poses(None, rec.ctypes.data_as(C.POINTER(slam_b200.ICPResultC)), n, 1.0, None, out.ctypes.data_as(D))
+    assert s == 0
+    pose = np.eye(4)
+    assert np.array_equal(out[0].reshape(4, 4), pose)
+    for i in range(n):
+        pose = pose @ (np.eye(4) if i in (3, 5) else Ts[i])
+        assert np.allclose(out[i + 1].reshape(4, 4), pose, rtol=0, atol=1e-15)
+    p0 = Ts[0].reshape(-1).copy()
+    assert lib.sb_odometry_poses(None, None, 0, 1.0, p0.ctypes.data_as(D), out.ctypes.data_as(D)) == 0
+    assert np.array_equal(out[0], p0)
+    assert lib.sb_odometry_poses(None, None, 3, 1.0, None, out.ctypes.data_as(D)) != 0   # results missing

@@ -587,6 +587,17 @@ def test_world_frame_occupancy_and_global_map(engine, oracle, synth, scene):
     assert np.array_equal(gm, ref_gm)
     assert np.array_equal(engine.global_map(allpts, off, Ts, 0.0), ref_world)
     assert engine.occupancy_cells(np.zeros((0, 3)), [0], np.zeros((0, 16)))[1] == 0
+    # the whole offline-mapping chain through the ABI: register the sequence as one batch, chain the poses the way
+    # process_frame does (slam_node.cpp:139-145), build the map from them
+    res = engine.register_batch(allpts, off, np.arange(1, 6), np.arange(0, 5), voxel=0.0)
+    chain = engine.odometry_poses(res)
+    pose = np.eye(4)
+    for i in range(5):
+        r = res[i]
+        pose = pose @ (r.transformation if r.converged and not r.final_error > 1.0 else np.eye(4))
+        assert np.allclose(chain[i + 1], pose, rtol=0, atol=1e-14)
+    assert np.all(np.isfinite(chain)) and np.array_equal(chain[0], np.eye(4))
+    assert len(engine.global_map(allpts, off, chain, 1.0)) > 1000
 
 
 # ------------------------------------------------------------------ fixtures produced by the reference's own sources
