@@ -437,7 +437,8 @@ __global__ void __launch_bounds__(256) k_vox_list(const VoxCloud* __restrict__ c
 // one thread per output voxel (sorted by key): centroid from the integer sums, or a request for the ordered sum
 __global__ void __launch_bounds__(256) k_vox_finalize(const u64* __restrict__ keys, const uint32_t* __restrict__ slots,
                                                       i64 m, double voxel, VoxelPack P, VoxSlot* __restrict__ table,
-                                                      double* __restrict__ out_xyz, i64* __restrict__ out_keys) {
+                                                      double* __restrict__ out_xyz, i64* __restrict__ out_keys,
+                                                      int* __restrict__ n_unproven) {
     const i64 v = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= m) return;
     const u64 k = keys[v];
@@ -456,6 +457,7 @@ __global__ void __launch_bounds__(256) k_vox_finalize(const u64* __restrict__ ke
         proven = proven && B < ((fl >> a) & 1u ? VQ_LIMIT_FINE : VQ_LIMIT_COARSE);
     }
     S->flags = proven ? 0u : (unsigned)(v + 1);
+    if (!proven) atomicAdd(n_unproven, 1);  // rare; lets the member collection skip its pass over all rows
     out_xyz[3 * v + 0] = __ddiv_rn((double)S->sx / VQ_SCALE, dc);  // file_utils.cpp:191
     out_xyz[3 * v + 1] = __ddiv_rn((double)S->sy / VQ_SCALE, dc);
     out_xyz[3 * v + 2] = __ddiv_rn((double)S->sz / VQ_SCALE, dc);
@@ -467,7 +469,9 @@ __global__ void __launch_bounds__(256) k_vox_collect(const VoxCloud* __restrict_
                                                      const int* __restrict__ tile_cloud, i64 n_tiles,
                                                      const unsigned* __restrict__ slot_of_point,
                                                      const VoxSlot* __restrict__ table, u64* __restrict__ list,
-                                                     int* __restrict__ list_n, int* __restrict__ flags) {
+                                                     int* __restrict__ list_n, int* __restrict__ flags,
+                                                     const int* __restrict__ n_unproven) {
+    if (*n_unproven == 0) return;  // every voxel was proven exact (always, for scans born as float32)
     for (i64 tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const VoxCloud C = clouds[tile_cloud[tile]];
         const i64 t0 = (tile - C.tile_off) * VTILE;
@@ -569,17 +573,18 @@ static int voxel_hashed_dev(Ctx* ctx, const PointSrc src, const i64* h_off, int 
     SB_TRY(arena_get(ctx, (size_t)(n_tiles > 0 ? n_tiles : 1), &d_tile_cloud));
     SB_TRY(arena_get(ctx, (size_t)n_slots, &d_table));
     SB_TRY(arena_get(ctx, (size_t)n, &d_slot_of));
-    SB_TRY(arena_get(ctx, (size_t)2 * n_clouds + 1, &d_nvox));
+    SB_TRY(arena_get(ctx, (size_t)2 * n_clouds + 2, &d_nvox));
     SB_TRY(arena_get(ctx, 6, &d_mm));
     SB_TRY(arena_get(ctx, (size_t)PATCH_CAP, &d_list));
     d_cursor = d_nvox + n_clouds;
     d_list_n = d_nvox + 2 * n_clouds;
+    int* d_unproven = d_nvox + 2 * n_clouds + 1;
     SB_TRY(table_upload(ctx, d_clouds, hc.data(), sizeof(VoxCloud) * n_clouds));
     SB_TRY(table_upload(ctx, d_tile_cloud, h_tile_cloud.data(), sizeof(int) * (size_t)n_tiles));
     trace_mark(ctx, "vox:begin");
     SB_LAUNCH(ctx, k_vox_clear, ceil_div(n_slots, 256), 256, 0, d_table, n_slots);
     trace_mark(ctx, "vox:clear");
-    SB_CUDA(ctx, cudaMemsetAsync(d_nvox, 0, sizeof(int) * (2 * (size_t)n_clouds + 1), ctx->stream));
+    SB_CUDA(ctx, cudaMemsetAsync(d_nvox, 0, sizeof(int) * (2 * (size_t)n_clouds + 2), ctx->stream));
     SB_CUDA(ctx, cudaMemsetAsync(ctx->d_flags, 0, sizeof(int), ctx->stream));
     i64 init[6] = {INT64_MAX, INT64_MAX, INT64_MAX, INT64_MIN, INT64_MIN, INT64_MIN};
     SB_CUDA(ctx, cudaMemcpyAsync(d_mm, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
@@ -661,10 +666,11 @@ static int voxel_hashed_dev(Ctx* ctx, const PointSrc src, const i64* h_off, int 
     trace_mark(ctx, "vox:list");
     SB_TRY(segmented_sort_pairs(ctx, ka, kb, va, vb, h_out_off, n_clouds, bx + by + bz, &ks, &vs));
     trace_mark(ctx, "vox:sort");
-    SB_LAUNCH(ctx, k_vox_finalize, ceil_div(m, 256), 256, 0, ks, vs, m, voxel, P, d_table, d_out_xyz, d_out_keys);
+    SB_LAUNCH(ctx, k_vox_finalize, ceil_div(m, 256), 256, 0, ks, vs, m, voxel, P, d_table, d_out_xyz, d_out_keys,
+              d_unproven);
     // ---- ordered re-summation of the voxels that could not be proven exact
     SB_LAUNCH(ctx, k_vox_collect, pgrid, 256, 0, d_clouds, d_tile_cloud, n_tiles, d_slot_of, d_table, d_list, d_list_n,
-              ctx->d_flags);
+              ctx->d_flags, d_unproven);
     SB_LAUNCH(ctx, k_vox_patch, 1, 1024, 0, src, d_list, d_list_n, d_out_xyz);
     trace_mark(ctx, "vox:finalize+patch");
     SB_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, ctx->d_flags, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
