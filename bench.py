@@ -400,8 +400,24 @@ def main():
             max_dt = max(max_dt, float(np.linalg.norm(dT[:3, 3])))
         cpu_baseline = {"value": n_cpu / cpu_dt, "unit": "pairs/s", "cores": 1, "kind": "port",
                         "sample": f"first {n_cpu} pairs of the same sequence, single thread, reference cost model "
-                                  "(NN search twice per iteration); reference binary not buildable (no Eigen)",
+                                  "(NN search twice per iteration); the reference's own sources build only over an "
+                                  "Eigen stand-in (oracle/_ref), a checker whose eager loops are not Eigen's speed",
                         "parity_max_translation_diff_m": max_dt}
+        try:  # for the record: the reference's own sources (oracle/_ref, Eigen stand-in) on the first two pairs
+            import ref_lib
+            if os.path.exists(ref_lib.SO):
+                rf = ref_lib.Reference()
+                t0 = time.perf_counter()
+                for i in range(2):
+                    a_ds = rf.voxel_downsample(scans[i + 1], VOXEL)
+                    b_ds = rf.voxel_downsample(scans[i], VOXEL)
+                    rf.sc_compute(a_ds)
+                    rr = rf.icp_point_to_plane(a_ds, b_ds)
+                cpu_baseline["reference_sources_over_eigen_standin"] = {
+                    "value": 2 / (time.perf_counter() - t0), "unit": "pairs/s", "cores": 1,
+                    "iterations_last_pair": rr["num_iterations"], "gpu_iterations_same_pair": int(res[1].num_iterations)}
+        except Exception as ex:
+            cpu_baseline["reference_sources_over_eigen_standin"] = {"error": repr(ex)}
 
         # ---- the other metrics BASELINE.json names, on their own configurations (short, device-resident, untimed
         # by the driver): C3 = k-NN (k=10) + normals on 128-beam scans at voxel 0.2; C4 = Scan Context search over a
