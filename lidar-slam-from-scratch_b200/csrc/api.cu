@@ -328,7 +328,7 @@ static int register_batch_impl(Ctx* ctx, PointSrc src, const void* h_raw, const 
     if (cfg->normals_k < 1 || cfg->normals_k > SB_MAX_K)
         return fail(ctx, SB_ERR_INVALID_ARG, "normals_k %d outside [1, %d]", cfg->normals_k, SB_MAX_K);
     // one tree + normals per distinct target cloud (icp.hpp:166-171); clouds that are only sources get a tree too
-    // (no normals): the ICP passes read every source in its own Morton order (PairDesc::src_pts)
+    // (no normals): the ICP passes read every source in its own curve order (PairDesc::src_pts)
     std::vector<char> is_tgt((size_t)n_clouds, 0), is_src((size_t)n_clouds, 0);
     for (int p = 0; p < n_pairs; ++p) { is_tgt[pair_tgt[p]] = 1; is_src[pair_src[p]] = 1; }
     std::vector<int> tree_of((size_t)n_clouds, -1);

@@ -194,7 +194,7 @@ int voxel_downsample_dev(Ctx* ctx, const double* d_xyz, const i64* h_off, int n_
                          double* d_out_xyz, i64* h_out_off, i64* d_out_keys);
 
 // ---------------------------------------------------------------------------------------------------------------
-// forest.cu — the spatial index: one implicit 32-ary bounding-box tree per cloud over Morton-sorted points
+// forest.cu — the spatial index: one implicit 32-ary bounding-box tree per cloud over points sorted along a space-filling curve (Hilbert)
 // ---------------------------------------------------------------------------------------------------------------
 #define SB_MAX_LEVELS 7
 
@@ -205,7 +205,7 @@ struct GridSlot;
 struct TreeDesc {      // device-resident, one per indexed cloud
     // The arrays of the batch of trees this tree was built with (forest_append): several batches can live in one
     // forest, e.g. one per uploaded chunk of clouds, so every tree carries its own base pointers.
-    const TreePoint* pts;   // Morton-sorted points
+    const TreePoint* pts;   // points in curve (Hilbert) order
     const float* boxes;     // 6 floats per box: lo xyz (rounded down), hi xyz (up)
     TreeNormal* nrm;        // per sorted point, filled by forest_normals
     NbrEntry* nbr;          // normals_k entries per sorted point, filled by forest_normals
@@ -231,7 +231,7 @@ struct GridSlot {
     int pad;
 };
 
-// One Morton-sorted point: exactly one 32-byte sector, so that a gathered candidate costs one sector and a leaf
+// One curve-sorted point: exactly one 32-byte sector, so that a gathered candidate costs one sector and a leaf
 // (32 consecutive points) is one coalesced 1 KB load.
 struct alignas(32) TreePoint {
     double x, y, z;
@@ -306,7 +306,7 @@ int make_items_dev(Ctx* ctx, const std::vector<QueryItem>& items, QueryItem** d_
 // icp.cu
 // ---------------------------------------------------------------------------------------------------------------
 struct PairDesc {      // device-resident, one per scan pair
-    const TreePoint* src_pts;  // the source cloud in ITS OWN Morton order (it is indexed too: forest tree src_tree):
+    const TreePoint* src_pts;  // the source cloud in ITS OWN curve order (it is indexed too: forest tree src_tree):
                                // neighbouring lanes then work on neighbouring points, and the order — hence the
                                // summation order — does not depend on what else is in the batch
     int n_src;

@@ -6,7 +6,7 @@
 //   KDTree::k_nearest                     kdtree.hpp:65-78, 144-180
 //   slam::estimate_normals                slam_viz/include/slam_viz/core/icp.hpp:23-67
 // The index is not a KD-tree: see traverse.cuh.  Build = per-cloud bounding box (exact atomic min/max on ordered
-// integers) -> 30-bit Morton codes -> segmented radix sort -> gather into SoA + leaf boxes -> upper box levels.
+// integers) -> 30-bit Hilbert-curve indices -> segmented radix sort -> gather into SoA + leaf boxes -> upper box levels.
 #include "traverse.cuh"
 
 #include <cstdlib>

@@ -5,7 +5,7 @@
 //     voxel key inside each cloud; stability keeps the members of a voxel in ascending input order so that the
 //     centroid sum has the reference's summation order;
 //   * spatial index (kdtree.hpp:87-110 in the reference is a recursive nth_element build): points are sorted by
-//     Morton code inside each cloud.
+//     space-filling-curve index (Hilbert) inside each cloud.
 // Segments (clouds) never mix: tiles do not cross segment boundaries and the digit histogram is laid out
 // [segment][digit][tile-in-segment], so one flat exclusive scan yields segment-local stable destinations.
 #include "common.cuh"
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(const u64* __rest
 // =============================================================================================================
 // one-CTA-per-segment sort in shared memory (segments of up to SEG_CAP rows, keys of up to 32 bits)
 // =============================================================================================================
-// A downsampled scan is 7-10 k rows: the tiled sort above spends five launches per digit on it (20 for a Morton
+// A downsampled scan is 7-10 k rows: the tiled sort above spends five launches per digit on it (20 for a 30-bit
 // code) and all of them are latency.  Here a CTA keeps the segment's keys and a 16-bit permutation in shared memory
 // and does every digit pass there: rank by __match_any inside each warp's contiguous block of rows (stable), one
 // block scan over the [digit][warp] counters, scatter of the permutation; keys and values move once, at the end.

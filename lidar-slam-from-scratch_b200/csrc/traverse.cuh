@@ -2,7 +2,7 @@
 //
 // Replaces the recursive KD-tree searches of the reference (slam_viz/include/slam_viz/core/kdtree.hpp:112-142
 // search_nearest and :144-180 search_k_nearest).  The index of one cloud is an implicit 32-ary tree of axis-aligned
-// boxes over the Morton-sorted points: level-0 box b bounds sorted points [32b, 32b+32), level-l box b bounds the
+// boxes over the curve-sorted (Hilbert) points: level-0 box b bounds sorted points [32b, 32b+32), level-l box b bounds the
 // level-(l-1) boxes [32b, 32b+32).  One warp answers one query: the 32 lanes test the 32 children of a node (one
 // coalesced 768-byte load), descend nearest-box-first, and evaluate the 32 points of a leaf with one coalesced
 // 32-byte load per lane (TreePoint).  A subtree is skipped only if a conservative lower bound of its squared distance is
@@ -222,7 +222,7 @@ struct KnnVisitor {
     // Seeds the list with up to 32 DISTINCT tree points (this lane's `pos`, cloud-local sorted position, or -1):
     // distances to the new query are evaluated and the 32 entries are put in (d2, idx) order across the warp.  The
     // seeds arrive in the order of the previous query's list, which is almost the order for this query (consecutive
-    // queries are neighbours on the Morton curve), so an odd-even transposition sort that stops as soon as a whole
+    // queries are neighbours on the space-filling curve), so an odd-even transposition sort that stops as soon as a whole
     // pass swaps nothing takes a few passes instead of the 15 stages of a full sorting network.  Any k distinct real
     // points bound the k-th nearest distance from above, so the result stays exact.
     __device__ __forceinline__ void seed(int pos) {
