@@ -271,3 +271,47 @@ def test_voxel_grid_scales_and_signs(oracle, ref, voxel, scale):
     o, _ = oracle.voxel_downsample(pts, voxel)
     r = ref.voxel_downsample(pts, voxel)
     assert np.array_equal(sort_rows(o), sort_rows(r))
+
+
+# ------------------------------------------------------------------ property-based (hypothesis), small sizes
+from hypothesis import given, settings, strategies as st  # noqa: E402
+from hypothesis.extra import numpy as hnp  # noqa: E402
+
+_coords = st.floats(min_value=-200.0, max_value=200.0, allow_nan=False, allow_infinity=False, width=32)
+
+
+@settings(max_examples=60, deadline=None)
+@given(pts=hnp.arrays(np.float32, st.tuples(st.integers(1, 120), st.just(3)), elements=_coords),
+       voxel=st.sampled_from([0.05, 0.2, 0.5, 1.0, 7.5]))
+def test_property_voxel_grid(pts, voxel):
+    """Any float32 cloud (duplicates, zeros, negative zero, denormals included): same voxel set, same centroids."""
+    o = _ORACLE.voxel_downsample(pts.astype(np.float64), voxel)[0]
+    r = _REF.voxel_downsample(pts.astype(np.float64), voxel)
+    assert np.array_equal(sort_rows(o), sort_rows(r))
+
+
+@settings(max_examples=60, deadline=None)
+@given(pts=hnp.arrays(np.float64, st.tuples(st.integers(1, 80), st.just(3)),
+                      elements=st.floats(-50, 50, allow_nan=False, allow_infinity=False)),
+       q=hnp.arrays(np.float64, st.tuples(st.integers(1, 20), st.just(3)),
+                    elements=st.floats(-60, 60, allow_nan=False, allow_infinity=False)),
+       k=st.integers(1, 32))
+def test_property_search_distances(pts, q, k):
+    """Arbitrary clouds (exact duplicates and ties allowed): nearest and k-nearest DISTANCES agree bit for bit; indices
+    agree wherever the distance is not shared with another point."""
+    ot, rt = _ORACLE.tree(pts), _REF.tree(pts)
+    oi, od = ot.nearest_batch(q)
+    ri, rd = rt.nearest_batch(q)
+    assert np.array_equal(od, rd)
+    d_all = ((pts[None, :, 0] - q[:, None, 0]) ** 2 + (pts[None, :, 1] - q[:, None, 1]) ** 2) + (pts[None, :, 2] - q[:, None, 2]) ** 2
+    unique_min = (d_all == d_all.min(axis=1, keepdims=True)).sum(axis=1) == 1
+    assert np.array_equal(oi[unique_min], ri[unique_min])
+    ok, okd = ot.k_nearest_batch(q, k)
+    rk = rt.k_nearest_batch(q, k)
+    m = min(k, len(pts))
+    rkd = np.take_along_axis(d_all, np.clip(rk[:, :m], 0, None), axis=1)
+    assert np.array_equal(okd[:, :m], rkd) and np.all(rk[:, m:] == -1) and np.all(ok[:, m:] == -1)
+
+
+_ORACLE = oracle_lib.Oracle()
+_REF = ref_lib.Reference() if ref_lib.available() else None
