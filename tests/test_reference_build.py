@@ -280,7 +280,7 @@ from hypothesis.extra import numpy as hnp  # noqa: E402
 _coords = st.floats(min_value=-200.0, max_value=200.0, allow_nan=False, allow_infinity=False, width=32)
 
 
-@settings(max_examples=60, deadline=None)
+@settings(max_examples=60, deadline=None, derandomize=True)
 @given(pts=hnp.arrays(np.float32, st.tuples(st.integers(1, 120), st.just(3)), elements=_coords),
        voxel=st.sampled_from([0.05, 0.2, 0.5, 1.0, 7.5]))
 def test_property_voxel_grid(pts, voxel):
@@ -290,7 +290,7 @@ def test_property_voxel_grid(pts, voxel):
     assert np.array_equal(sort_rows(o), sort_rows(r))
 
 
-@settings(max_examples=60, deadline=None)
+@settings(max_examples=60, deadline=None, derandomize=True)
 @given(pts=hnp.arrays(np.float64, st.tuples(st.integers(1, 80), st.just(3)),
                       elements=st.floats(-50, 50, allow_nan=False, allow_infinity=False)),
        q=hnp.arrays(np.float64, st.tuples(st.integers(1, 20), st.just(3)),
