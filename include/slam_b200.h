@@ -252,6 +252,29 @@ int sb_global_map(sb_ctx* ctx, const double* xyz, const int64_t* offsets, int32_
 int sb_odometry_poses(sb_ctx* ctx, const sb_icp_result* results, int32_t n, double max_error,
                       const double* initial_pose16, double* poses16_out);
 
+/* ---------------------------------------------------------------- pose-graph hand-off ----- */
+/* The pose graph itself (slam::PoseGraph, GTSAM) stays on the host and is not part of this library.  These two
+ * entries turn a batch of registration / loop-closure results into the factors process_frame hands to it one frame
+ * at a time, as plain records in the order the node would have produced them. */
+enum { SB_FACTOR_ODOMETRY = 0, SB_FACTOR_LOOP = 1 };
+typedef struct sb_pose_factor {
+    int32_t kind;          /* SB_FACTOR_ODOMETRY | SB_FACTOR_LOOP */
+    int32_t from;          /* odometry: frame i-1 (slam_node.cpp:145); loop: match_frame (slam_node.cpp:165) */
+    int32_t to;            /* odometry: frame i; loop: query_frame */
+    int32_t pad;
+    double relative[16];   /* row-major 4x4 transform from `from` to `to`, as PoseGraph::add* take it */
+    double fitness;        /* odometry: ICP final_error, passed as fitness_score; loop: icp_fitness */
+    double noise_scale;    /* odometry: 1 + 10 * fitness, the sigma multiplier of pose_graph.cpp:88; loop: 1 */
+} sb_pose_factor;
+/* results[i] = registration of frame first_frame+i+1 against frame first_frame+i.  relative = identity if the pair
+ * did not converge or final_error > max_error (slam_node.cpp:139-140; the node uses 1.0) — the fitness passed on is the
+ * result's final_error either way (slam_node.cpp:145).  out: n records.  Host arithmetic; ctx may be NULL. */
+int sb_odometry_factors(sb_ctx* ctx, const sb_icp_result* results, int32_t n, int32_t first_frame, double max_error,
+                        sb_pose_factor* out);
+/* Accepted loop closures (sb_loop_detect / sb_loop_verify_entries) -> addLoopClosure(match, query, transform)
+ * records (slam_node.cpp:163-167).  out: n records.  Host arithmetic; ctx may be NULL. */
+int sb_loop_factors(sb_ctx* ctx, const sb_loop_result* results, int32_t n, sb_pose_factor* out);
+
 /* ---------------------------------------------------------------- bench/test input generator --------------- */
 /* Synthetic 64/128-beam raycast straight into device memory (synth/lidar_synth.h).  boxes: host, n_boxes*6 floats;
  * poses: host, n_scans*3 doubles (x, y, yaw); d_xyz: device, n_scans*beams*azimuth_steps*3 doubles capacity;

@@ -1120,6 +1120,42 @@ int sb_odometry_poses(sb_ctx*, const sb_icp_result* results, int32_t n, double m
     return SB_OK;
 }
 
+// slam_node.cpp:139-145 for a batch: delta selection + the arguments of PoseGraph::addOdometryFactor
+int sb_odometry_factors(sb_ctx*, const sb_icp_result* results, int32_t n, int32_t first_frame, double max_error,
+                        sb_pose_factor* out) {
+    if (n < 0 || (n > 0 && (!results || !out))) return SB_ERR_INVALID_ARG;
+    static const double I16[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    for (int32_t i = 0; i < n; ++i) {
+        const sb_icp_result& R = results[i];
+        const bool keep = R.status == SB_OK && R.converged && !(R.final_error > max_error);
+        sb_pose_factor& f = out[i];
+        f.kind = SB_FACTOR_ODOMETRY;
+        f.from = first_frame + i;
+        f.to = first_frame + i + 1;
+        f.pad = 0;
+        memcpy(f.relative, keep ? R.transformation : I16, sizeof(I16));
+        f.fitness = R.final_error;
+        f.noise_scale = 1.0 + R.final_error * 10.0;  // pose_graph.cpp:88
+    }
+    return SB_OK;
+}
+
+// slam_node.cpp:163-167: addLoopClosure(lc.match_frame, lc.query_frame, lc.transform)
+int sb_loop_factors(sb_ctx*, const sb_loop_result* results, int32_t n, sb_pose_factor* out) {
+    if (n < 0 || (n > 0 && (!results || !out))) return SB_ERR_INVALID_ARG;
+    for (int32_t i = 0; i < n; ++i) {
+        sb_pose_factor& f = out[i];
+        f.kind = SB_FACTOR_LOOP;
+        f.from = results[i].match_frame;
+        f.to = results[i].query_frame;
+        f.pad = 0;
+        memcpy(f.relative, results[i].transform, sizeof(f.relative));
+        f.fitness = results[i].icp_fitness;
+        f.noise_scale = 1.0;
+    }
+    return SB_OK;
+}
+
 int sb_global_map(sb_ctx* ctx, const double* xyz, const int64_t* offsets, int32_t n_clouds, const double* poses16,
                   double voxel, double* out_xyz, int64_t* out_m) {
     if (!ctx || !offsets || n_clouds < 0 || !out_m) return SB_ERR_INVALID_ARG;

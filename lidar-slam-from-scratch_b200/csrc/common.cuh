@@ -206,6 +206,7 @@ struct TreeDesc {      // device-resident, one per indexed cloud
     // The arrays of the batch of trees this tree was built with (forest_append): several batches can live in one
     // forest, e.g. one per uploaded chunk of clouds, so every tree carries its own base pointers.
     const TreePoint* pts;   // points in curve (Hilbert) order
+    const float4* pts32;    // the same points as float32 offsets from glo (w unused): candidate PRE-FILTER only
     const float* boxes;     // 6 floats per box: lo xyz (rounded down), hi xyz (up)
     TreeNormal* nrm;        // per sorted point, filled by forest_normals
     NbrEntry* nbr;          // normals_k entries per sorted point, filled by forest_normals
@@ -256,6 +257,7 @@ struct ForestBatch {    // the arrays of the trees [t0, t0 + n_trees) appended t
     int t0 = 0, n_trees = 0;
     i64 n_points = 0, n_boxes = 0, n_slots = 0;
     TreePoint* pts = nullptr;
+    float4* pts32 = nullptr;
     float* boxes = nullptr;
     TreeNormal* normals = nullptr;
     NbrEntry* nbr = nullptr;

@@ -147,7 +147,8 @@ __global__ void __launch_bounds__(256) k_gather_leaves(const double* __restrict_
                                                        const Chunk* __restrict__ chunks,
                                                        const TreeDesc* __restrict__ trees,
                                                        const uint32_t* __restrict__ sorted_vals,
-                                                       TreePoint* __restrict__ pts, float* __restrict__ boxes) {
+                                                       TreePoint* __restrict__ pts, float4* __restrict__ pts32,
+                                                       float* __restrict__ boxes) {
     Chunk c = chunks[blockIdx.x];
     const TreeDesc& T = trees[c.tree];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -175,11 +176,17 @@ __global__ void __launch_bounds__(256) k_gather_leaves(const double* __restrict_
                 hi[a] = fmax(hi[a], shfl_d_xor(hi[a], o));
             }
         }
+        const float l0 = __double2float_rd(lo[0]), l1 = __double2float_rd(lo[1]), l2 = __double2float_rd(lo[2]);
+        // float32 offsets from the leaf box's lower corner (as stored: rounded down to float32), the coordinates of
+        // k_self_knn's approximate distances: a value is at most the leaf's extent, so its rounding error is
+        // 2^-24 of THAT, not of the coordinate itself
+        if (valid)
+            pts32[T.pt_off + j] = make_float4((float)(x - (double)l0), (float)(y - (double)l1), (float)(z - (double)l2), 0.f);
         if (lane == 0) {
             float* b = boxes + 6 * (T.box_off[0] + (c.start >> 5) + l);
-            b[0] = __double2float_rd(lo[0]);
-            b[1] = __double2float_rd(lo[1]);
-            b[2] = __double2float_rd(lo[2]);
+            b[0] = l0;
+            b[1] = l1;
+            b[2] = l2;
             b[3] = __double2float_ru(hi[0]);
             b[4] = __double2float_ru(hi[1]);
             b[5] = __double2float_ru(hi[2]);
@@ -225,7 +232,7 @@ void forest_free(Forest* f) {
     if (!f) return;
     if (!f->in_arena) {
         for (ForestBatch& B : f->batches) {
-            cudaFree(B.pts); cudaFree(B.boxes); cudaFree(B.normals); cudaFree(B.nbr); cudaFree(B.grid);
+            cudaFree(B.pts); cudaFree(B.pts32); cudaFree(B.boxes); cudaFree(B.normals); cudaFree(B.nbr); cudaFree(B.grid);
         }
         cudaFree(f->d_trees);
     }
@@ -306,13 +313,16 @@ int forest_append(Ctx* ctx, Forest* f, const double* d_xyz, const i64* h_off, co
     size_t npa = (size_t)(np > 0 ? np : 1), nba = (size_t)(nb > 0 ? nb : 1);
     if (f->in_arena) {
         SB_TRY(arena_get(ctx, npa, &B.pts));
+        SB_TRY(arena_get(ctx, npa, &B.pts32));
         SB_TRY(arena_get(ctx, 6 * nba, &B.boxes));
     } else {
         SB_CUDA(ctx, cudaMalloc(&B.pts, sizeof(TreePoint) * npa));
+        SB_CUDA(ctx, cudaMalloc(&B.pts32, sizeof(float4) * npa));
         SB_CUDA(ctx, cudaMalloc(&B.boxes, sizeof(float) * 6 * nba));
     }
     for (int t = 0; t < n_new; ++t) {
         f->h_trees[(size_t)(t0 + t)].pts = B.pts;
+        f->h_trees[(size_t)(t0 + t)].pts32 = B.pts32;
         f->h_trees[(size_t)(t0 + t)].boxes = B.boxes;
     }
     f->batches.push_back(B);
@@ -352,7 +362,7 @@ int forest_append(Ctx* ctx, Forest* f, const double* d_xyz, const i64* h_off, co
     SB_LAUNCH(ctx, k_morton, nch, 256, 0, d_xyz, d_src_off, d_chunks, d_bb, d_new, ka, va, hilbert);
     SB_LAUNCH(ctx, k_tree_bounds, ceil_div(n_new, 128), 128, 0, d_new, d_bb, n_new);
     SB_TRY(segmented_sort_pairs(ctx, ka, kb, va, vb, seg_off.data(), n_new, 30, &ks, &vs));
-    SB_LAUNCH(ctx, k_gather_leaves, nch, 256, 0, d_xyz, d_src_off, d_chunks, d_new, vs, B.pts, B.boxes);
+    SB_LAUNCH(ctx, k_gather_leaves, nch, 256, 0, d_xyz, d_src_off, d_chunks, d_new, vs, B.pts, B.pts32, B.boxes);
     for (int l = 1; l <= max_top; ++l) SB_LAUNCH(ctx, k_boxes_up, (unsigned)n_new, 256, 0, d_new, l, B.boxes);
     arena_release(ctx, mark);
     return SB_OK;
@@ -456,6 +466,53 @@ __device__ __forceinline__ void jacobi3(double (&A)[3][3], double (&w)[3], doubl
     w[0] = A[0][0]; w[1] = A[1][1]; w[2] = A[2][2];
 }
 
+// Normal of one sorted point from its m nearest neighbours (cloud-local sorted positions nb[0], nb[stride], ...,
+// ascending by (d2, idx), the point itself included): icp.hpp:34-63 in the oracle's operation order.  One thread.
+__device__ __forceinline__ void normal_of_point(const TreeDesc& T, const int* nb, int stride, int m, i64 ps,
+                                                TreeNormal* __restrict__ nrm_sorted, double* __restrict__ nrm_orig,
+                                                double* __restrict__ evals_orig) {
+    double n0 = 0.0, n1 = 0.0, n2 = 1.0, e0 = 0.0, e1 = 0.0, e2 = 0.0;
+    if (m >= 3) {  // icp.hpp:34-37
+        double c0 = 0.0, c1 = 0.0, c2 = 0.0;
+        for (int j = 0; j < m; ++j) {  // icp.hpp:40-44, neighbours ascending by (d2, idx)
+            TreePoint P = load_point(T.pts + T.pt_off + nb[j * stride]);
+            c0 += P.x; c1 += P.y; c2 += P.z;
+        }
+        double md = (double)m;
+        c0 /= md; c1 /= md; c2 /= md;
+        double C00 = 0, C01 = 0, C02 = 0, C11 = 0, C12 = 0, C22 = 0;
+        for (int j = 0; j < m; ++j) {  // icp.hpp:47-52
+            TreePoint P = load_point(T.pts + T.pt_off + nb[j * stride]);
+            double d0 = P.x - c0, d1 = P.y - c1, d2 = P.z - c2;
+            C00 += d0 * d0; C01 += d0 * d1; C02 += d0 * d2;
+            C11 += d1 * d1; C12 += d1 * d2; C22 += d2 * d2;
+        }
+        double A[3][3], w[3], V[3][3];
+        A[0][0] = C00 / md; A[0][1] = C01 / md; A[0][2] = C02 / md;
+        A[1][0] = A[0][1];  A[1][1] = C11 / md; A[1][2] = C12 / md;
+        A[2][0] = A[0][2];  A[2][1] = A[1][2];  A[2][2] = C22 / md;
+        jacobi3(A, w, V);
+        // eigenvector of the smallest eigenvalue, first index on ties (icp.hpp:56 col(0))
+        double v0 = V[0][0], v1 = V[1][0], v2 = V[2][0], ws = w[0];
+        if (w[1] < ws) { ws = w[1]; v0 = V[0][1]; v1 = V[1][1]; v2 = V[2][1]; }
+        if (w[2] < ws) { ws = w[2]; v0 = V[0][2]; v1 = V[1][2]; v2 = V[2][2]; }
+        if (v2 < 0.0) { v0 = -v0; v1 = -v1; v2 = -v2; }  // icp.hpp:59-61
+        double nn = sqrt((v0 * v0 + v1 * v1) + v2 * v2);  // icp.hpp:63
+        n0 = v0 / nn; n1 = v1 / nn; n2 = v2 / nn;
+        // ascending eigenvalues (diagnostic output)
+        e0 = w[0]; e1 = w[1]; e2 = w[2];
+        if (e1 < e0) { double t = e0; e0 = e1; e1 = t; }
+        if (e2 < e1) { double t = e1; e1 = e2; e2 = t; }
+        if (e1 < e0) { double t = e0; e0 = e1; e1 = t; }
+    }
+    TreeNormal Nn;
+    Nn.x = n0; Nn.y = n1; Nn.z = n2; Nn.pad = 0.0;
+    nrm_sorted[ps] = Nn;
+    i64 po = T.out_off + T.pts[ps].idx;
+    if (nrm_orig) { nrm_orig[3 * po + 0] = n0; nrm_orig[3 * po + 1] = n1; nrm_orig[3 * po + 2] = n2; }
+    if (evals_orig) { evals_orig[3 * po + 0] = e0; evals_orig[3 * po + 1] = e1; evals_orig[3 * po + 2] = e2; }
+}
+
 // largest s in [0, n) with off[s] <= x (off ascending, off[0] <= x)
 __device__ __forceinline__ int find_segment(const i64* __restrict__ off, int n, i64 x) {
     int lo = 0, hi = n;
@@ -541,55 +598,15 @@ __global__ void __launch_bounds__(QWARPS * 32) k_knn(ForestView F, const double*
         if (MODE == 1) {
             if (lane == 1 && spacing) atomicAdd(&spacing_acc[I.tree], spacing);  // integer: order-independent
             __syncwarp();
-            if (lane < I.count) {
-                const int* nb = s_nbr[warp][lane];
-                const int m = my_m;
-                double n0 = 0.0, n1 = 0.0, n2 = 1.0, e0 = 0.0, e1 = 0.0, e2 = 0.0;
-                if (m >= 3) {  // icp.hpp:34-37
-                    double c0 = 0.0, c1 = 0.0, c2 = 0.0;
-                    for (int j = 0; j < m; ++j) {  // icp.hpp:40-44, neighbours ascending by (d2, idx)
-                        TreePoint P = load_point(T.pts + T.pt_off + nb[j]);
-                        c0 += P.x; c1 += P.y; c2 += P.z;
-                    }
-                    double md = (double)m;
-                    c0 /= md; c1 /= md; c2 /= md;
-                    double C00 = 0, C01 = 0, C02 = 0, C11 = 0, C12 = 0, C22 = 0;
-                    for (int j = 0; j < m; ++j) {  // icp.hpp:47-52
-                        TreePoint P = load_point(T.pts + T.pt_off + nb[j]);
-                        double d0 = P.x - c0, d1 = P.y - c1, d2 = P.z - c2;
-                        C00 += d0 * d0; C01 += d0 * d1; C02 += d0 * d2;
-                        C11 += d1 * d1; C12 += d1 * d2; C22 += d2 * d2;
-                    }
-                    double A[3][3], w[3], V[3][3];
-                    A[0][0] = C00 / md; A[0][1] = C01 / md; A[0][2] = C02 / md;
-                    A[1][0] = A[0][1];  A[1][1] = C11 / md; A[1][2] = C12 / md;
-                    A[2][0] = A[0][2];  A[2][1] = A[1][2];  A[2][2] = C22 / md;
-                    jacobi3(A, w, V);
-                    // eigenvector of the smallest eigenvalue, first index on ties (icp.hpp:56 col(0))
-                    double v0 = V[0][0], v1 = V[1][0], v2 = V[2][0], ws = w[0];
-                    if (w[1] < ws) { ws = w[1]; v0 = V[0][1]; v1 = V[1][1]; v2 = V[2][1]; }
-                    if (w[2] < ws) { ws = w[2]; v0 = V[0][2]; v1 = V[1][2]; v2 = V[2][2]; }
-                    if (v2 < 0.0) { v0 = -v0; v1 = -v1; v2 = -v2; }  // icp.hpp:59-61
-                    double nn = sqrt((v0 * v0 + v1 * v1) + v2 * v2);  // icp.hpp:63
-                    n0 = v0 / nn; n1 = v1 / nn; n2 = v2 / nn;
-                    // ascending eigenvalues (diagnostic output)
-                    e0 = w[0]; e1 = w[1]; e2 = w[2];
-                    if (e1 < e0) { double t = e0; e0 = e1; e1 = t; }
-                    if (e2 < e1) { double t = e1; e1 = e2; e2 = t; }
-                    if (e1 < e0) { double t = e0; e0 = e1; e1 = t; }
-                }
-                i64 ps = T.pt_off + I.q_off + lane;
-                TreeNormal Nn;
-                Nn.x = n0; Nn.y = n1; Nn.z = n2; Nn.pad = 0.0;
-                nrm_sorted[ps] = Nn;
-                i64 po = T.out_off + T.pts[ps].idx;
-                if (nrm_orig) { nrm_orig[3 * po + 0] = n0; nrm_orig[3 * po + 1] = n1; nrm_orig[3 * po + 2] = n2; }
-                if (evals_orig) { evals_orig[3 * po + 0] = e0; evals_orig[3 * po + 1] = e1; evals_orig[3 * po + 2] = e2; }
-            }
+            if (lane < I.count)
+                normal_of_point(T, s_nbr[warp][lane], 1, my_m, T.pt_off + I.q_off + lane, nrm_sorted, nrm_orig, evals_orig);
             __syncwarp();
         }
     }
 }
+
+
+#include "selfknn.cuh"
 
 // ----- seed grid: cell size = 3 x the mean distance to the nearest other point, one representative point per cell
 __global__ void k_grid_params(TreeDesc* __restrict__ trees, const unsigned long long* __restrict__ spacing_acc,
@@ -713,9 +730,56 @@ int forest_normals(Ctx* ctx, Forest* f, int k, double* d_out_normals, double* d_
     SB_TRY(table_upload(ctx, d_tio, tio.data(), sizeof(i64) * tio.size()));
     SB_CUDA(ctx, cudaMemsetAsync(d_spacing, 0, sizeof(unsigned long long) * (size_t)B.n_trees, ctx->stream));
     SB_CUDA(ctx, cudaMemsetAsync(B.grid, 0xff, sizeof(GridSlot) * (size_t)B.n_slots, ctx->stream));
-    SB_LAUNCH(ctx, k_knn<1>, query_grid(ctx, n_items), QWARPS * 32, 0, view_of(f, B.t0), nullptr,
-              reinterpret_cast<const QueryItem*>(d_tio), n_items, k, nullptr, nullptr, B.normals, B.nbr, d_out_normals,
-              d_out_evals, B.n_trees, d_spacing);
+    // one lane per query (k_self_knn) for the k the pipelines use; SB_KNN_PACKET=0 or any other k: one warp per query
+    static const bool packet = !(getenv("SB_KNN_PACKET") && atoi(getenv("SB_KNN_PACKET")) == 0);
+    if (packet && (k == 20 || k == 10)) {
+        static const bool want_stats = getenv("SB_KNN_STATS") != nullptr;
+        static const int pcap = getenv("SB_KNN_PCAP") ? atoi(getenv("SB_KNN_PCAP")) : 48;
+        unsigned long long* d_stats = nullptr;
+        if (want_stats) {
+            SB_TRY(arena_get(ctx, (size_t)PS_N, &d_stats));
+            SB_CUDA(ctx, cudaMemsetAsync(d_stats, 0, sizeof(unsigned long long) * PS_N, ctx->stream));
+        }
+        static const int per_sm = getenv("SB_KNN_GRID") ? atoi(getenv("SB_KNN_GRID")) : 32;
+        i64 blocks = (n_items + PWARPS - 1) / PWARPS, cap = (i64)ctx->sm_count * per_sm;
+        const int grid = (int)(blocks < cap ? blocks : cap);
+        // queries the packet search leaves open (exact ties, float32 gaps): list + count for k_knn_redo
+        RedoEntry* d_redo;
+        int* d_redo_count;
+        SB_TRY(arena_get(ctx, (size_t)B.n_points, &d_redo));
+        SB_TRY(arena_get(ctx, (size_t)1, &d_redo_count));
+        SB_CUDA(ctx, cudaMemsetAsync(d_redo_count, 0, sizeof(int), ctx->stream));
+        auto launch = [&](auto kern, int cap_entries) -> int {
+            const int row = k | 1;
+            const size_t entries = (size_t)(32 * row > cap_entries * 32 ? 32 * row : cap_entries * 32);
+            const size_t smem = (size_t)PWARPS * entries * sizeof(int2);
+            SB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            SB_LAUNCH(ctx, kern, grid, PWARPS * 32, smem, view_of(f, B.t0), d_tio, n_items, B.n_trees, B.nbr, d_redo,
+                      d_redo_count, d_stats);
+            return SB_OK;
+        };
+#define SB_SELF_KNN(KK, CAP) (want_stats ? launch(k_self_knn<KK, 32, CAP, true>, CAP) : launch(k_self_knn<KK, 32, CAP, false>, CAP))
+        if (k == 20) SB_TRY(pcap >= 64 ? SB_SELF_KNN(20, 64) : SB_SELF_KNN(20, 48));
+        else SB_TRY(pcap >= 64 ? SB_SELF_KNN(10, 64) : SB_SELF_KNN(10, 48));
+#undef SB_SELF_KNN
+        SB_LAUNCH(ctx, k_knn_redo, ctx->sm_count * 8, QWARPS * 32, 0, view_of(f, B.t0), d_redo, d_redo_count, k, B.nbr);
+        SB_LAUNCH(ctx, k_normals_from_graph, (unsigned)((n_items * 32 + 255) / 256), 256, 0, view_of(f, B.t0), d_tio,
+                  n_items, B.n_trees, k, B.nbr, B.normals, d_out_normals, d_out_evals, d_spacing);
+        if (d_stats) {
+            unsigned long long h[PS_N];
+            SB_CUDA(ctx, cudaMemcpyAsync(h, d_stats, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+            SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            const double np = (double)(h[PS_PACKETS] ? h[PS_PACKETS] : 1);
+            fprintf(stderr, "[slam_b200] self-knn k=%d: %llu packets; per packet: leaves offered %.2f, scanned %.2f, candidates "
+                    "%.1f, kept/lane %.1f, flushes %.2f, rounds %.2f, merges %.2f, redo queries %.4f\n", k, h[PS_PACKETS],
+                    h[PS_LEAVES] / np, h[PS_SCANNED] / np, h[PS_CAND] / np, h[PS_APPENDED] / np / 32.0, h[PS_FLUSHES] / np,
+                    h[PS_ROUNDS] / np, h[PS_MERGES] / np, h[PS_REDO] / np);
+        }
+    } else {
+        SB_LAUNCH(ctx, k_knn<1>, query_grid(ctx, n_items), QWARPS * 32, 0, view_of(f, B.t0), nullptr,
+                  reinterpret_cast<const QueryItem*>(d_tio), n_items, k, nullptr, nullptr, B.normals, B.nbr, d_out_normals,
+                  d_out_evals, B.n_trees, d_spacing);
+    }
     // seed grid for icp.cu (cell size from the measured point spacing)
     SB_LAUNCH(ctx, k_grid_params, ceil_div(B.n_trees, 128), 128, 0, d_bt, d_spacing, B.n_trees);
     SB_LAUNCH(ctx, k_grid_build, (unsigned)((n_items * 32 + 255) / 256), 256, 0, view_of(f, B.t0), d_tio, n_items,

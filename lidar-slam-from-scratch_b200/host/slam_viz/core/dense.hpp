@@ -44,6 +44,23 @@ public:
     const T& operator()(long i) const { return v_[(size_t)i]; }
     T& operator[](long i) { return v_[(size_t)i]; }
     const T& operator[](long i) const { return v_[(size_t)i]; }
+    // row(i): a view of one row, just enough for PointCloud::row (types.hpp:36-37)
+    struct RowView {
+        T* p;
+        long stride, n;
+        T& operator()(long j) const { return p[j * stride]; }
+        long size() const { return n; }
+        long cols() const { return n; }
+    };
+    struct ConstRowView {
+        const T* p;
+        long stride, n;
+        const T& operator()(long j) const { return p[j * stride]; }
+        long size() const { return n; }
+        long cols() const { return n; }
+    };
+    RowView row(long i) { return RowView{&v_[index(i, 0)], Options == RowMajor ? 1 : rows_, cols_}; }
+    ConstRowView row(long i) const { return ConstRowView{&v_[index(i, 0)], Options == RowMajor ? 1 : rows_, cols_}; }
     static Matrix Zero() { return Matrix(); }
     static Matrix Identity() {
         Matrix m;

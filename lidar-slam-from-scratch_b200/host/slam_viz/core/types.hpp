@@ -27,6 +27,8 @@ public:
     Matrix& points() { return points_; }
     size_t size() const { return static_cast<size_t>(points_.rows()); }
     bool empty() const { return points_.rows() == 0; }
+    auto row(int i) const { return points_.row(i); }  // types.hpp:36-37
+    auto row(int i) { return points_.row(i); }
 
     Vector3 centroid() const {  // types.hpp:44-46
         Vector3 c;

@@ -58,6 +58,14 @@ class LoopResultC(C.Structure):
                 ("scan_context_distance", C.c_double), ("icp_fitness", C.c_double)]
 
 
+class PoseFactorC(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("from_", C.c_int32), ("to", C.c_int32), ("pad", C.c_int32),
+                ("relative", C.c_double * 16), ("fitness", C.c_double), ("noise_scale", C.c_double)]
+
+
+FACTOR_DTYPE = np.dtype([("kind", "<i4"), ("from", "<i4"), ("to", "<i4"), ("pad", "<i4"), ("relative", "<f8", (4, 4)),
+                         ("fitness", "<f8"), ("noise_scale", "<f8")])
+
 _P = C.c_void_p
 _D = C.POINTER(C.c_double)
 _I32 = C.POINTER(C.c_int32)
@@ -114,6 +122,8 @@ SYMBOLS = {
     "sb_loop_candidates_local": (C.c_int, [_P, _D, _I32, C.c_int32, _I32]),
     "sb_loop_verify_entries": (C.c_int, [_P, _I32, _D, C.c_int32, C.POINTER(LoopResultC), _I32]),
     "sb_odometry_poses": (C.c_int, [_P, C.POINTER(ICPResultC), C.c_int32, C.c_double, _D, _D]),
+    "sb_odometry_factors": (C.c_int, [_P, C.POINTER(ICPResultC), C.c_int32, C.c_int32, C.c_double, C.POINTER(PoseFactorC)]),
+    "sb_loop_factors": (C.c_int, [_P, C.POINTER(LoopResultC), C.c_int32, C.POINTER(PoseFactorC)]),
     "sb_default_grid_config": (None, [_P]),
     "sb_transform_clouds": (C.c_int, [_P, _D, _I64, C.c_int32, _D, _D]),
     "sb_occupancy_cells": (C.c_int, [_P, _D, _I64, C.c_int32, _D, _P, _I32, C.c_int64, _I64]),
@@ -327,6 +337,33 @@ class Engine:
         self._check(self.lib.sb_odometry_poses(self.h, rec.ctypes.data_as(C.POINTER(ICPResultC)), n, float(max_error),
                                                _dp(p0) if p0 is not None else None, _dp(out)))
         return out.reshape(n + 1, 4, 4)
+
+    def odometry_factors(self, results, first_frame=0, max_error=1.0):
+        """slam_node.cpp:139-145 for a batch: the (from, to, relative, fitness, noise scale) records the node hands to
+        PoseGraph::addOdometryFactor (pose_graph.cpp:81-117), as a structured array (FACTOR_DTYPE)."""
+        rec = np.ascontiguousarray(results.rec)
+        out = np.zeros(rec.shape[0], dtype=FACTOR_DTYPE)
+        self._check(self.lib.sb_odometry_factors(self.h, rec.ctypes.data_as(C.POINTER(ICPResultC)), rec.shape[0],
+                                                 int(first_frame), float(max_error),
+                                                 out.ctypes.data_as(C.POINTER(PoseFactorC))))
+        return out
+
+    def loop_factors(self, loop_results):
+        """slam_node.cpp:163-167: accepted loop closures (list of dicts as LoopClosureDetector.detect returns them, or a
+        ctypes array of LoopResultC) -> addLoopClosure(match, query, transform) records."""
+        if isinstance(loop_results, (list, tuple)):
+            arr = (LoopResultC * max(len(loop_results), 1))()
+            for i, r in enumerate(loop_results):
+                arr[i].query_frame, arr[i].match_frame = int(r["query_frame"]), int(r["match_frame"])
+                arr[i].transform[:] = list(np.asarray(r["transform"], dtype=np.float64).reshape(16))
+                arr[i].scan_context_distance = float(r["scan_context_distance"])
+                arr[i].icp_fitness = float(r["icp_fitness"])
+            n = len(loop_results)
+        else:
+            arr, n = loop_results, len(loop_results)
+        out = np.zeros(n, dtype=FACTOR_DTYPE)
+        self._check(self.lib.sb_loop_factors(self.h, arr, n, out.ctypes.data_as(C.POINTER(PoseFactorC))))
+        return out
 
     def transform_clouds(self, points, offsets, poses):
         pts, off = _f64(points, 3), np.ascontiguousarray(offsets, dtype=np.int64)

@@ -113,3 +113,40 @@ def test_odometry_pose_chain_host_only():
     assert lib.sb_odometry_poses(None, None, 0, 1.0, p0.ctypes.data_as(D), out.ctypes.data_as(D)) == 0
     assert np.array_equal(out[0], p0)
     assert lib.sb_odometry_poses(None, None, 3, 1.0, None, out.ctypes.data_as(D)) != 0   # results missing
+
+
+def test_pose_graph_factor_hand_off_host_only():
+    """sb_odometry_factors / sb_loop_factors are host arithmetic: the arguments process_frame passes
+    to PoseGraph::addOdometryFactor (slam_node.cpp:139-145; noise scale 1 + 10 * fitness, pose_graph.cpp:88) and to
+    addLoopClosure(match, query, transform) (slam_node.cpp:163-167)."""
+    import numpy as np
+    lib = slam_b200.load_library()
+    rng = np.random.default_rng(8)
+    n = 6
+    rec = np.zeros(n, dtype=slam_b200.ICP_DTYPE)
+    for i in range(n):
+        T = np.eye(4)
+        T[:3, 3] = rng.uniform(-1, 1, 3)
+        rec[i]["transformation"] = T.reshape(-1)
+        rec[i]["converged"] = 0 if i == 2 else 1
+        rec[i]["final_error"] = 1.25 if i == 4 else 0.1 * (i + 1)
+    out = np.zeros(n, dtype=slam_b200.FACTOR_DTYPE)
+    F = C.POINTER(slam_b200.PoseFactorC)
+    assert lib.sb_odometry_factors(None, rec.ctypes.data_as(C.POINTER(slam_b200.ICPResultC)), n, 10, 1.0,
+                                   out.ctypes.data_as(F)) == 0
+    for i in range(n):
+        assert (out[i]["kind"], out[i]["from"], out[i]["to"]) == (0, 10 + i, 11 + i)
+        want = np.eye(4) if i in (2, 4) else rec[i]["transformation"].reshape(4, 4)
+        assert np.array_equal(out[i]["relative"], want)
+        assert out[i]["fitness"] == rec[i]["final_error"]          # passed on even when the delta is replaced
+        assert out[i]["noise_scale"] == 1.0 + rec[i]["final_error"] * 10.0
+    loops = (slam_b200.LoopResultC * 2)()
+    for j, (q, m) in enumerate([(120, 7), (130, 12)]):
+        loops[j].query_frame, loops[j].match_frame, loops[j].icp_fitness = q, m, 0.05 * (j + 1)
+        loops[j].transform[:] = list(np.arange(16, dtype=float) + j)
+    lout = np.zeros(2, dtype=slam_b200.FACTOR_DTYPE)
+    assert lib.sb_loop_factors(None, loops, 2, lout.ctypes.data_as(F)) == 0
+    assert [(int(r["kind"]), int(r["from"]), int(r["to"])) for r in lout] == [(1, 7, 120), (1, 12, 130)]
+    assert np.array_equal(lout[1]["relative"].reshape(-1), np.arange(16, dtype=float) + 1)
+    assert list(lout["noise_scale"]) == [1.0, 1.0]
+    assert lib.sb_odometry_factors(None, None, 1, 0, 1.0, None) != 0   # invalid arguments are refused
