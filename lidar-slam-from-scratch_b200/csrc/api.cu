@@ -3,6 +3,7 @@
 // There is no CPU implementation of any stage behind these entry points.
 #include <chrono>
 #include <cstdarg>
+#include <limits>
 #include <functional>
 #include <cstdlib>
 #include <algorithm>
@@ -12,6 +13,7 @@
 struct sb_index {
     sb::Ctx* ctx = nullptr;
     sb::Forest forest;
+    std::vector<double> host_rows;  // the indexed cloud in ORIGINAL row order (find_correspondences), fetched once
 };
 
 namespace sb {
@@ -474,7 +476,7 @@ int sb_ctx_create(int device, void* stream, sb_ctx** out) {
     }
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return SB_ERR_NO_DEVICE;
-    if (prop.major < 10) return SB_ERR_NO_DEVICE;  // kernels are built for sm_100a only
+    if (prop.major != 10 || prop.minor != 0) return SB_ERR_NO_DEVICE;  // the library holds sm_100a SASS only, no PTX
     if (cudaSetDevice(device) != cudaSuccess) return SB_ERR_NO_DEVICE;
     sb_ctx* c = new sb_ctx();
     c->c.device = device;
@@ -490,6 +492,7 @@ int sb_ctx_create(int device, void* stream, sb_ctx** out) {
     }
     c->c.vox_force_sort = getenv("SB_VOXEL_SORT") != nullptr;
     if (cudaMalloc(&c->c.d_flags, sizeof(int)) != cudaSuccess) {
+        if (c->c.own_stream) cudaStreamDestroy(c->c.stream);
         delete c;
         return SB_ERR_CUDA;
     }
@@ -755,19 +758,29 @@ int sb_index_find_correspondences(sb_index* index, const double* source, int64_t
     std::vector<int32_t> idx((size_t)ns);
     std::vector<double> d2((size_t)ns);
     SB_TRY(sb_index_nearest_batch(index, source, ns, idx.data(), d2.data()));
-    // matched rows: gather from the device copy of the target (sorted SoA + original index)
+    // matched rows (kdtree.hpp:208-212): from a host copy of the indexed cloud in original row order, fetched from the
+    // device tree on the first call only — callers of the mirror's NearestNeighborSearch make this call once per
+    // ICP iteration
     Enter g(c);
     const Forest& F = index->forest;
-    i64 n = F.n_points;
-    std::vector<TreePoint> pts((size_t)n);
-    SB_TRY(download(c, pts.data(), F.batches[0].pts, sizeof(TreePoint) * n));
-    SB_CUDA(c, cudaStreamSynchronize(c->stream));
-    std::vector<int> pos_of((size_t)n);
-    for (i64 p = 0; p < n; ++p) pos_of[pts[p].idx] = (int)p;
-    for (i64 i = 0; i < ns; ++i) {  // kdtree.hpp:208-212
-        const TreePoint& P = pts[pos_of[idx[i]]];
-        matched_xyz[3 * i] = P.x; matched_xyz[3 * i + 1] = P.y; matched_xyz[3 * i + 2] = P.z;
-        if (distances) distances[i] = sqrt(d2[i]);
+    const i64 n = F.n_points;
+    if ((i64)index->host_rows.size() != 3 * n) {
+        std::vector<TreePoint> pts((size_t)n);
+        SB_TRY(download(c, pts.data(), F.batches[0].pts, sizeof(TreePoint) * n));
+        SB_CUDA(c, cudaStreamSynchronize(c->stream));
+        index->host_rows.assign((size_t)(3 * n), 0.0);
+        for (i64 p = 0; p < n; ++p) {
+            double* r = index->host_rows.data() + 3 * (size_t)pts[p].idx;
+            r[0] = pts[p].x; r[1] = pts[p].y; r[2] = pts[p].z;
+        }
+    }
+    const double nan = std::numeric_limits<double>::quiet_NaN();
+    for (i64 i = 0; i < ns; ++i) {
+        // a NaN query has no nearest neighbour (index -1, kdtree.hpp:125 never updates): NaN row, NaN distance
+        const bool hit = idx[i] >= 0 && idx[i] < n;
+        const double* r = hit ? index->host_rows.data() + 3 * (size_t)idx[i] : nullptr;
+        matched_xyz[3 * i] = hit ? r[0] : nan; matched_xyz[3 * i + 1] = hit ? r[1] : nan; matched_xyz[3 * i + 2] = hit ? r[2] : nan;
+        if (distances) distances[i] = hit ? sqrt(d2[i]) : nan;
     }
     return SB_OK;
 }

@@ -18,6 +18,8 @@
 // IcpJob, so the instantiated graph is reused by every call on the context.
 #include "traverse.cuh"
 
+#include <cooperative_groups.h>
+
 #include <cstdlib>
 
 namespace sb {
@@ -58,14 +60,15 @@ struct IcpJob {
     int nbr_k;
     int q_count;                // entries in `queue` (reset by k_icp_solve / k_icp_init)
     int n_act;                  // entries of act_pair
-    int pad;
+    int tail_pairs;             // the loop stops once this many pairs (or fewer) still iterate: k_icp_tail takes them
+    int passes;                 // batch passes run so far (launch accounting)
+    int pad2;
     i64 n_act_items;            // = act_off[n_act]
 };
 
 static constexpr int IWARPS = 8;
-static constexpr int NSUM = 28;
+static constexpr int NSUM = 29;      // 21 of J^T J, 6 of J^T r, sum r^2, and the number of points with a correspondence
 static constexpr int ITEM_Q = 32;   // source points per warp work item: one per lane
-static constexpr int WALK_GROUP = 1;  // neighbour-list entries whose candidate points are fetched together
 static constexpr int MAX_HOPS = 6;  // re-centrings of the neighbour-graph walk before the tree takes over
 
 // -------------------------------------------------------------------------------------------------------------
@@ -135,8 +138,9 @@ __global__ void __launch_bounds__(256) k_icp_init(IcpJob* __restrict__ job, cuda
         job->state[p] = s;
     }
     __syncthreads();
-    const bool loop = job->n_active > 0 && job->max_it > 0;
-    build_active(job, loop ? ST_ACTIVE : ST_EXHAUSTED);
+    // the batch passes run while more than tail_pairs pairs iterate; k_icp_tail finishes the rest
+    const bool loop = job->n_active > job->tail_pairs && job->max_it > 0;
+    build_active(job, ST_ACTIVE);
     if (threadIdx.x == 0) {
         job->q_count = 0;
         if (use_cond) cudaGraphSetConditional(cond, loop ? 1u : 0u);
@@ -229,6 +233,50 @@ __device__ __forceinline__ void accumulate_item(const IcpJob* __restrict__ job, 
 // best point IS the nearest neighbour (all bounds rounded conservatively in fp32, the candidates themselves compared
 // in the oracle's fp64 (d2, index) order).  If the list runs out first, re-centre on the best point and repeat.
 // Points whose walk ends without that proof are queued for k_icp_fallback.
+// The walk of one source point (one lane): cur = Tm * src, then the neighbour-graph walk from `center` (the previous
+// correspondence; < 0 or stale: the seed grid).  Returns the best target position found (-1: none) and whether it is
+// PROVEN to be the nearest neighbour.
+__device__ __forceinline__ void walk_lane(const TreeDesc& T, int K, const double* __restrict__ Tm,
+                                          const TreePoint* __restrict__ src_pt, int center, int& bpos, bool& cert,
+                                          double& cx, double& cy, double& cz) {
+    bpos = -1;
+    cert = false;
+    transform_point(Tm, reinterpret_cast<const double*>(src_pt), cx, cy, cz);
+    if (center < 0 || center >= T.n) center = grid_seed(T, cx, cy, cz);
+    if (center < 0) return;
+    const TreePoint* TP = T.pts + T.pt_off;
+    const NbrEntry* TN = T.nbr + T.pt_off * (i64)K;
+    TreePoint c = load_point(TP + center);
+    double bd = dist2_rn(c.x, c.y, c.z, cx, cy, cz);
+    int bidx = c.idx;
+    bpos = center;
+    if (!(bd == bd)) {  // NaN query: never matches (kdtree.hpp:125 strict <); the traversal returns -1 for it
+        bpos = -1;
+        return;
+    }
+    for (int hop = 0; hop < MAX_HOPS; ++hop) {
+        const float dc = sqrt_up(bd);  // |q centre|: the centre is the best point so far
+        float sb = dc;
+        const int2* L = reinterpret_cast<const int2*>(TN + (i64)center * K);
+        float rlast = 0.f;
+        for (int j = 0; j < K && !cert; ++j) {
+            const int2 e = __ldg(L + j);
+            rlast = __int_as_float(e.y);
+            if (e.x < 0 || __fsub_rd(rlast, dc) > sb) { cert = true; break; }
+            if (e.x == center) continue;
+            const TreePoint t = load_point(TP + e.x);
+            const double d = dist2_rn(t.x, t.y, t.z, cx, cy, cz);
+            if (d < bd || (d == bd && t.idx < bidx)) {
+                bd = d; bidx = t.idx; bpos = e.x;
+                sb = sqrt_up(bd);
+            }
+        }
+        if (!cert && __fsub_rd(rlast, dc) > sb) cert = true;  // list exhausted: the rest is >= r_{K-1}
+        if (cert || bpos == center) break;
+        center = bpos;
+    }
+}
+
 __global__ void __launch_bounds__(IWARPS * 32) k_icp_match(IcpJob* __restrict__ job) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const ForestView F = job->F;
@@ -248,54 +296,7 @@ __global__ void __launch_bounds__(IWARPS * 32) k_icp_match(IcpJob* __restrict__ 
         bool cert = false;
         double cx = 0, cy = 0, cz = 0;
         if (lane < count) {
-            transform_point(Tm, reinterpret_cast<const double*>(P.src_pts + s0 + lane), cx, cy, cz);
-            int center = job->match[it * ITEM_Q + lane];  // -1 before the first pass
-            if (center < 0 || center >= T.n) center = grid_seed(T, cx, cy, cz);
-            if (center >= 0) {
-                const TreePoint* TP = T.pts + T.pt_off;
-                const NbrEntry* TN = T.nbr + T.pt_off * (i64)K;
-                TreePoint c = load_point(TP + center);
-                double bd = dist2_rn(c.x, c.y, c.z, cx, cy, cz);
-                int bidx = c.idx;
-                bpos = center;
-                if (bd == bd) {
-                    for (int hop = 0; hop < MAX_HOPS; ++hop) {
-                        const float dc = sqrt_up(bd);  // |q centre|: the centre is the best point so far
-                        float sb = dc;
-                        const int2* L = reinterpret_cast<const int2*>(TN + (i64)center * K);
-                        float rlast = 0.f;
-                        // entries WALK_GROUP at a time: their candidate points are fetched together (speculatively — the
-                        // proof may arrive before all of them are needed) so that the walk waits for one memory round
-                        // trip per group instead of one per candidate; evaluation order is unchanged
-                        for (int j0 = 0; j0 < K && !cert; j0 += WALK_GROUP) {
-                            int2 e[WALK_GROUP];
-                            TreePoint t[WALK_GROUP];
-#pragma unroll
-                            for (int u = 0; u < WALK_GROUP; ++u) {
-                                e[u] = j0 + u < K ? __ldg(L + j0 + u) : make_int2(-1, 0x7f800000);
-                                if (e[u].x >= 0 && e[u].x != center) t[u] = load_point(TP + e[u].x);
-                            }
-#pragma unroll
-                            for (int u = 0; u < WALK_GROUP; ++u) {
-                                if (cert || j0 + u >= K) break;
-                                rlast = __int_as_float(e[u].y);
-                                if (e[u].x < 0 || __fsub_rd(rlast, dc) > sb) { cert = true; break; }
-                                if (e[u].x == center) continue;
-                                double d = dist2_rn(t[u].x, t[u].y, t[u].z, cx, cy, cz);
-                                if (d < bd || (d == bd && t[u].idx < bidx)) {
-                                    bd = d; bidx = t[u].idx; bpos = e[u].x;
-                                    sb = sqrt_up(bd);
-                                }
-                            }
-                        }
-                        if (!cert && __fsub_rd(rlast, dc) > sb) cert = true;  // list exhausted: the rest is >= r_{K-1}
-                        if (cert || bpos == center) break;
-                        center = bpos;
-                    }
-                } else {  // NaN query: never matches (kdtree.hpp:125 strict <); the traversal returns -1 for it
-                    bpos = -1;
-                }
-            }
+            walk_lane(T, K, Tm, P.src_pts + s0 + lane, job->match[it * ITEM_Q + lane], bpos, cert, cx, cy, cz);
             if (cert) job->match[it * ITEM_Q + lane] = bpos;
         }
         // queue the points without a proof (warp-aggregated append)
@@ -404,6 +405,12 @@ __device__ __forceinline__ void accumulate_item(const IcpJob* __restrict__ job, 
         for (int o = 16; o > 0; o >>= 1) v += shfl_d_xor(v, o);
         if (lane == 27) mine = v;
     }
+    {
+        double v = my_pos >= 0 ? 1.0 : 0.0;   // points with a correspondence (exact in any order)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += shfl_d_xor(v, o);
+        if (lane == 28) mine = v;
+    }
     if (lane < NSUM) job->partials[it * NSUM + lane] = mine;
 }
 
@@ -433,46 +440,45 @@ __global__ void __launch_bounds__(IWARPS * 32) k_icp_accum(const IcpJob* __restr
     }
 }
 
-// 6x6 SPD solve by LDL^T without pivoting (Eigen: pivoted LDLT, icp.hpp:120; oracle ldlt6_solve)
-__device__ __forceinline__ void ldlt6_solve(const double (&A)[6][6], const double (&b)[6], double (&x)[6]) {
-    double L[6][6], D[6];
-#pragma unroll
-    for (int j = 0; j < 6; ++j) {
-        double d = A[j][j];
-#pragma unroll
-        for (int k = 0; k < 6; ++k)
-            if (k < j) d -= L[j][k] * L[j][k] * D[k];
-        D[j] = d;
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-            if (i > j) {
-                double s = A[i][j];
-#pragma unroll
-                for (int k = 0; k < 6; ++k)
-                    if (k < j) s -= L[i][k] * L[j][k] * D[k];
-                L[i][j] = s / d;
-            }
+// 6x6 symmetric solve by LDL^T with diagonal pivoting (Eigen's (J^T J).ldlt().solve, icp.hpp:120; the oracle's
+// ldlt6_solve, same operation order): largest remaining diagonal entry first, symmetric swaps, and a pivot that is
+// exactly zero leaves its component at zero, so a rank-deficient J^T J (planar target, fewer than six points) gives
+// a finite step instead of 0/0.  One thread per pair and iteration runs this: the dynamically indexed arrays
+// may live in local memory.
+__device__ __noinline__ void ldlt6_solve(const double (&Ain)[6][6], const double (&bin)[6], double (&x)[6]) {
+    double a[6][6];
+    int perm[6];
+    for (int i = 0; i < 6; ++i) {
+        perm[i] = i;
+        for (int j = 0; j < 6; ++j) a[i][j] = Ain[i][j];
+    }
+    for (int k = 0; k < 6; ++k) {
+        int p = k;
+        double best = fabs(a[k][k]);
+        for (int i = k + 1; i < 6; ++i)
+            if (fabs(a[i][i]) > best) { best = fabs(a[i][i]); p = i; }
+        if (p != k) {
+            for (int j = 0; j < 6; ++j) { double t = a[k][j]; a[k][j] = a[p][j]; a[p][j] = t; }
+            for (int i = 0; i < 6; ++i) { double t = a[i][k]; a[i][k] = a[i][p]; a[i][p] = t; }
+            int t = perm[k]; perm[k] = perm[p]; perm[p] = t;
         }
+        const double d = a[k][k];
+        if (d == 0.0) continue;
+        for (int i = k + 1; i < 6; ++i) a[i][k] /= d;
+        for (int i = k + 1; i < 6; ++i)
+            for (int j = k + 1; j <= i; ++j) {
+                a[i][j] -= a[i][k] * d * a[j][k];
+                a[j][i] = a[i][j];
+            }
     }
     double y[6];
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-        double s = b[i];
-#pragma unroll
-        for (int k = 0; k < 6; ++k)
-            if (k < i) s -= L[i][k] * y[k];
-        y[i] = s;
-    }
-#pragma unroll
-    for (int i = 0; i < 6; ++i) y[i] /= D[i];
-#pragma unroll
-    for (int i = 5; i >= 0; --i) {
-        double s = y[i];
-#pragma unroll
-        for (int k = 0; k < 6; ++k)
-            if (k > i) s -= L[k][i] * x[k];
-        x[i] = s;
-    }
+    for (int i = 0; i < 6; ++i) y[i] = bin[perm[i]];
+    for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < i; ++j) y[i] -= a[i][j] * y[j];
+    for (int i = 0; i < 6; ++i) y[i] = a[i][i] == 0.0 ? 0.0 : y[i] / a[i][i];
+    for (int i = 5; i >= 0; --i)
+        for (int j = i + 1; j < 6; ++j) y[i] -= a[j][i] * y[j];
+    for (int i = 0; i < 6; ++i) x[perm[i]] = y[i];
 }
 
 // x -> 4x4 row-major delta (icp.hpp:123-144)
@@ -520,108 +526,143 @@ __device__ __forceinline__ void mat4_mul(const double (&A)[16], const double* B,
         }
 }
 
-// mode 0: loop body (icp.hpp:181-232) for the pairs of the active list; mode 1: final error (icp.hpp:235-255).
-// One block per pair: warp w adds the partials of the items w, w+8, w+16, ... in that order, warp 0 adds the eight
-// warp sums in warp order — a fixed association, so the result is run-to-run and batch-composition independent.
-__global__ void __launch_bounds__(256) k_icp_solve(IcpJob* __restrict__ job, int mode, cudaGraphConditionalHandle cond,
-                                                   int use_cond) {
-    __shared__ double s_part[8][32];
+// One pair, one block of 256 threads.  mode 0: the end of a loop iteration (icp.hpp:198-232: error, convergence test,
+// Gauss-Newton step); mode 1: the final error (icp.hpp:235-255).  Warp w adds the partials of the items w, w+8,
+// w+16, ... in that order, warp 0 adds the eight warp sums in warp order — a fixed association, so the result is
+// run-to-run, batch-composition and code-path independent (k_icp_solve and k_icp_tail both call this).
+// The partials are read past L1 (__ldcg): in k_icp_tail other CTAs of the cluster rewrote them since the last pass.
+__device__ __forceinline__ void solve_pair(IcpJob* __restrict__ job, int p, int mode, double (&s_part)[8][32]) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int n_loop = mode == 0 ? job->n_act : job->n_pairs;
-    for (int a = blockIdx.x; a < n_loop; a += gridDim.x) {
-        const int p = mode == 0 ? job->act_pair[a] : a;
-        const PairState st = job->state[p];  // block-uniform
-        sb_icp_result& R = job->results[p];
-        if (mode == 1) {
-            if (st.state == ST_CONVERGED) {
-                if (threadIdx.x == 0) {  // broke out of the loop: the final pass repeats the last error (Appendix A.5)
-                    double e = R.error_history[R.history_len - 1];
-                    R.final_error = e;
-                    R.error_history[R.history_len] = e;
-                    R.history_len += 1;
-                    R.num_iterations = R.history_len - 1;  // icp.hpp:255
-                    job->state[p].state = ST_DONE;
-                }
-                continue;
-            }
-            if (st.state != ST_EXHAUSTED) continue;
-        } else if (st.state != ST_ACTIVE) {
-            continue;
-        }
-        const PairDesc P = job->pairs[p];
-        {
-            double s = 0.0;
-            if (lane < NSUM) {
-                const double* base = job->partials + P.item_off * NSUM + lane;
-                int i = warp;
-                for (; i + 24 < P.n_items; i += 32) {  // four loads in flight, additions in item order
-                    const double v0 = base[(i64)i * NSUM], v1 = base[(i64)(i + 8) * NSUM],
-                                 v2 = base[(i64)(i + 16) * NSUM], v3 = base[(i64)(i + 24) * NSUM];
-                    s += v0; s += v1; s += v2; s += v3;
-                }
-                for (; i < P.n_items; i += 8) s += base[(i64)i * NSUM];
-            }
-            __syncthreads();  // the previous pair's sums have been consumed
-            s_part[warp][lane] = s;
-            __syncthreads();
-        }
-        if (warp != 0) continue;
-        double s = 0.0;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) s += s_part[w][lane];
-        double sr2 = shfl_d(s, 27);
-        double e = sqrt(sr2 / (double)P.n_src);  // icp.hpp:198-207
-        if (mode == 1) {
-            if (lane == 0) {
+    PairState st;
+    st.prev_error = __ldcg(&job->state[p].prev_error);
+    st.state = __ldcg(&job->state[p].state);
+    st.iter = __ldcg(&job->state[p].iter);
+    sb_icp_result& R = job->results[p];
+    if (mode == 1) {
+        if (st.state == ST_CONVERGED) {
+            if (threadIdx.x == 0) {  // broke out of the loop: the final pass repeats the last error (Appendix A.5)
+                double e = R.error_history[R.history_len - 1];
                 R.final_error = e;
                 R.error_history[R.history_len] = e;
                 R.history_len += 1;
-                R.num_iterations = R.history_len - 1;
+                R.num_iterations = R.history_len - 1;  // icp.hpp:255
                 job->state[p].state = ST_DONE;
             }
-            continue;
+            return;
         }
-        double A[6][6], g[6];
-        {
-            int t = 0;
-#pragma unroll
-            for (int a2 = 0; a2 < 6; ++a2)
-#pragma unroll
-                for (int c = a2; c < 6; ++c) {
-                    double v = shfl_d(s, t);
-                    A[a2][c] = v;
-                    A[c][a2] = v;
-                    ++t;
-                }
-#pragma unroll
-            for (int a2 = 0; a2 < 6; ++a2) g[a2] = shfl_d(s, 21 + a2);
+        if (st.state != ST_EXHAUSTED) return;
+    } else if (st.state != ST_ACTIVE) {
+        return;
+    }
+    const PairDesc P = job->pairs[p];
+    {
+        double s = 0.0;
+        if (lane < NSUM) {
+            const double* base = job->partials + P.item_off * NSUM + lane;
+            int i = warp;
+            for (; i + 24 < P.n_items; i += 32) {  // four loads in flight, additions in item order
+                const double v0 = __ldcg(base + (i64)i * NSUM), v1 = __ldcg(base + (i64)(i + 8) * NSUM),
+                             v2 = __ldcg(base + (i64)(i + 16) * NSUM), v3 = __ldcg(base + (i64)(i + 24) * NSUM);
+                s += v0; s += v1; s += v2; s += v3;
+            }
+            for (; i < P.n_items; i += 8) s += __ldcg(base + (i64)i * NSUM);
         }
+        __syncthreads();  // the previous pair's sums have been consumed
+        s_part[warp][lane] = s;
+        __syncthreads();
+    }
+    if (warp != 0) return;
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += s_part[w][lane];
+    double sr2 = shfl_d(s, 27);
+    const double n_match = shfl_d(s, 28);
+    double e = sqrt(sr2 / (double)P.n_src);  // icp.hpp:198-207
+    if (mode == 1) {
         if (lane == 0) {
-            int hl = R.history_len;
-            R.error_history[hl] = e;  // icp.hpp:207
-            R.history_len = hl + 1;
-            if (e < job->min_err || fabs(st.prev_error - e) < job->tol) {  // icp.hpp:210-217
-                R.converged = 1;
-                job->state[p].state = ST_CONVERGED;
+            if (n_match == 0.0) { R.status = SB_ERR_RANGE; R.converged = 0; }  // see the loop pass below
+            R.final_error = e;
+            R.error_history[R.history_len] = e;
+            R.history_len += 1;
+            R.num_iterations = R.history_len - 1;
+            job->state[p].state = ST_DONE;
+        }
+        return;
+    }
+    double A[6][6], g[6];
+    {
+        int t = 0;
+#pragma unroll
+        for (int a2 = 0; a2 < 6; ++a2)
+#pragma unroll
+            for (int c = a2; c < 6; ++c) {
+                double v = shfl_d(s, t);
+                A[a2][c] = v;
+                A[c][a2] = v;
+                ++t;
+            }
+#pragma unroll
+        for (int a2 = 0; a2 < 6; ++a2) g[a2] = shfl_d(s, 21 + a2);
+    }
+    if (lane == 0) {
+        int hl = R.history_len;
+        R.error_history[hl] = e;  // icp.hpp:207
+        R.history_len = hl + 1;
+        if (n_match == 0.0) {
+            // not one source point has a nearest neighbour (every query or every target coordinate is NaN:
+            // kdtree.hpp:125 never updates): the sums are empty and e = 0 would pass for convergence
+            R.status = SB_ERR_RANGE;
+            R.converged = 0;
+            R.final_error = e;
+            R.num_iterations = R.history_len - 1;
+            job->state[p].state = ST_DONE;
+            atomicSub(&job->n_active, 1);
+        } else if (e < job->min_err || fabs(st.prev_error - e) < job->tol) {  // icp.hpp:210-217
+            R.converged = 1;
+            job->state[p].state = ST_CONVERGED;
+            atomicSub(&job->n_active, 1);
+        } else {
+            double x[6], Dm[16], Tn[16];
+            ldlt6_solve(A, g, x);
+            delta_from_x(x, Dm);
+            mat4_mul(Dm, R.transformation, Tn);  // total = delta * total, icp.hpp:229
+            bool finite = true;
+#pragma unroll
+            for (int i = 0; i < 12; ++i) finite = finite && (fabs(Tn[i]) <= 1.7976931348623157e308);
+            PairState ns;
+            ns.prev_error = e;
+            ns.iter = st.iter + 1;
+            ns.state = ST_ACTIVE;
+            if (!finite) {
+                // NaN / Inf in the sums (non-finite input coordinates): the reference would carry the NaN on and
+                // compare it against the tolerances; here the pair stops, unconverged, with a status to say why
+                R.status = SB_ERR_RANGE;
+                R.converged = 0;
+                R.final_error = e;
+                R.num_iterations = R.history_len - 1;
+                ns.state = ST_DONE;
                 atomicSub(&job->n_active, 1);
             } else {
-                double x[6], Dm[16], Tn[16];
-                ldlt6_solve(A, g, x);
-                delta_from_x(x, Dm);
-                mat4_mul(Dm, R.transformation, Tn);  // total = delta * total, icp.hpp:229
 #pragma unroll
                 for (int i = 0; i < 16; ++i) R.transformation[i] = Tn[i];
-                PairState ns;
-                ns.prev_error = e;
-                ns.iter = st.iter + 1;
-                ns.state = ST_ACTIVE;
                 if (ns.iter >= job->max_it) {
                     ns.state = ST_EXHAUSTED;
                     atomicSub(&job->n_active, 1);
                 }
-                job->state[p] = ns;
             }
+            job->state[p] = ns;
         }
+    }
+}
+
+// mode 0: loop body for the pairs of the active list; mode 1: final error of every pair.  One block per pair.
+__global__ void __launch_bounds__(256) k_icp_solve(IcpJob* __restrict__ job, int mode, cudaGraphConditionalHandle cond,
+                                                   int use_cond) {
+    __shared__ double s_part[8][32];
+    const int n_loop = mode == 0 ? job->n_act : job->n_pairs;
+    for (int a = blockIdx.x; a < n_loop; a += gridDim.x) {
+        const int p = mode == 0 ? job->act_pair[a] : a;
+        solve_pair(job, p, mode, s_part);
     }
     if (mode == 0) {
         // last block to finish decides whether the WHILE node runs another iteration
@@ -636,16 +677,91 @@ __global__ void __launch_bounds__(256) k_icp_solve(IcpJob* __restrict__ job, int
         if (s_last) {  // every other block's state updates are visible now
             __threadfence();
             const int active = *reinterpret_cast<volatile int*>(&job->n_active);
-            // next pass: the pairs still iterating, or — once none is left — the final error pass of the pairs that
-            // ran out of iterations (icp.hpp:235-252)
-            build_active(job, active > 0 ? ST_ACTIVE : ST_EXHAUSTED);
+            // next pass: the pairs still iterating (the loop hands the last few to k_icp_tail)
+            build_active(job, ST_ACTIVE);
             if (threadIdx.x == 0) {
                 job->ticket = 0;
                 job->q_count = 0;
-                if (use_cond) cudaGraphSetConditional(cond, active > 0 ? 1u : 0u);
+                job->passes += 1;
+                if (use_cond) cudaGraphSetConditional(cond, active > job->tail_pairs ? 1u : 0u);
             }
         }
     }
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// k_icp_tail — the pairs still iterating once only a few are left (and every pair of a small batch, e.g. the one pair
+// of sb_icp_point_to_plane): one thread-block CLUSTER per pair runs the whole loop of that pair on the device.
+// A pass over the last 3 % of the pairs is latency: four launches of near-empty grids, ~70 us, 38 times for the C2
+// batch.  Pairs are independent, so nothing needs a grid-wide barrier — only a pair-wide one: TAIL_CTAS x 8 warps take
+// the pair's work items (walk, tree fallback in place, accumulate), cluster.sync(), CTA 0 does the solve, cluster.sync().
+// Same device functions and the same summation association as the batch passes: identical bits.
+// -------------------------------------------------------------------------------------------------------------
+static constexpr int TAIL_CTAS = 8;
+
+__global__ void __cluster_dims__(TAIL_CTAS, 1, 1) __launch_bounds__(256) k_icp_tail(IcpJob* __restrict__ job) {
+    __shared__ WarpStack stacks[8];
+    __shared__ TreeDesc s_tree;
+    __shared__ double s_T[12];
+    __shared__ double s_part[8][32];
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int crank = (int)cluster.block_rank();
+    const int n_clusters = (int)gridDim.x / TAIL_CTAS, cid = (int)blockIdx.x / TAIL_CTAS;
+    const ForestView F = job->F;
+    const int K = job->nbr_k;
+    const int n_act = job->n_act;
+    WarpStack& S = stacks[warp];
+    for (int a = cid; a < n_act; a += n_clusters) {
+        const int pair = job->act_pair[a];
+        const PairDesc P = job->pairs[pair];
+        __syncthreads();
+        {
+            const int* src = reinterpret_cast<const int*>(&F.trees[P.tree]);
+            int* dst = reinterpret_cast<int*>(&s_tree);
+            for (int i = threadIdx.x; i < (int)(sizeof(TreeDesc) / 4); i += 256) dst[i] = src[i];
+        }
+        __syncthreads();
+        const TreeDesc& T = s_tree;
+        while (__ldcg(&job->state[pair].state) == ST_ACTIVE) {   // the same value in every thread of the cluster
+            // this pass's transformation, past L1 (CTA 0 of the cluster rewrote it after the previous pass)
+            if (threadIdx.x < 12) s_T[threadIdx.x] = __ldcg(&job->results[pair].transformation[threadIdx.x]);
+            __syncthreads();
+            for (int li = crank * 8 + warp; li < P.n_items; li += 8 * TAIL_CTAS) {
+                const i64 it = P.item_off + li;
+                const int s0 = li * ITEM_Q;
+                const int count = P.n_src - s0 < ITEM_Q ? P.n_src - s0 : ITEM_Q;
+                int bpos = -1;
+                bool cert = false;
+                double cx = 0, cy = 0, cz = 0;
+                if (lane < count) walk_lane(T, K, s_T, P.src_pts + s0 + lane, job->match[it * ITEM_Q + lane], bpos, cert, cx, cy, cz);
+                // points without a proof: the exact tree traversal, right here, one after the other
+                unsigned todo = __ballot_sync(0xffffffffu, lane < count && !cert);
+                while (todo) {
+                    const int j = __ffs(todo) - 1;
+                    todo &= todo - 1u;
+                    const double qx = shfl_d(cx, j), qy = shfl_d(cy, j), qz = shfl_d(cz, j);
+                    const int seed = __shfl_sync(0xffffffffu, bpos, j);
+                    NearestVisitor V(F, T, qx, qy, qz, lane);
+                    V.seed(seed);
+                    traverse(F, T, qx, qy, qz, S, V, lane);
+                    if (lane == j) bpos = V.best_pos;
+                }
+                if (lane < count) job->match[it * ITEM_Q + lane] = bpos;
+                accumulate_item(job, T, it, lane, lane < count ? bpos : -1, cx, cy, cz);
+            }
+            cluster.sync();   // every partial of the pair is written (release/acquire at cluster scope)
+            if (crank == 0) solve_pair(job, pair, 0, s_part);
+            cluster.sync();   // the new transformation and state are visible
+        }
+    }
+}
+
+// one block: the list of pairs that ran out of iterations, for the final error pass (icp.hpp:235-252)
+__global__ void __launch_bounds__(256) k_icp_prepare_final(IcpJob* __restrict__ job) {
+    build_active(job, ST_EXHAUSTED);
+    if (threadIdx.x == 0) job->q_count = 0;
 }
 
 // solve_point_to_plane on explicit correspondences (icp.hpp:89-144): one block, fixed-order reduction
@@ -718,7 +834,7 @@ struct IcpGraph {
     IcpJob* d_job = nullptr;
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
-    int iter_grid = 0, solve_grid = 0;
+    int iter_grid = 0, solve_grid = 0, tail_grid = 0, tail_pairs = 0;
     unsigned long long* d_stats = nullptr;  // SB_ICP_STATS=1: per iteration bucket [queries, queued for the tree]
 };
 
@@ -778,17 +894,22 @@ static int add_pass(Ctx* ctx, IcpGraph* G, cudaGraph_t g, const cudaGraphNode_t*
     return SB_OK;
 }
 
-static int icp_graph_get(Ctx* ctx, IcpGraph** out) {
-    if (ctx->icp_graph) {
-        *out = static_cast<IcpGraph*>(ctx->icp_graph);
-        return SB_OK;
-    }
-    IcpGraph* G = new IcpGraph();
-    ctx->icp_graph = G;
-    *out = G;
+static void icp_graph_destroy(IcpGraph* G) {
+    if (G->exec) cudaGraphExecDestroy(G->exec);
+    if (G->graph) cudaGraphDestroy(G->graph);
+    cudaFree(G->d_stats);
+    cudaFree(G->d_job);
+    delete G;
+}
+
+static int icp_graph_build(Ctx* ctx, IcpGraph* G) {
     SB_CUDA(ctx, cudaMalloc(&G->d_job, sizeof(IcpJob)));
     G->iter_grid = ctx->sm_count * (getenv("SB_ICP_GRID") ? atoi(getenv("SB_ICP_GRID")) : 32);
     G->solve_grid = ctx->sm_count * 4;
+    // SB_ICP_TAIL: hand the loop to k_icp_tail once this many pairs (or fewer) still iterate; 0: never
+    G->tail_pairs = getenv("SB_ICP_TAIL") ? atoi(getenv("SB_ICP_TAIL")) : 64;
+    if (G->tail_pairs < 0) G->tail_pairs = 0;
+    G->tail_grid = TAIL_CTAS * (G->tail_pairs > 0 ? (G->tail_pairs < 64 ? G->tail_pairs : 64) : 1);
     if (getenv("SB_ICP_STATS")) {
         SB_CUDA(ctx, cudaMalloc(&G->d_stats, 8 * sizeof(unsigned long long)));
         SB_CUDA(ctx, cudaMemset(G->d_stats, 0, 8 * sizeof(unsigned long long)));
@@ -812,8 +933,32 @@ static int icp_graph_get(Ctx* ctx, IcpGraph** out) {
     SB_CUDA(ctx, cudaGraphAddNode(&n_while, G->graph, &n_init, 1, &wp));
     cudaGraph_t body = wp.conditional.phGraph_out[0];
     SB_TRY(add_pass(ctx, G, body, nullptr, 0, cond, 1, &n_body_last));       // icp.hpp:181-232
-    SB_TRY(add_pass(ctx, G, G->graph, &n_while, 1, cond, 0, &n_final));      // icp.hpp:235-255
+    cudaGraphNode_t n_tail, n_prep;
+    {
+        void* args[] = {&job};
+        SB_TRY(add_kernel(ctx, G->graph, &n_tail, &n_while, (void*)k_icp_tail, G->tail_grid, 256, args));
+        SB_TRY(add_kernel(ctx, G->graph, &n_prep, &n_tail, (void*)k_icp_prepare_final, 1, 256, args));
+    }
+    SB_TRY(add_pass(ctx, G, G->graph, &n_prep, 1, cond, 0, &n_final));       // icp.hpp:235-255
     SB_CUDA(ctx, cudaGraphInstantiate(&G->exec, G->graph, 0));
+    return SB_OK;
+}
+
+// The loop graph of the context, built on first use.  It is cached only once it is complete: a failure on the way
+// (no conditional-node support in the driver, out of memory) is reported and leaves nothing half-built behind.
+static int icp_graph_get(Ctx* ctx, IcpGraph** out) {
+    if (ctx->icp_graph) {
+        *out = static_cast<IcpGraph*>(ctx->icp_graph);
+        return SB_OK;
+    }
+    IcpGraph* G = new IcpGraph();
+    const int s = icp_graph_build(ctx, G);
+    if (s != SB_OK) {
+        icp_graph_destroy(G);
+        return s;
+    }
+    ctx->icp_graph = G;
+    *out = G;
     return SB_OK;
 }
 
@@ -890,6 +1035,7 @@ int icp_batch(Ctx* ctx, const Forest* f, const std::vector<PairDesc>& pairs_in, 
     job.n_active = cfg->max_iterations > 0 ? n_valid : 0;
     job.ticket = 0;
     job.q_count = 0;
+    job.tail_pairs = G->tail_pairs;
     SB_CUDA(ctx, cudaMemcpyAsync(G->d_job, &job, sizeof(job), cudaMemcpyHostToDevice, ctx->stream));
     if (G->exec) {
         SB_CUDA(ctx, cudaGraphLaunch(G->exec, ctx->stream));
@@ -897,17 +1043,19 @@ int icp_batch(Ctx* ctx, const Forest* f, const std::vector<PairDesc>& pairs_in, 
         cudaGraphConditionalHandle none = 0;
         SB_LAUNCH(ctx, k_icp_init, 1, 256, 0, G->d_job, none, 0);
         for (int it = 0; it < cfg->max_iterations; ++it) {
+            if ((it & 3) == 0) {  // the graph decides after every pass; looking every fourth pass gives the same results
+                int active = 0;
+                SB_CUDA(ctx, cudaMemcpyAsync(&active, &G->d_job->n_active, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+                SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                if (active <= G->tail_pairs) break;
+            }
             SB_LAUNCH(ctx, k_icp_match, G->iter_grid, IWARPS * 32, 0, G->d_job);
             SB_LAUNCH(ctx, k_icp_fallback, G->iter_grid, IWARPS * 32, 0, G->d_job);
             SB_LAUNCH(ctx, k_icp_accum, G->iter_grid, IWARPS * 32, 0, G->d_job);
             SB_LAUNCH(ctx, k_icp_solve, G->solve_grid, 256, 0, G->d_job, 0, none, 0);
-            if ((it & 3) == 3) {
-                int active = 0;
-                SB_CUDA(ctx, cudaMemcpyAsync(&active, &G->d_job->n_active, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-                SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-                if (active <= 0) break;
-            }
         }
+        SB_LAUNCH(ctx, k_icp_tail, G->tail_grid, 256, 0, G->d_job);
+        SB_LAUNCH(ctx, k_icp_prepare_final, 1, 256, 0, G->d_job);
         SB_LAUNCH(ctx, k_icp_match, G->iter_grid, IWARPS * 32, 0, G->d_job);
         SB_LAUNCH(ctx, k_icp_fallback, G->iter_grid, IWARPS * 32, 0, G->d_job);
         SB_LAUNCH(ctx, k_icp_accum, G->iter_grid, IWARPS * 32, 0, G->d_job);
@@ -915,11 +1063,13 @@ int icp_batch(Ctx* ctx, const Forest* f, const std::vector<PairDesc>& pairs_in, 
     }
     if (after_launch && *after_launch) SB_TRY((*after_launch)());
     SB_CUDA(ctx, cudaMemcpyAsync(results, d_res, sizeof(sb_icp_result) * n_pairs, cudaMemcpyDeviceToHost, ctx->stream));
+    int passes = 0;
+    SB_CUDA(ctx, cudaMemcpyAsync(&passes, &G->d_job->passes, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     int max_hist = 1;
     for (int p = 0; p < n_pairs; ++p)
         if (results[p].history_len > max_hist) max_hist = results[p].history_len;
-    if (G->exec) ctx->launches += 5 + 4 * (i64)(max_hist - 1);  // init + 4 per loop pass + 4 of the final pass
+    if (G->exec) ctx->launches += 7 + 4 * (i64)passes;  // init + 4 per batch pass + tail + prepare + 4 of the final pass
     ctx->last_icp_iterations = max_hist;
     return SB_OK;
 }

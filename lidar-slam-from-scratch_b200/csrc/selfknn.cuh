@@ -43,6 +43,23 @@ static constexpr int PWARPS = 4;   // warps per CTA
 // SB_KNN_STATS=1 (debugging aid): per-launch totals printed by forest_normals
 enum { PS_PACKETS, PS_LEAVES, PS_SCANNED, PS_CAND, PS_APPENDED, PS_FLUSHES, PS_ROUNDS, PS_MERGES, PS_REDO, PS_N };
 
+// Shared memory through 32-bit shared-window addresses: with a generic pointer kept in a struct the compiler
+// re-derives the window base (S2R SR_CgaCtaId ...) at every access — 9 of the 22 instructions per scanned candidate.
+__device__ __forceinline__ void sts64(unsigned addr, int a, int b) {
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b));
+}
+__device__ __forceinline__ void sts32(unsigned addr, int a) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(a)); }
+__device__ __forceinline__ int2 lds64(unsigned addr) {
+    int2 v;
+    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ int lds32(unsigned addr) {
+    int v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
 __device__ __forceinline__ void ce_asc(float& a, int& pa, float& b, int& pb) {  // afterwards a <= b (no NaNs)
     const bool sw = b < a;
     const float lo = fminf(a, b), hi = fmaxf(a, b);
@@ -89,16 +106,16 @@ struct PacketVisitor {
     const TreeDesc& T;
     const int lane;
     const int own_p0;
-    int2* const buf;           // shared: buf[slot * 32 + lane] = (key bits, position)
+    const unsigned buf;        // shared-window address of this lane's column: entry `slot` at buf + slot * 256 = (key bits, position)
     double qx, qy, qz;         // this lane's query (NaN for lanes without one: nothing is ever kept)
     float xk[TOT];             // [0, KL): the list's keys, ascending; [KL, TOT): the batch being merged
     int xp[TOT];               // positions (cloud-local, sorted order)
     float U;                   // key of entry K-1: an upper bound of the K-th nearest d2 (+inf until K points are known)
     float U_warp;              // max over lanes
-    float beta_max;            // largest beta of any leaf this lane scanned
+    float beta_max;            // largest beta of any leaf this lane KEPT a candidate of
     int cnt;                   // buffered candidates of this lane
     unsigned st[STATS ? PS_N : 1];
-    __device__ __forceinline__ PacketVisitor(const TreeDesc& t, int l, int p0, int2* b) : T(t), lane(l), own_p0(p0), buf(b) {}
+    __device__ __forceinline__ PacketVisitor(const TreeDesc& t, int l, int p0, unsigned b) : T(t), lane(l), own_p0(p0), buf(b) {}
     __device__ __forceinline__ double tau() const { return (double)U_warp; }
     __device__ __forceinline__ void refresh_bounds() {
         U = xk[K - 1];
@@ -114,7 +131,6 @@ struct PacketVisitor {
         S = fmaxf(S, fmaxf(fmaxf(__fsub_ru(b1.y, b0.x), __fsub_ru(b2.x, b0.y)), __fsub_ru(b2.y, b1.x)));
         const float a = __fmul_ru(S, 2.386520565e-07f);          // 2^-22 (1 + 2^-10), rounded up
         beta = __fmul_ru(__fmul_ru(a, a), 1572868.0f);           // 3 * 2^19 + 4
-        beta_max = fmaxf(beta_max, beta);                        // (NaN offsets: fmaxf keeps the number)
     }
     __device__ __forceinline__ void init(bool valid, double x, double y, double z) {
         const double nan_ = __longlong_as_double(0x7ff8000000000000LL);
@@ -131,8 +147,8 @@ struct PacketVisitor {
     // candidates [p0, p0 + n) of one leaf
     __device__ __forceinline__ void scan_leaf(int p0, int n, float ox, float oy, float oz, float beta) {
         const float4* __restrict__ c = T.pts32 + T.pt_off + p0;
-        int2* w = buf + cnt * 32 + lane;
-        int added = 0;
+        unsigned w = buf + (unsigned)cnt * 256u;
+        const unsigned w0 = w;
         const float thr = U;
 #pragma unroll 8
         for (int i = 0; i < n; ++i) {
@@ -141,11 +157,13 @@ struct PacketVisitor {
             const float d = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx));
             const float lo = __fmaf_rd(d, SB_RHO_DN, -beta);
             if (lo <= thr) {   // false for NaN
-                w[added * 32] = make_int2(__float_as_int(__fmaf_ru(d, SB_RHO_UP, beta)), p0 + i);
-                ++added;
+                sts64(w, __float_as_int(__fmaf_ru(d, SB_RHO_UP, beta)), p0 + i);
+                w += 256u;
             }
         }
+        const int added = (int)((w - w0) >> 8);
         cnt += added;
+        if (added) beta_max = fmaxf(beta_max, beta);   // only candidates that were kept enter condition (ii)
         if (STATS) { st[PS_SCANNED]++; st[PS_CAND] += n; st[PS_APPENDED] += added; }
     }
     // merges the buffered candidates into the sorted list, NB at a time
@@ -161,7 +179,7 @@ struct PacketVisitor {
                 float key = inf;
                 int p = -1;
                 if (slot >= 0) {
-                    const int2 e = buf[slot * 32 + lane];
+                    const int2 e = lds64(buf + (unsigned)slot * 256u);
                     // a candidate can only enter the K+1 list if its key is below the list's last key
                     if (__int_as_float(e.x) < xk[KL - 1]) { key = __int_as_float(e.x); p = e.y; fresh = true; }
                 }
@@ -242,7 +260,7 @@ struct RedoEntry {
 };
 
 template <int K, int TOT, int PCAP, bool STATS>
-__global__ void __launch_bounds__(PWARPS * 32) k_self_knn(ForestView F, const i64* __restrict__ tio, i64 n_items,
+__global__ void __launch_bounds__(PWARPS * 32, 4) k_self_knn(ForestView F, const i64* __restrict__ tio, i64 n_items,
                                                           int n_trees, NbrEntry* __restrict__ nbr_sorted,
                                                           RedoEntry* __restrict__ redo_list, int* __restrict__ redo_count,
                                                           unsigned long long* __restrict__ stats) {
@@ -252,8 +270,9 @@ __global__ void __launch_bounds__(PWARPS * 32) k_self_knn(ForestView F, const i6
     __shared__ WarpStack stacks[PWARPS];
     __shared__ TreeDesc s_tree[PWARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // candidate buffer during the search, then the packet's result rows
-    int2* const rows = reinterpret_cast<int2*>(s_dyn) + (size_t)warp * ENTRIES;
+    // candidate buffer during the search (entry `slot` of lane l at + (slot * 32 + l) * 8), then the packet's result
+    // rows (entry j of query l at + (l * ROW + j) * 8); always addressed through the shared window (sts64 / lds64)
+    const unsigned rows = (unsigned)__cvta_generic_to_shared(s_dyn) + (unsigned)warp * (unsigned)(ENTRIES * 8);
     WarpStack& S = stacks[warp];
     for (i64 it = (i64)blockIdx.x * PWARPS + warp; it < n_items; it += (i64)gridDim.x * PWARPS) {
         const int t = find_segment(tio, n_trees, it);
@@ -269,7 +288,7 @@ __global__ void __launch_bounds__(PWARPS * 32) k_self_knn(ForestView F, const i6
         }
         bool ok = false;
         if (T.gext < 1.0e15) {   // finite, moderate extent (false for NaN too): the float32 error bounds cannot overflow
-            PacketVisitor<K, TOT, PCAP, STATS> V(T, lane, q_off, rows);
+            PacketVisitor<K, TOT, PCAP, STATS> V(T, lane, q_off, rows + (unsigned)lane * 8u);
             V.init(lane < count, mx, my, mz);
             V.scan_own(count);
             const float2* b = reinterpret_cast<const float2*>(T.boxes + 6 * (T.box_off[0] + (q_off >> 5)));
@@ -291,16 +310,18 @@ __global__ void __launch_bounds__(PWARPS * 32) k_self_knn(ForestView F, const i6
             double prev = -1.0;
             int m = 0;
 #pragma unroll
-            for (int j = 0; j < K; ++j) rows[lane * ROW + j] = make_int2(V.xp[j], 0x7f800000);
+            const unsigned my_row = rows + (unsigned)(lane * ROW) * 8u;
+#pragma unroll
+            for (int j = 0; j < K; ++j) sts64(my_row + 8u * j, V.xp[j], 0x7f800000);
 #pragma unroll 1
             for (int j = 0; j < K; ++j) {   // rolled on purpose (code size): the positions come back from shared memory
-                const int p = rows[lane * ROW + j].x;
+                const int p = lds32(my_row + 8u * j);
                 if (p >= 0) {
                     const TreePoint P = load_point(TP + p);
                     const double D = dist2_rn(P.x, P.y, P.z, V.qx, V.qy, V.qz);
                     ok = ok && (D > prev);
                     prev = D;
-                    rows[lane * ROW + j].y = __float_as_int(__fmul_rd(__fsqrt_rd(__double2float_rd(D)), 0.999999f));
+                    sts32(my_row + 8u * j + 4u, __float_as_int(__fmul_rd(__fsqrt_rd(__double2float_rd(D)), 0.999999f)));
                     ++m;
                 }
             }
@@ -333,7 +354,7 @@ __global__ void __launch_bounds__(PWARPS * 32) k_self_knn(ForestView F, const i6
         // rewritten by k_knn_redo
         if (T.gext < 1.0e15) {
             int2* out = reinterpret_cast<int2*>(nbr_sorted + (T.pt_off + q_off) * (i64)K);
-            for (int e = lane; e < count * K; e += 32) out[e] = rows[(e / K) * ROW + (e % K)];
+            for (int e = lane; e < count * K; e += 32) out[e] = lds64(rows + (unsigned)((e / K) * ROW + (e % K)) * 8u);
         }
         __syncwarp();
     }

@@ -362,32 +362,45 @@ static void apply_rt(const double T[16], double* pts, int n) {
     }
 }
 
-// 6x6 SPD solve by LDL^T without pivoting (Eigen: pivoted LDLT, icp.hpp:120).
+// 6x6 symmetric solve by LDL^T with diagonal pivoting, the decomposition behind (J^T J).ldlt().solve(J^T b)
+// (icp.hpp:120).  At every step the largest remaining diagonal entry becomes the pivot (first one on ties), rows and
+// columns are swapped symmetrically, and a pivot that is exactly zero leaves its component of the solution at
+// zero — the behaviour of Eigen's LDLT on a rank-deficient J^T J (a planar target: every normal (0, 0, 1); fewer
+// than six points), where an unpivoted factorisation divides 0 by 0.  Same operation order as csrc/icp.cu.
 static void ldlt6_solve(const double Ain[6][6], const double bin[6], double x[6]) {
-    double L[6][6] = {{0}}, D[6];
-    for (int j = 0; j < 6; ++j) {
-        double d = Ain[j][j];
-        for (int k = 0; k < j; ++k) d -= L[j][k] * L[j][k] * D[k];
-        D[j] = d;
-        L[j][j] = 1.0;
-        for (int i = j + 1; i < 6; ++i) {
-            double s = Ain[i][j];
-            for (int k = 0; k < j; ++k) s -= L[i][k] * L[j][k] * D[k];
-            L[i][j] = s / d;
+    double a[6][6];
+    int perm[6];
+    for (int i = 0; i < 6; ++i) {
+        perm[i] = i;
+        for (int j = 0; j < 6; ++j) a[i][j] = Ain[i][j];
+    }
+    for (int k = 0; k < 6; ++k) {
+        int p = k;
+        double best = std::fabs(a[k][k]);
+        for (int i = k + 1; i < 6; ++i)
+            if (std::fabs(a[i][i]) > best) { best = std::fabs(a[i][i]); p = i; }
+        if (p != k) {
+            for (int j = 0; j < 6; ++j) { double t = a[k][j]; a[k][j] = a[p][j]; a[p][j] = t; }
+            for (int i = 0; i < 6; ++i) { double t = a[i][k]; a[i][k] = a[i][p]; a[i][p] = t; }
+            int t = perm[k]; perm[k] = perm[p]; perm[p] = t;
         }
+        const double d = a[k][k];
+        if (d == 0.0) continue;
+        for (int i = k + 1; i < 6; ++i) a[i][k] /= d;  // column k of L
+        for (int i = k + 1; i < 6; ++i)
+            for (int j = k + 1; j <= i; ++j) {
+                a[i][j] -= a[i][k] * d * a[j][k];
+                a[j][i] = a[i][j];
+            }
     }
     double y[6];
-    for (int i = 0; i < 6; ++i) {
-        double s = bin[i];
-        for (int k = 0; k < i; ++k) s -= L[i][k] * y[k];
-        y[i] = s;
-    }
-    for (int i = 0; i < 6; ++i) y[i] /= D[i];
-    for (int i = 5; i >= 0; --i) {
-        double s = y[i];
-        for (int k = i + 1; k < 6; ++k) s -= L[k][i] * x[k];
-        x[i] = s;
-    }
+    for (int i = 0; i < 6; ++i) y[i] = bin[perm[i]];
+    for (int i = 0; i < 6; ++i)  // L y = P b
+        for (int j = 0; j < i; ++j) y[i] -= a[i][j] * y[j];
+    for (int i = 0; i < 6; ++i) y[i] = a[i][i] == 0.0 ? 0.0 : y[i] / a[i][i];  // D z = y
+    for (int i = 5; i >= 0; --i)  // L^T w = z
+        for (int j = i + 1; j < 6; ++j) y[i] -= a[j][i] * y[j];
+    for (int i = 0; i < 6; ++i) x[perm[i]] = y[i];
 }
 
 // solve_point_to_plane — icp.hpp:89-144

@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -q --tb=short --timeout 600 -p no:cacheprovider -x > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest exit $?" >> gpurun_out/pytest_gpu.log; tail -15 gpurun_out/pytest_gpu.log
-for v in ${VARIANTS:-48 64 0}; do
+for v in ${VARIANTS:-48}; do
   if [ "$v" = "0" ]; then export SB_KNN_PACKET=0; else export SB_KNN_PACKET=1 SB_KNN_PCAP=$v; fi
   timeout 600 python bench.py --frames 1000 --steps 3 --warmup 3 --no-e2e --cpu-seconds 0.1 > gpurun_out/knn_v_$v.log 2>&1
   echo "variant=$v exit $?"; python - <<PY

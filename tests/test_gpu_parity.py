@@ -332,6 +332,46 @@ def test_icp_config_variants(engine, oracle, small_pair):
     check_icp(g, oracle.icp_point_to_plane(b, a, T0=T0))
 
 
+@pytest.mark.gpu
+def test_icp_rank_deficient_cases(engine, oracle, small_pair):
+    """J^T J exactly singular (icp.hpp:120: Eigen's pivoted ldlt() leaves the unconstrained components at zero): a planar
+    target whose normals are all (0, 0, 1), and fewer than six source points.  The step must stay finite and equal
+    the oracle's; nothing may be reported as converged with a NaN pose."""
+    from test_reference_build import planar_pair
+    src, tgt = planar_pair()
+    g = engine.icp_point_to_plane(src, tgt)
+    o = oracle.icp_point_to_plane(src, tgt)
+    assert np.all(np.isfinite(g.transformation))
+    check_icp(g, o)
+    assert np.max(np.abs(g.transformation - o["transformation"])) < 1e-12
+    # four source points: rank <= 4 with rounding-noise pivots, an ill-posed step (the oracle and the reference build
+    # already take different paths there) — the result must be finite and flagged OK, no more can be asked
+    few = small_pair["b"][[10, 500, 900, 1500]]
+    g = engine.icp_point_to_plane(few, small_pair["a"])
+    assert g.status == 0 and np.all(np.isfinite(g.transformation)) and np.all(np.isfinite(g.error_history))
+    # the same two pairs inside a batch
+    pts = np.vstack([src, tgt, few, small_pair["a"]])
+    off = np.cumsum([0, len(src), len(tgt), len(few), len(small_pair["a"])]).astype(np.int64)
+    res = engine.register_batch(pts, off, [0, 2], [1, 3])
+    check_icp(res[0], o)
+    assert res[1].status == 0 and np.all(np.isfinite(res[1].transformation))
+
+
+@pytest.mark.gpu
+def test_icp_without_any_correspondence_is_not_reported_converged(engine, small_pair):
+    """Every source coordinate NaN: no query has a nearest neighbour (kdtree.hpp:125 never updates), the sums are
+    empty and the RMS error is 0 — which must not pass for convergence (a NaN-free identity 'result' with
+    final_error 0 would be accepted by the pose chain, slam_node.cpp:139-140, and by detect(), loop_closure.hpp:112)."""
+    bad = np.full((50, 3), np.nan)
+    pts = np.vstack([bad, small_pair["a"], small_pair["b"]])
+    off = np.cumsum([0, len(bad), len(small_pair["a"]), len(small_pair["b"])]).astype(np.int64)
+    res = engine.register_batch(pts, off, [0, 2], [1, 1])
+    assert res[0].status != 0 and res[0].converged == 0
+    assert res[1].status == 0 and res[1].converged == 1      # the healthy pair of the same batch is untouched
+    poses = engine.odometry_poses(res)
+    assert np.array_equal(poses[1], np.eye(4))               # the failed pair contributes the identity
+
+
 def test_icp_empty_is_an_error(engine, small_pair):
     import slam_b200
     with pytest.raises(slam_b200.SlamB200Error) as e:

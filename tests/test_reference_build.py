@@ -151,6 +151,40 @@ def test_icp_loop_matches(oracle, ref, small_pair, cfg):
     assert np.linalg.norm(dT[:3, 3]) < 1e-8 and rot_angle(dT[:3, :3]) < 1e-8
 
 
+def planar_pair(n_side=24, dz=0.15):
+    """A target whose every normal is exactly (0, 0, 1) (points on z = 0) and a source lifted off it: J^T J has rank 3
+    with exact zeros on its diagonal — the case where an unpivoted LDL^T divides 0 by 0 (icp.hpp:120 uses Eigen's
+    pivoted ldlt(), which leaves those components at zero)."""
+    g = np.arange(n_side, dtype=np.float64) * 0.5
+    xx, yy = np.meshgrid(g, g + 0.125 * (g % 1.0))
+    tgt = np.stack([xx.ravel(), yy.ravel(), np.zeros(xx.size)], axis=1)
+    src = tgt[::3] + np.array([0.05, -0.03, dz])
+    return src, tgt
+
+
+def test_icp_rank_deficient_planar_target(oracle, ref):
+    src, tgt = planar_pair()
+    o = oracle.icp_point_to_plane(src, tgt)
+    r = ref.icp_point_to_plane(src, tgt)
+    assert np.all(np.isfinite(r["transformation"])) and np.all(np.isfinite(o["transformation"]))
+    assert o["num_iterations"] == r["num_iterations"] and o["converged"] == r["converged"] == 1
+    assert np.allclose(o["error_history"], r["error_history"], rtol=0, atol=1e-12)
+    assert np.max(np.abs(o["transformation"] - r["transformation"])) < 1e-12
+    # only what the plane constrains moves: z translation (and x/y rotation), nothing in the plane
+    assert abs(o["transformation"][2, 3] + 0.15) < 1e-9 and np.allclose(o["transformation"][:2, 3], 0.0, atol=1e-9)
+    assert o["final_error"] < 1e-9
+
+
+def test_icp_fewer_than_six_source_points(oracle, ref, small_pair):
+    src = small_pair["b"][[10, 500, 900, 1500]]
+    o = oracle.icp_point_to_plane(src, small_pair["a"])
+    r = ref.icp_point_to_plane(src, small_pair["a"])
+    # rank <= 4 with rounding-noise pivots instead of exact zeros: the step is ill-posed, so the two builds may take
+    # different paths — but neither may produce a non-finite pose or error
+    assert np.all(np.isfinite(r["transformation"])) and np.all(np.isfinite(o["transformation"]))
+    assert np.all(np.isfinite(r["error_history"])) and np.all(np.isfinite(o["error_history"]))
+
+
 def test_icp_initial_transform(oracle, ref, small_pair):
     c, s = np.cos(0.01), np.sin(0.01)
     T0 = np.array([[c, -s, 0, 0.8], [s, c, 0, 0.1], [0, 0, 1, 0.0], [0, 0, 0, 1.0]])
