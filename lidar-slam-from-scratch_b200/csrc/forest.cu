@@ -753,7 +753,11 @@ int forest_normals(Ctx* ctx, Forest* f, int k, double* d_out_normals, double* d_
             const int row = k | 1;
             const size_t entries = (size_t)(32 * row > cap_entries * 32 ? 32 * row : cap_entries * 32);
             const size_t smem = (size_t)PWARPS * entries * sizeof(int2);
-            SB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            static bool attr_set = false;   // one per instantiation of this generic lambda, i.e. per kernel
+            if (!attr_set) {
+                SB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                attr_set = true;
+            }
             SB_LAUNCH(ctx, kern, grid, PWARPS * 32, smem, view_of(f, B.t0), d_tio, n_items, B.n_trees, B.nbr, d_redo,
                       d_redo_count, d_stats);
             return SB_OK;

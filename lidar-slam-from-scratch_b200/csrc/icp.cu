@@ -4,21 +4,22 @@
 // The reference runs, per pair and per iteration: a KD-tree 1-NN pass over the source (twice, icp.hpp:185,190),
 // an RMS pass, an n x 6 Jacobian build, J^T J, an LDLT solve, a Rodrigues update and a full rewrite of the
 // source cloud.  Here one iteration of ALL pairs of a batch is four kernels:
-//   k_icp_match     one THREAD per source point: cur = T * src (never stored), then a walk over the target's
-//                   k-nearest-neighbour graph from the previous correspondence (first pass: from the seed grid)
-//                   that ends with a proof that the best point seen is the exact nearest neighbour; points without
-//                   a proof go to a device-wide queue;
+//   k_icp_match     one warp per 32 consecutive source points (in the source's own curve order), one point per lane:
+//                   cur = T * src (never stored); a walk over the target's k-nearest-neighbour graph from the previous
+//                   correspondence that ends with a PROOF that the best point seen is the exact nearest neighbour.
+//                   If many lanes of the item are left without a proof (the first pass: no previous correspondences)
+//                   they are answered together, in place, by ONE packet traversal of the tree
+//                   (NearestPacketVisitor, traverse.cuh); a few open lanes go to a device-wide queue;
 //   k_icp_fallback  one WARP per queued point: the exact warp-cooperative tree traversal of traverse.cuh;
-//   k_icp_accum     one warp per 32 source points: residual + the 28 sums (21 of J^T J, 6 of J^T r, 1 of r^2),
-//                   fixed-order shuffle tree, one 224-byte partial per work item;
-//   k_icp_solve     one warp per pair: adds the pair's partials in item order (run-to-run deterministic), RMS error,
-//                   convergence test (icp.hpp:210-217), 6x6 LDL^T, Rodrigues (icp.hpp:127-142), T <- delta * T.
+//   k_icp_accum     one warp per 32 source points: residual + the 29 sums (21 of J^T J, 6 of J^T r, sum r^2, matched
+//                   points), fixed-order shuffle tree, one 232-byte partial per work item (items whose points were
+//                   all settled in k_icp_match are finished there, same device function, same bits);
+//   k_icp_solve     one block per pair: adds the pair's partials in item order (run-to-run deterministic), RMS error,
+//                   convergence test (icp.hpp:210-217), 6x6 pivoted LDL^T, Rodrigues (icp.hpp:127-142), T <- delta * T.
 // The loop is a CUDA-graph WHILE node whose condition k_icp_solve's last block sets from the device-side count of
 // still-active pairs: no host round trip per iteration.  All kernels read their arguments from one device-resident
 // IcpJob, so the instantiated graph is reused by every call on the context.
 #include "traverse.cuh"
-
-#include <cooperative_groups.h>
 
 #include <cstdlib>
 
@@ -46,11 +47,11 @@ struct IcpJob {
     sb_icp_result* results;
     PairState* state;
     double* partials;           // n_items x 28
-    unsigned char* item_done;   // n_items: 1 if k_icp_match already wrote the item's partial in this pass
-    FallbackEntry* queue;       // capacity n_items x ITEM_Q
     int* act_pair;              // pairs the next pass works on (ascending), rebuilt after every solve
     i64* act_off;               // n_act + 1 prefix sums of their work items
-    unsigned long long* stats;  // optional (SB_ICP_STATS): per iteration bucket [queries, queued]
+    unsigned char* item_done;   // n_items: 1 if k_icp_match already wrote the item's partial in this pass
+    FallbackEntry* queue;       // capacity n_items x ITEM_Q
+    unsigned long long* stats;  // optional (SB_ICP_STATS): per iteration bucket [queries, answered by the tree]
     double T0[16];
     double tol, min_err;
     int n_pairs;
@@ -60,7 +61,7 @@ struct IcpJob {
     int nbr_k;
     int q_count;                // entries in `queue` (reset by k_icp_solve / k_icp_init)
     int n_act;                  // entries of act_pair
-    int tail_pairs;             // the loop stops once this many pairs (or fewer) still iterate: k_icp_tail takes them
+    int packet_min;             // open lanes of a work item from which the packet traversal takes over (SB_ICP_PACKET_MIN)
     int passes;                 // batch passes run so far (launch accounting)
     int pad2;
     i64 n_act_items;            // = act_off[n_act]
@@ -69,6 +70,7 @@ struct IcpJob {
 static constexpr int IWARPS = 8;
 static constexpr int NSUM = 29;      // 21 of J^T J, 6 of J^T r, sum r^2, and the number of points with a correspondence
 static constexpr int ITEM_Q = 32;   // source points per warp work item: one per lane
+static constexpr int PACKET_MIN_ITEMS = 32768;  // work items of a pass (32 source points each) from which packets are used
 static constexpr int MAX_HOPS = 6;  // re-centrings of the neighbour-graph walk before the tree takes over
 
 // -------------------------------------------------------------------------------------------------------------
@@ -138,9 +140,8 @@ __global__ void __launch_bounds__(256) k_icp_init(IcpJob* __restrict__ job, cuda
         job->state[p] = s;
     }
     __syncthreads();
-    // the batch passes run while more than tail_pairs pairs iterate; k_icp_tail finishes the rest
-    const bool loop = job->n_active > job->tail_pairs && job->max_it > 0;
-    build_active(job, ST_ACTIVE);
+    const bool loop = job->n_active > 0 && job->max_it > 0;
+    build_active(job, loop ? ST_ACTIVE : ST_EXHAUSTED);
     if (threadIdx.x == 0) {
         job->q_count = 0;
         if (use_cond) cudaGraphSetConditional(cond, loop ? 1u : 0u);
@@ -219,20 +220,13 @@ __device__ __forceinline__ int grid_seed(const TreeDesc& T, double qx, double qy
     return pos;
 }
 
-__device__ __forceinline__ void accumulate_item(const IcpJob* __restrict__ job, const TreeDesc& T, i64 it, int lane,
-                                                int my_pos, double cx, double cy, double cz);
-
-// Works on the pairs listed in job->act_pair: the ST_ACTIVE ones inside the loop, the ST_EXHAUSTED ones in the final
-// error pass (icp.hpp:235-252).  Work item = ITEM_Q consecutive source points of one pair (implicit: binary search
-// over the prefix sums act_off), one source point per lane.
-//
 // Correspondence search (replaces KDTree::nearest_batch, kdtree.hpp:43-59, exact): start from the previous
 // iteration's match (or the seed grid) and walk the target's k-nearest-neighbour graph.  With c the current centre,
 // entries of c's list are evaluated in ascending distance from c; every point not yet evaluated is at least r_j
 // from c, hence at least r_j - |q c| from the query q.  As soon as that bound exceeds the best distance found, the
 // best point IS the nearest neighbour (all bounds rounded conservatively in fp32, the candidates themselves compared
 // in the oracle's fp64 (d2, index) order).  If the list runs out first, re-centre on the best point and repeat.
-// Points whose walk ends without that proof are queued for k_icp_fallback.
+// Points whose walk ends without that proof are answered by packet_nearest (many per item) or k_icp_fallback (few).
 // The walk of one source point (one lane): cur = Tm * src, then the neighbour-graph walk from `center` (the previous
 // correspondence; < 0 or stale: the seed grid).  Returns the best target position found (-1: none) and whether it is
 // PROVEN to be the nearest neighbour.
@@ -277,12 +271,52 @@ __device__ __forceinline__ void walk_lane(const TreeDesc& T, int K, const double
     }
 }
 
+// ordered image of a float for warp-wide min / max reductions
+__device__ __forceinline__ unsigned ordered_u32(float f) {
+    const unsigned b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float float_from_ordered_u32(unsigned u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+// Exact nearest neighbours of the lanes in `todo` (queries (cx, cy, cz), starting points bpos): one packet traversal
+// for all of them (NearestPacketVisitor, traverse.cuh).  The caller checks T.gext < 1e15 (float32 bounds).
+__device__ __forceinline__ void packet_nearest(const ForestView& F, const TreeDesc& T, WarpStack& S, int lane,
+                                               unsigned todo, double cx, double cy, double cz, int& bpos) {
+    const bool mine = (todo >> lane) & 1u;
+    NearestPacketVisitor V(T, lane);
+    V.init(mine, cx, cy, cz, bpos);
+    // bounding box of the packet's queries (float32, rounded outwards)
+    const float inf = __int_as_float(0x7f800000);
+    const bool in = V.need;
+    const float lx = float_from_ordered_u32(__reduce_min_sync(0xffffffffu, ordered_u32(in ? __double2float_rd(cx) : inf)));
+    const float ly = float_from_ordered_u32(__reduce_min_sync(0xffffffffu, ordered_u32(in ? __double2float_rd(cy) : inf)));
+    const float lz = float_from_ordered_u32(__reduce_min_sync(0xffffffffu, ordered_u32(in ? __double2float_rd(cz) : inf)));
+    const float hx = float_from_ordered_u32(__reduce_max_sync(0xffffffffu, ordered_u32(in ? __double2float_ru(cx) : -inf)));
+    const float hy = float_from_ordered_u32(__reduce_max_sync(0xffffffffu, ordered_u32(in ? __double2float_ru(cy) : -inf)));
+    const float hz = float_from_ordered_u32(__reduce_max_sync(0xffffffffu, ordered_u32(in ? __double2float_ru(cz) : -inf)));
+    if (lx <= hx) {   // at least one searchable query
+        BoxQuery Q;
+        Q.lox = lx; Q.loy = ly; Q.loz = lz; Q.hix = hx; Q.hiy = hy; Q.hiz = hz;
+        traverse(F, T, Q, S, V, lane);
+    }
+    if (mine) bpos = V.bpos;
+}
+
+__device__ __forceinline__ void accumulate_item(const IcpJob* __restrict__ job, const TreeDesc& T, i64 it, int lane,
+                                                int my_pos, double cx, double cy, double cz);
+
+// Works on the pairs listed in job->act_pair: the ST_ACTIVE ones inside the loop, the ST_EXHAUSTED ones in the final
+// error pass (icp.hpp:235-252).  Work item = ITEM_Q consecutive source points of one pair (implicit: binary search
+// over the prefix sums act_off), one source point per lane.  Replaces KDTree::nearest_batch (kdtree.hpp:43-59), exact.
 __global__ void __launch_bounds__(IWARPS * 32) k_icp_match(IcpJob* __restrict__ job) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const ForestView F = job->F;
     const i64 n_act_items = job->n_act_items;
     const int n_act = job->n_act;
     const int K = job->nbr_k;
+    const int packet_min = job->packet_min;
     for (i64 ai = (i64)blockIdx.x * IWARPS + warp; ai < n_act_items; ai += (i64)gridDim.x * IWARPS) {
         const int a = find_active(job->act_off, n_act, ai);
         const int pair = job->act_pair[a];
@@ -297,19 +331,26 @@ __global__ void __launch_bounds__(IWARPS * 32) k_icp_match(IcpJob* __restrict__ 
         double cx = 0, cy = 0, cz = 0;
         if (lane < count) {
             walk_lane(T, K, Tm, P.src_pts + s0 + lane, job->match[it * ITEM_Q + lane], bpos, cert, cx, cy, cz);
-            if (cert) job->match[it * ITEM_Q + lane] = bpos;
+            job->match[it * ITEM_Q + lane] = bpos;   // proven, or the starting point of the tree search
         }
-        // queue the points without a proof (warp-aggregated append)
+        // The points without a proof go to the device-wide queue of k_icp_fallback: one entry per point, or — when the
+        // item has many of them (the first pass: no previous correspondences) — ONE entry for the item, whose open
+        // points are then answered together by a packet traversal.
         const unsigned todo = __ballot_sync(0xffffffffu, lane < count && !cert);
         if (todo) {
+            // (only while the pass is busy enough to be bound by instruction throughput: the packet visits a leaf's 32
+            // points one after the other, the warp-cooperative search all at once, and with few pairs left a pass costs
+            // what its longest dependency chain costs — measured: 149 vs 79 us per pass with 34 pairs iterating)
+            const bool as_item = __popc(todo) >= packet_min && n_act_items >= PACKET_MIN_ITEMS;
             int base = 0;
-            if (lane == 0) base = atomicAdd(&job->q_count, __popc(todo));
+            if (lane == 0) base = atomicAdd(&job->q_count, as_item ? 1 : __popc(todo));
             base = __shfl_sync(0xffffffffu, base, 0);
-            if ((todo >> lane) & 1u) {
-                FallbackEntry e;
-                e.q = it * ITEM_Q + lane;
-                e.seed = bpos;
-                e.pad = 0;
+            FallbackEntry e;
+            if (as_item) {
+                e.q = it * ITEM_Q; e.seed = (int)todo; e.pad = 1;
+                if (lane == 0) job->queue[base] = e;
+            } else if ((todo >> lane) & 1u) {
+                e.q = it * ITEM_Q + lane; e.seed = bpos; e.pad = 0;
                 job->queue[base + __popc(todo & lanemask_lt())] = e;
             }
         }
@@ -325,7 +366,8 @@ __global__ void __launch_bounds__(IWARPS * 32) k_icp_match(IcpJob* __restrict__ 
     }
 }
 
-// One warp per queued point: the exact tree traversal, started from the best point of the walk.
+// One warp per queue entry.  A point entry: the exact warp-cooperative tree traversal, started from the best point of
+// the walk.  An item entry (pad == 1, seed = mask of the item's open lanes): one packet traversal for all of them.
 __global__ void __launch_bounds__(IWARPS * 32) k_icp_fallback(IcpJob* __restrict__ job) {
     __shared__ WarpStack stacks[IWARPS];
     __shared__ TreeDesc s_tree[IWARPS];
@@ -347,13 +389,33 @@ __global__ void __launch_bounds__(IWARPS * 32) k_icp_fallback(IcpJob* __restrict
             __syncwarp();
         }
         const TreeDesc& T = s_tree[warp];
-        double qx, qy, qz;
-        transform_point(job->results[pair].transformation,
-                        reinterpret_cast<const double*>(P.src_pts + (E.q - P.item_off * ITEM_Q)), qx, qy, qz);
-        NearestVisitor V(F, T, qx, qy, qz, lane);
-        V.seed(E.seed);
-        traverse(F, T, qx, qy, qz, S, V, lane);
-        if (lane == 0) job->match[E.q] = V.best_pos;
+        const double* Tm = job->results[pair].transformation;
+        if (E.pad == 1 && T.gext < 1.0e15) {
+            const int s0 = (int)(it - P.item_off) * ITEM_Q;
+            const int count = P.n_src - s0 < ITEM_Q ? P.n_src - s0 : ITEM_Q;
+            const unsigned todo = (unsigned)E.seed;
+            double cx = 0, cy = 0, cz = 0;
+            int bpos = -1;
+            if (lane < count) {
+                transform_point(Tm, reinterpret_cast<const double*>(P.src_pts + s0 + lane), cx, cy, cz);
+                bpos = job->match[E.q + lane];
+            }
+            packet_nearest(F, T, S, lane, todo, cx, cy, cz, bpos);
+            if ((todo >> lane) & 1u) job->match[E.q + lane] = bpos;
+        } else {
+            unsigned todo = E.pad == 1 ? (unsigned)E.seed : 1u;   // (an item entry of a tree of extreme extent: lane by lane)
+            while (todo) {
+                const int j = __ffs(todo) - 1;
+                todo &= todo - 1u;
+                const i64 q = E.pad == 1 ? E.q + j : E.q;
+                double qx, qy, qz;
+                transform_point(Tm, reinterpret_cast<const double*>(P.src_pts + (q - P.item_off * ITEM_Q)), qx, qy, qz);
+                NearestVisitor V(F, T, qx, qy, qz, lane);
+                V.seed(E.pad == 1 ? job->match[q] : E.seed);
+                traverse(F, T, qx, qy, qz, S, V, lane);
+                if (lane == 0) job->match[q] = V.best_pos;
+            }
+        }
     }
 }
 
@@ -441,44 +503,73 @@ __global__ void __launch_bounds__(IWARPS * 32) k_icp_accum(const IcpJob* __restr
 }
 
 // 6x6 symmetric solve by LDL^T with diagonal pivoting (Eigen's (J^T J).ldlt().solve, icp.hpp:120; the oracle's
-// ldlt6_solve, same operation order): largest remaining diagonal entry first, symmetric swaps, and a pivot that is
-// exactly zero leaves its component at zero, so a rank-deficient J^T J (planar target, fewer than six points) gives
-// a finite step instead of 0/0.  One thread per pair and iteration runs this: the dynamically indexed arrays
-// may live in local memory.
-__device__ __noinline__ void ldlt6_solve(const double (&Ain)[6][6], const double (&bin)[6], double (&x)[6]) {
-    double a[6][6];
-    int perm[6];
+// ldlt6_solve, same operation order): largest remaining diagonal entry first (first one on ties), symmetric swaps, and
+// a pivot that is exactly zero leaves its component at zero, so a rank-deficient J^T J (planar target, fewer than
+// six points) gives a finite step instead of 0/0.  Every index is a compile-time constant — the pivot row is swapped
+// in by predicated exchanges — so the matrix stays in registers: one thread per pair and iteration runs this, and
+// with dynamically indexed (local-memory) arrays the first touch of every line cost that thread ~14 us per pass.
+__device__ __forceinline__ void cswap(bool c, double& x, double& y) {
+    const double t = x;
+    x = c ? y : x;
+    y = c ? t : y;
+}
+__device__ __forceinline__ void ldlt6_solve(const double (&Ain)[6][6], const double (&bin)[6], double (&x)[6]) {
+    double a[6][6], y[6];
+#pragma unroll
     for (int i = 0; i < 6; ++i) {
-        perm[i] = i;
+        y[i] = bin[i];   // permuted along with the rows: y = P b
+#pragma unroll
         for (int j = 0; j < 6; ++j) a[i][j] = Ain[i][j];
     }
+    int perm[6] = {0, 1, 2, 3, 4, 5};
+#pragma unroll
     for (int k = 0; k < 6; ++k) {
         int p = k;
         double best = fabs(a[k][k]);
+#pragma unroll
         for (int i = k + 1; i < 6; ++i)
             if (fabs(a[i][i]) > best) { best = fabs(a[i][i]); p = i; }
-        if (p != k) {
-            for (int j = 0; j < 6; ++j) { double t = a[k][j]; a[k][j] = a[p][j]; a[p][j] = t; }
-            for (int i = 0; i < 6; ++i) { double t = a[i][k]; a[i][k] = a[i][p]; a[i][p] = t; }
-            int t = perm[k]; perm[k] = perm[p]; perm[p] = t;
+#pragma unroll
+        for (int r = k + 1; r < 6; ++r) {   // p == r: swap rows and columns k <-> r
+            const bool c = p == r;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) cswap(c, a[k][j], a[r][j]);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) cswap(c, a[i][k], a[i][r]);
+            cswap(c, y[k], y[r]);
+            const int t = perm[k];
+            perm[k] = c ? perm[r] : perm[k];
+            perm[r] = c ? t : perm[r];
         }
         const double d = a[k][k];
-        if (d == 0.0) continue;
-        for (int i = k + 1; i < 6; ++i) a[i][k] /= d;
-        for (int i = k + 1; i < 6; ++i)
-            for (int j = k + 1; j <= i; ++j) {
-                a[i][j] -= a[i][k] * d * a[j][k];
-                a[j][i] = a[i][j];
-            }
+        if (d != 0.0) {
+#pragma unroll
+            for (int i = k + 1; i < 6; ++i) a[i][k] /= d;  // column k of L
+#pragma unroll
+            for (int i = k + 1; i < 6; ++i)
+#pragma unroll
+                for (int j = k + 1; j <= i; ++j) {
+                    a[i][j] -= a[i][k] * d * a[j][k];
+                    a[j][i] = a[i][j];
+                }
+        }
     }
-    double y[6];
-    for (int i = 0; i < 6; ++i) y[i] = bin[perm[i]];
-    for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int i = 0; i < 6; ++i)  // L y' = P b
+#pragma unroll
         for (int j = 0; j < i; ++j) y[i] -= a[i][j] * y[j];
-    for (int i = 0; i < 6; ++i) y[i] = a[i][i] == 0.0 ? 0.0 : y[i] / a[i][i];
-    for (int i = 5; i >= 0; --i)
+#pragma unroll
+    for (int i = 0; i < 6; ++i) y[i] = a[i][i] == 0.0 ? 0.0 : y[i] / a[i][i];  // D z = y'
+#pragma unroll
+    for (int i = 5; i >= 0; --i)  // L^T w = z
+#pragma unroll
         for (int j = i + 1; j < 6; ++j) y[i] -= a[j][i] * y[j];
-    for (int i = 0; i < 6; ++i) x[perm[i]] = y[i];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {   // x = P^T w
+#pragma unroll
+        for (int o = 0; o < 6; ++o)
+            if (perm[i] == o) x[o] = y[i];
+    }
 }
 
 // x -> 4x4 row-major delta (icp.hpp:123-144)
@@ -677,91 +768,17 @@ __global__ void __launch_bounds__(256) k_icp_solve(IcpJob* __restrict__ job, int
         if (s_last) {  // every other block's state updates are visible now
             __threadfence();
             const int active = *reinterpret_cast<volatile int*>(&job->n_active);
-            // next pass: the pairs still iterating (the loop hands the last few to k_icp_tail)
-            build_active(job, ST_ACTIVE);
+            // next pass: the pairs still iterating, or — once none is left — the final error pass of the pairs that
+            // ran out of iterations (icp.hpp:235-252)
+            build_active(job, active > 0 ? ST_ACTIVE : ST_EXHAUSTED);
             if (threadIdx.x == 0) {
                 job->ticket = 0;
                 job->q_count = 0;
                 job->passes += 1;
-                if (use_cond) cudaGraphSetConditional(cond, active > job->tail_pairs ? 1u : 0u);
+                if (use_cond) cudaGraphSetConditional(cond, active > 0 ? 1u : 0u);
             }
         }
     }
-}
-
-// -------------------------------------------------------------------------------------------------------------
-// k_icp_tail — the pairs still iterating once only a few are left (and every pair of a small batch, e.g. the one pair
-// of sb_icp_point_to_plane): one thread-block CLUSTER per pair runs the whole loop of that pair on the device.
-// A pass over the last 3 % of the pairs is latency: four launches of near-empty grids, ~70 us, 38 times for the C2
-// batch.  Pairs are independent, so nothing needs a grid-wide barrier — only a pair-wide one: TAIL_CTAS x 8 warps take
-// the pair's work items (walk, tree fallback in place, accumulate), cluster.sync(), CTA 0 does the solve, cluster.sync().
-// Same device functions and the same summation association as the batch passes: identical bits.
-// -------------------------------------------------------------------------------------------------------------
-static constexpr int TAIL_CTAS = 8;
-
-__global__ void __cluster_dims__(TAIL_CTAS, 1, 1) __launch_bounds__(256) k_icp_tail(IcpJob* __restrict__ job) {
-    __shared__ WarpStack stacks[8];
-    __shared__ TreeDesc s_tree;
-    __shared__ double s_T[12];
-    __shared__ double s_part[8][32];
-    namespace cg = cooperative_groups;
-    cg::cluster_group cluster = cg::this_cluster();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int crank = (int)cluster.block_rank();
-    const int n_clusters = (int)gridDim.x / TAIL_CTAS, cid = (int)blockIdx.x / TAIL_CTAS;
-    const ForestView F = job->F;
-    const int K = job->nbr_k;
-    const int n_act = job->n_act;
-    WarpStack& S = stacks[warp];
-    for (int a = cid; a < n_act; a += n_clusters) {
-        const int pair = job->act_pair[a];
-        const PairDesc P = job->pairs[pair];
-        __syncthreads();
-        {
-            const int* src = reinterpret_cast<const int*>(&F.trees[P.tree]);
-            int* dst = reinterpret_cast<int*>(&s_tree);
-            for (int i = threadIdx.x; i < (int)(sizeof(TreeDesc) / 4); i += 256) dst[i] = src[i];
-        }
-        __syncthreads();
-        const TreeDesc& T = s_tree;
-        while (__ldcg(&job->state[pair].state) == ST_ACTIVE) {   // the same value in every thread of the cluster
-            // this pass's transformation, past L1 (CTA 0 of the cluster rewrote it after the previous pass)
-            if (threadIdx.x < 12) s_T[threadIdx.x] = __ldcg(&job->results[pair].transformation[threadIdx.x]);
-            __syncthreads();
-            for (int li = crank * 8 + warp; li < P.n_items; li += 8 * TAIL_CTAS) {
-                const i64 it = P.item_off + li;
-                const int s0 = li * ITEM_Q;
-                const int count = P.n_src - s0 < ITEM_Q ? P.n_src - s0 : ITEM_Q;
-                int bpos = -1;
-                bool cert = false;
-                double cx = 0, cy = 0, cz = 0;
-                if (lane < count) walk_lane(T, K, s_T, P.src_pts + s0 + lane, job->match[it * ITEM_Q + lane], bpos, cert, cx, cy, cz);
-                // points without a proof: the exact tree traversal, right here, one after the other
-                unsigned todo = __ballot_sync(0xffffffffu, lane < count && !cert);
-                while (todo) {
-                    const int j = __ffs(todo) - 1;
-                    todo &= todo - 1u;
-                    const double qx = shfl_d(cx, j), qy = shfl_d(cy, j), qz = shfl_d(cz, j);
-                    const int seed = __shfl_sync(0xffffffffu, bpos, j);
-                    NearestVisitor V(F, T, qx, qy, qz, lane);
-                    V.seed(seed);
-                    traverse(F, T, qx, qy, qz, S, V, lane);
-                    if (lane == j) bpos = V.best_pos;
-                }
-                if (lane < count) job->match[it * ITEM_Q + lane] = bpos;
-                accumulate_item(job, T, it, lane, lane < count ? bpos : -1, cx, cy, cz);
-            }
-            cluster.sync();   // every partial of the pair is written (release/acquire at cluster scope)
-            if (crank == 0) solve_pair(job, pair, 0, s_part);
-            cluster.sync();   // the new transformation and state are visible
-        }
-    }
-}
-
-// one block: the list of pairs that ran out of iterations, for the final error pass (icp.hpp:235-252)
-__global__ void __launch_bounds__(256) k_icp_prepare_final(IcpJob* __restrict__ job) {
-    build_active(job, ST_EXHAUSTED);
-    if (threadIdx.x == 0) job->q_count = 0;
 }
 
 // solve_point_to_plane on explicit correspondences (icp.hpp:89-144): one block, fixed-order reduction
@@ -834,7 +851,7 @@ struct IcpGraph {
     IcpJob* d_job = nullptr;
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
-    int iter_grid = 0, solve_grid = 0, tail_grid = 0, tail_pairs = 0;
+    int iter_grid = 0, solve_grid = 0;
     unsigned long long* d_stats = nullptr;  // SB_ICP_STATS=1: per iteration bucket [queries, queued for the tree]
 };
 
@@ -906,10 +923,6 @@ static int icp_graph_build(Ctx* ctx, IcpGraph* G) {
     SB_CUDA(ctx, cudaMalloc(&G->d_job, sizeof(IcpJob)));
     G->iter_grid = ctx->sm_count * (getenv("SB_ICP_GRID") ? atoi(getenv("SB_ICP_GRID")) : 32);
     G->solve_grid = ctx->sm_count * 4;
-    // SB_ICP_TAIL: hand the loop to k_icp_tail once this many pairs (or fewer) still iterate; 0: never
-    G->tail_pairs = getenv("SB_ICP_TAIL") ? atoi(getenv("SB_ICP_TAIL")) : 64;
-    if (G->tail_pairs < 0) G->tail_pairs = 0;
-    G->tail_grid = TAIL_CTAS * (G->tail_pairs > 0 ? (G->tail_pairs < 64 ? G->tail_pairs : 64) : 1);
     if (getenv("SB_ICP_STATS")) {
         SB_CUDA(ctx, cudaMalloc(&G->d_stats, 8 * sizeof(unsigned long long)));
         SB_CUDA(ctx, cudaMemset(G->d_stats, 0, 8 * sizeof(unsigned long long)));
@@ -933,13 +946,7 @@ static int icp_graph_build(Ctx* ctx, IcpGraph* G) {
     SB_CUDA(ctx, cudaGraphAddNode(&n_while, G->graph, &n_init, 1, &wp));
     cudaGraph_t body = wp.conditional.phGraph_out[0];
     SB_TRY(add_pass(ctx, G, body, nullptr, 0, cond, 1, &n_body_last));       // icp.hpp:181-232
-    cudaGraphNode_t n_tail, n_prep;
-    {
-        void* args[] = {&job};
-        SB_TRY(add_kernel(ctx, G->graph, &n_tail, &n_while, (void*)k_icp_tail, G->tail_grid, 256, args));
-        SB_TRY(add_kernel(ctx, G->graph, &n_prep, &n_tail, (void*)k_icp_prepare_final, 1, 256, args));
-    }
-    SB_TRY(add_pass(ctx, G, G->graph, &n_prep, 1, cond, 0, &n_final));       // icp.hpp:235-255
+    SB_TRY(add_pass(ctx, G, G->graph, &n_while, 1, cond, 0, &n_final));      // icp.hpp:235-255
     SB_CUDA(ctx, cudaGraphInstantiate(&G->exec, G->graph, 0));
     return SB_OK;
 }
@@ -996,8 +1003,6 @@ int icp_batch(Ctx* ctx, const Forest* f, const std::vector<PairDesc>& pairs_in, 
     sb_icp_result* d_res;
     PairState* d_state;
     double* d_part;
-    FallbackEntry* d_queue;
-    unsigned char* d_item_done;
     int* d_act_pair;
     i64* d_act_off;
     size_t ni = (size_t)(n_items > 0 ? n_items : 1);
@@ -1006,6 +1011,8 @@ int icp_batch(Ctx* ctx, const Forest* f, const std::vector<PairDesc>& pairs_in, 
     SB_TRY(arena_get(ctx, (size_t)n_pairs, &d_res));
     SB_TRY(arena_get(ctx, (size_t)n_pairs, &d_state));
     SB_TRY(arena_get(ctx, ni * NSUM, &d_part));
+    FallbackEntry* d_queue;
+    unsigned char* d_item_done;
     SB_TRY(arena_get(ctx, ni * ITEM_Q, &d_queue));
     SB_TRY(arena_get(ctx, ni, &d_item_done));
     SB_TRY(arena_get(ctx, (size_t)n_pairs, &d_act_pair));
@@ -1025,6 +1032,7 @@ int icp_batch(Ctx* ctx, const Forest* f, const std::vector<PairDesc>& pairs_in, 
     job.partials = d_part;
     job.queue = d_queue;
     job.item_done = d_item_done;
+    job.q_count = 0;
     job.act_pair = d_act_pair;
     job.act_off = d_act_off;
     memcpy(job.T0, cfg->initial_transform, sizeof(job.T0));
@@ -1034,8 +1042,8 @@ int icp_batch(Ctx* ctx, const Forest* f, const std::vector<PairDesc>& pairs_in, 
     job.max_it = cfg->max_iterations;
     job.n_active = cfg->max_iterations > 0 ? n_valid : 0;
     job.ticket = 0;
-    job.q_count = 0;
-    job.tail_pairs = G->tail_pairs;
+    static const int packet_min = getenv("SB_ICP_PACKET_MIN") ? atoi(getenv("SB_ICP_PACKET_MIN")) : 6;
+    job.packet_min = packet_min;
     SB_CUDA(ctx, cudaMemcpyAsync(G->d_job, &job, sizeof(job), cudaMemcpyHostToDevice, ctx->stream));
     if (G->exec) {
         SB_CUDA(ctx, cudaGraphLaunch(G->exec, ctx->stream));
@@ -1047,15 +1055,13 @@ int icp_batch(Ctx* ctx, const Forest* f, const std::vector<PairDesc>& pairs_in, 
                 int active = 0;
                 SB_CUDA(ctx, cudaMemcpyAsync(&active, &G->d_job->n_active, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
                 SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-                if (active <= G->tail_pairs) break;
+                if (active <= 0) break;
             }
             SB_LAUNCH(ctx, k_icp_match, G->iter_grid, IWARPS * 32, 0, G->d_job);
             SB_LAUNCH(ctx, k_icp_fallback, G->iter_grid, IWARPS * 32, 0, G->d_job);
             SB_LAUNCH(ctx, k_icp_accum, G->iter_grid, IWARPS * 32, 0, G->d_job);
             SB_LAUNCH(ctx, k_icp_solve, G->solve_grid, 256, 0, G->d_job, 0, none, 0);
         }
-        SB_LAUNCH(ctx, k_icp_tail, G->tail_grid, 256, 0, G->d_job);
-        SB_LAUNCH(ctx, k_icp_prepare_final, 1, 256, 0, G->d_job);
         SB_LAUNCH(ctx, k_icp_match, G->iter_grid, IWARPS * 32, 0, G->d_job);
         SB_LAUNCH(ctx, k_icp_fallback, G->iter_grid, IWARPS * 32, 0, G->d_job);
         SB_LAUNCH(ctx, k_icp_accum, G->iter_grid, IWARPS * 32, 0, G->d_job);
@@ -1069,7 +1075,7 @@ int icp_batch(Ctx* ctx, const Forest* f, const std::vector<PairDesc>& pairs_in, 
     int max_hist = 1;
     for (int p = 0; p < n_pairs; ++p)
         if (results[p].history_len > max_hist) max_hist = results[p].history_len;
-    if (G->exec) ctx->launches += 7 + 4 * (i64)passes;  // init + 4 per batch pass + tail + prepare + 4 of the final pass
+    if (G->exec) ctx->launches += 5 + 4 * (i64)passes;  // init + 4 per loop pass + 4 of the final pass
     ctx->last_icp_iterations = max_hist;
     return SB_OK;
 }

@@ -30,12 +30,7 @@
 // of code are each far smaller than their sum, and instruction fetch — not issue slots — was what bound the fused
 // version (ncu: 25 % issue-active, 7.9 cycles of `no_instruction` stall per issue with 94 KB of code).
 //
-// Error analysis.  Let S bound every leaf-local coordinate involved (the leaf's extent and the query's offsets from
-// the leaf corner).  Stored offsets and the query's offsets are within 2^-24 S of the exact ones, their float32
-// difference within 2^-22 S (1 + 2^-10) =: a of the exact coordinate difference, so | |d~vec| - d | <= sqrt(3) a.
-// With 2xy <= r x^2 + y^2 / r, r = 2^-19, and 3 * 2^-24 for the float32 evaluation of the sum of squares:
-//     d2 <= d~ (1 + rho) + beta,   d2 >= d~ (1 - rho) - beta,   rho = 2^-18,  beta = a^2 (3 * 2^19 + 4).
-// Both are evaluated with directed rounding.
+// Error analysis ([lo, hi] = [d~ (1 - rho) - beta, d~ (1 + rho) + beta]): traverse.cuh, "Leaf-local float32 arithmetic".
 #pragma once
 
 static constexpr int PWARPS = 4;   // warps per CTA
@@ -95,10 +90,6 @@ __device__ __forceinline__ void sort_network(float (&xk)[TOT], int (&xp)[TOT]) {
     }
 }
 
-#define SB_RHO_UP 1.000003814697265625f    // 1 + 2^-18
-#define SB_RHO_DN 0.999996185302734375f    // 1 - 2^-18
-#define SB_RHO2_DN 0.99999237060546875f    // 1 - 2^-17
-
 template <int K, int TOT, int PCAP, bool STATS>
 struct PacketVisitor {
     static constexpr int KL = K + 1, NB = TOT - KL;
@@ -121,16 +112,10 @@ struct PacketVisitor {
         U = xk[K - 1];
         U_warp = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(U)));  // non-negative floats
     }
-    // leaf-local query offsets and the error term beta of this (lane, leaf)
+    // leaf-local query offsets and the error term beta of this (lane, leaf): traverse.cuh
     __device__ __forceinline__ void leaf_frame(float2 b0, float2 b1, float2 b2, float& ox, float& oy, float& oz,
                                                float& beta) {
-        ox = (float)(qx - (double)b0.x);
-        oy = (float)(qy - (double)b0.y);
-        oz = (float)(qz - (double)b1.x);
-        float S = fmaxf(fmaxf(fabsf(ox), fabsf(oy)), fabsf(oz));
-        S = fmaxf(S, fmaxf(fmaxf(__fsub_ru(b1.y, b0.x), __fsub_ru(b2.x, b0.y)), __fsub_ru(b2.y, b1.x)));
-        const float a = __fmul_ru(S, 2.386520565e-07f);          // 2^-22 (1 + 2^-10), rounded up
-        beta = __fmul_ru(__fmul_ru(a, a), 1572868.0f);           // 3 * 2^19 + 4
+        leaf_local_frame(qx, qy, qz, b0, b1, b2, ox, oy, oz, beta);
     }
     __device__ __forceinline__ void init(bool valid, double x, double y, double z) {
         const double nan_ = __longlong_as_double(0x7ff8000000000000LL);

@@ -296,4 +296,96 @@ struct KnnVisitor {
     }
 };
 
+// -------------------------------------------------------------------------------------------------------------
+// Leaf-local float32 arithmetic (TreeDesc::pts32): bounds of the exact squared distance from a float32 evaluation.
+//
+// pts32 holds every tree point as float32 offsets from its leaf box's lower corner (as stored: rounded down to
+// float32).  Let S bound every leaf-local coordinate involved (the leaf's extent and the query's offsets from that
+// corner).  Stored offsets and the query's offsets are within 2^-24 S of the exact ones, their float32 difference
+// within 2^-22 S (1 + 2^-10) =: a of the exact coordinate difference, so | |d~vec| - d | <= sqrt(3) a.  With
+// 2xy <= r x^2 + y^2 / r, r = 2^-19, and 3 * 2^-24 for the float32 evaluation of the sum of squares:
+//     d2 <= d~ (1 + rho) + beta,   d2 >= d~ (1 - rho) - beta,   rho = 2^-18,  beta = a^2 (3 * 2^19 + 4),
+// evaluated with directed rounding.  Valid while the tree's extent is moderate (callers check TreeDesc::gext < 1e15).
+// -------------------------------------------------------------------------------------------------------------
+#define SB_RHO_UP 1.000003814697265625f    // 1 + 2^-18
+#define SB_RHO_DN 0.999996185302734375f    // 1 - 2^-18
+#define SB_RHO2_DN 0.99999237060546875f    // 1 - 2^-17
+
+// query offsets from the corner of the leaf box (b0, b1, b2) and the error term beta of this (query, leaf)
+__device__ __forceinline__ void leaf_local_frame(double qx, double qy, double qz, float2 b0, float2 b1, float2 b2,
+                                                 float& ox, float& oy, float& oz, float& beta) {
+    ox = (float)(qx - (double)b0.x);
+    oy = (float)(qy - (double)b0.y);
+    oz = (float)(qz - (double)b1.x);
+    float S = fmaxf(fmaxf(fabsf(ox), fabsf(oy)), fabsf(oz));
+    S = fmaxf(S, fmaxf(fmaxf(__fsub_ru(b1.y, b0.x), __fsub_ru(b2.x, b0.y)), __fsub_ru(b2.y, b1.x)));
+    const float a = __fmul_ru(S, 2.386520565e-07f);          // 2^-22 (1 + 2^-10), rounded up
+    beta = __fmul_ru(__fmul_ru(a, a), 1572868.0f);           // 3 * 2^19 + 4
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// 1-NN of a PACKET of up to 32 nearby queries, one per lane (icp.cu): the packet shares one traversal (the query is
+// the packet's bounding box); a visited leaf's points are read as leaf-local float32 (one broadcast load per
+// candidate) and a lane evaluates a candidate in the oracle's fp64 arithmetic only if the float32 LOWER bound of its
+// distance does not exceed the lane's best distance so far — so the result is the exact (d2, index) minimum, like
+// NearestVisitor's.  Lanes with need == false take part in the warp-wide instructions but never search.
+// -------------------------------------------------------------------------------------------------------------
+struct NearestPacketVisitor {
+    const TreeDesc& T;
+    const int lane;
+    bool need;
+    double qx, qy, qz;
+    double bd;       // best exact d2 so far (+inf: none)
+    int bidx, bpos;  // its original row and sorted position
+    float U;         // >= bd (0 for lanes that do not search)
+    float U_warp;    // max over lanes
+    __device__ __forceinline__ NearestPacketVisitor(const TreeDesc& t, int l) : T(t), lane(l) {}
+    __device__ __forceinline__ double tau() const { return (double)U_warp; }
+    __device__ __forceinline__ void refresh() {
+        U = need ? __double2float_ru(bd) : 0.f;
+        U_warp = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(U)));  // non-negative floats
+    }
+    // (x, y, z): the lane's query; seed_pos: a tree point to start from (-1: none)
+    __device__ __forceinline__ void init(bool want, double x, double y, double z, int seed_pos) {
+        qx = x; qy = y; qz = z;
+        bd = (double)INFINITY; bidx = 0x7fffffff; bpos = -1;
+        need = want && x == x && y == y && z == z;   // a NaN query never matches (kdtree.hpp:125 strict <)
+        if (need && seed_pos >= 0 && seed_pos < T.n) {
+            const TreePoint P = load_point(T.pts + T.pt_off + seed_pos);
+            const double d = dist2_rn(P.x, P.y, P.z, qx, qy, qz);
+            if (d == d) { bd = d; bidx = P.idx; bpos = seed_pos; }
+        }
+        refresh();
+    }
+    __device__ __forceinline__ void leaf(int p0, int n) {
+        const float2* b = reinterpret_cast<const float2*>(T.boxes + 6 * (T.box_off[0] + (p0 >> 5)));
+        const float2 b0 = __ldg(b), b1 = __ldg(b + 1), b2 = __ldg(b + 2);
+        PointQuery Q;
+        Q.x = qx; Q.y = qy; Q.z = qz;
+        const bool want = need && Q.lb(b0, b1, b2) <= U;
+        if (!__any_sync(0xffffffffu, want)) return;
+        float ox, oy, oz, beta;
+        leaf_local_frame(qx, qy, qz, b0, b1, b2, ox, oy, oz, beta);
+        const float4* __restrict__ c = T.pts32 + T.pt_off + p0;
+        const TreePoint* __restrict__ TP = T.pts + T.pt_off + p0;
+        float thr = want ? U : -1.f;   // lanes that do not want this leaf pass nothing
+#pragma unroll 4
+        for (int i = 0; i < n; ++i) {
+            const float4 P32 = __ldg(c + i);  // same address in every lane: one broadcast load
+            const float dx = P32.x - ox, dy = P32.y - oy, dz = P32.z - oz;
+            const float dd = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx));
+            const float lo = __fmaf_rd(dd, SB_RHO_DN, -beta);
+            if (lo <= thr) {   // false for NaN
+                const TreePoint P = load_point(TP + i);   // also one address for the whole warp
+                const double d = dist2_rn(P.x, P.y, P.z, qx, qy, qz);
+                if (d < bd || (d == bd && P.idx < bidx)) {   // kdtree.hpp:125 + the canonical tie rule
+                    bd = d; bidx = P.idx; bpos = p0 + i;
+                    thr = __double2float_ru(bd);
+                }
+            }
+        }
+        refresh();
+    }
+};
+
 }  // namespace sb

@@ -1,14 +1,10 @@
 #!/bin/bash
-# GPU parity tests, then the 1000-pair bench with and without the pair-resident tail kernel
+# ICP loop variants: open lanes of an item from which the packet traversal takes over
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q --tb=short --timeout 600 -p no:cacheprovider -x > gpurun_out/pytest_gpu.log 2>&1
-echo "pytest exit $?" >> gpurun_out/pytest_gpu.log; tail -15 gpurun_out/pytest_gpu.log
-for v in ${VARIANTS:-64 0 16 256}; do
-  SB_ICP_TAIL=$v timeout 600 python bench.py --frames 1000 --steps 3 --warmup 3 --no-e2e --cpu-seconds 0.1 > gpurun_out/icp_tail_$v.log 2>&1
-  echo "tail=$v exit $?"; python - <<PY
-import json
-for l in open("gpurun_out/icp_tail_$v.log"):
-    if l.startswith("{"):
-        d = json.loads(l); print("tail=$v", d["ms_per_step"], d["roofline"]["stages_ms"], {k: d["extras"].get("c2_streaming", {}).get(k) for k in ("mean_ms", "p50_ms", "p99_ms", "ms_per_frame_mean")}, d["extras"].get("error"))
-PY
+timeout 1500 python -m pytest tests -m gpu -q --tb=short --timeout 600 -p no:cacheprovider -x > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log
+for v in ${VARIANTS:-6}; do
+  echo "packet_min=$v"; SB_ICP_PACKET_MIN=$v timeout 600 python scripts/icp_tail_cost.py 2>&1 | tail -7
 done
+timeout 600 python scripts/stream_latency.py --frames 150 | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print({k:d[k] for k in ('ms_per_frame_mean','p50','p99','max','split_ms_mean','launches_per_frame')})"
