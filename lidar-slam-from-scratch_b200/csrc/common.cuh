@@ -92,6 +92,7 @@ struct Ctx {
     int n_ev = 0, ev_created = 0;
     // SB_PIPE_TRACE=1: named device-time marks on the main stream (trace_mark / trace_dump), a debugging aid
     std::vector<std::pair<const char*, cudaEvent_t>> trace;
+    unsigned knn_attr_done = 0;    // forest.cu: k_self_knn instantiations whose shared-memory limit has been raised
     i64 last_icp_iterations = 0;   // max history length of the last icp_batch (launches of k_icp_iter)
     i64 last_counts[4] = {0, 0, 0, 0};  // raw rows, downsampled rows, target rows, sum over pairs of n_src * passes
 };

@@ -753,10 +753,10 @@ int forest_normals(Ctx* ctx, Forest* f, int k, double* d_out_normals, double* d_
             const int row = k | 1;
             const size_t entries = (size_t)(32 * row > cap_entries * 32 ? 32 * row : cap_entries * 32);
             const size_t smem = (size_t)PWARPS * entries * sizeof(int2);
-            static bool attr_set = false;   // one per instantiation of this generic lambda, i.e. per kernel
-            if (!attr_set) {
+            const unsigned bit = 1u << ((k == 20 ? 1 : 0) | (cap_entries >= 64 ? 2 : 0) | (want_stats ? 4 : 0));
+            if (!(ctx->knn_attr_done & bit)) {   // once per kernel instantiation and context (device)
                 SB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                attr_set = true;
+                ctx->knn_attr_done |= bit;
             }
             SB_LAUNCH(ctx, kern, grid, PWARPS * 32, smem, view_of(f, B.t0), d_tio, n_items, B.n_trees, B.nbr, d_redo,
                       d_redo_count, d_stats);

@@ -19,6 +19,7 @@
 // if there are too many of them, or keys do not fit 21 bits per axis, the call falls back to the sort.
 #include "common.cuh"
 
+#include <cmath>
 #include <cstdlib>
 
 namespace sb {
@@ -37,6 +38,27 @@ __device__ __forceinline__ bool voxel_key(double c, double voxel, i64* k) {
     }
     *k = (i64)q;
     return true;
+}
+
+// floor(c / voxel) without the division where that is provably the same integer.  rinv = fl(1 / voxel).  If voxel is
+// a power of two (pow2) c * rinv IS c / voxel.  Otherwise q~ = fl(c * rinv) is within 2^-51 |q~| of the exact quotient
+// and fl(c / voxel) within 2^-53: unless q~ lies within 2^-49 |q~| of an integer all three have the same floor; the
+// rare rest (and huge quotients) takes the IEEE division the reference performs (file_utils.cpp:177-179).
+__device__ __forceinline__ bool voxel_key_fast(double c, double voxel, double rinv, bool pow2, i64* k) {
+    const double q = c * rinv;
+    if (!(fabs(q) < 1.0e15)) return voxel_key(c, voxel, k);   // also NaN / inf
+    const double f = floor(q);
+    if (!pow2) {
+        const double r = q - f, tol = fabs(q) * 1.7763568394002505e-15 + 1.0e-300;   // 2^-49
+        if (!(r > tol && (1.0 - r) > tol)) return voxel_key(c, voxel, k);
+    }
+    *k = (i64)f;
+    return true;
+}
+
+// slot of `key` in a cloud's table (it is there: k_vox_insert put it)
+__device__ __forceinline__ unsigned vox_hash(unsigned long long key, unsigned size) {
+    return __umulhi((unsigned)((key * 0x9E3779B97F4A7C15ull) >> 32), size);
 }
 
 __global__ void __launch_bounds__(256) k_voxel_minmax(const double* __restrict__ xyz, i64 n, double voxel,
@@ -226,7 +248,7 @@ static constexpr int VTILE = 256 * VROWS;              // rows per block iterati
 static constexpr int PATCH_CAP = 4096;                 // members of unproven voxels that the patch-up pass can take
 #define VOX_EMPTY 0xffffffffffffffffull
 enum { FLAG_TABLE_FULL = 4, FLAG_PATCH_OVERFLOW = 8 };
-// VoxSlot::flags while inserting: bit a (0..2): a member's coordinate a is finer than 2^-33; bit 3: finer than
+// VoxAcc::flags while inserting: bit a (0..2): a member's coordinate a is finer than 2^-33; bit 3: finer than
 // 2^-44 (not representable in the sums).  After k_vox_finalize: 0, or 1 + output row of a voxel that needs the
 // ordered sum.
 enum { VF_FINE_X = 1, VF_FINE_Y = 2, VF_FINE_Z = 4, VF_UNREPRESENTABLE = 8 };
@@ -236,16 +258,16 @@ struct VoxCloud {   // per cloud, device-resident
     i64 tab_off;    // first slot of the cloud's table
     i64 tile_off;   // first tile (VTILE rows) of the cloud
     int n;
-    unsigned mask;  // slots - 1
+    unsigned size;  // slots of the cloud's table (a multiple of 256, not a power of two: no rounding up to 2x)
 };
 
-// one voxel of a cloud's hash table: 48 bytes, at most two 32-byte sectors
-struct alignas(16) VoxSlot {
-    unsigned long long key;   // packed (kx, ky, kz) or VOX_EMPTY
+// One voxel of a cloud's hash table = one 8-byte key (packed (kx, ky, kz) or VOX_EMPTY) in the key array + one
+// 32-byte accumulator — exactly one sector — in the accumulator array.  Probing walks the keys only: four to a sector,
+// 8 bytes per slot instead of 48, so a cloud's keys (~0.2 MB) stay in L1/L2 while the scan streams through.
+struct alignas(32) VoxAcc {
     long long sx, sy, sz;     // fixed-point sums of the member coordinates
     unsigned cnt;
     unsigned flags;
-    unsigned long long pad;
 };
 
 __device__ __forceinline__ void load_xyz(const PointSrc& S, i64 row, double& x, double& y, double& z) {
@@ -270,8 +292,8 @@ __device__ __forceinline__ long long vox_fixed(double v, unsigned bit, unsigned*
 // hash + accumulate.  mm: [0..2] min keys, [3..5] max keys; n_vox[c]: distinct voxels of cloud c.
 __global__ void __launch_bounds__(256) k_vox_insert(const PointSrc src, const VoxCloud* __restrict__ clouds,
                                                     const int* __restrict__ tile_cloud, i64 n_tiles, double voxel,
-                                                    VoxSlot* __restrict__ table, unsigned* __restrict__ slot_of_point,
-                                                    int* __restrict__ n_vox, i64* __restrict__ mm,
+                                                    double rinv, int pow2, unsigned long long* __restrict__ tkeys,
+                                                    VoxAcc* __restrict__ tacc, int* __restrict__ n_vox, i64* __restrict__ mm,
                                                     int* __restrict__ flags, i64 perm) {
     __shared__ i64 s_red[8][6];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -282,7 +304,8 @@ __global__ void __launch_bounds__(256) k_vox_insert(const PointSrc src, const Vo
         const int c = tile_cloud[tile];
         const VoxCloud C = clouds[c];
         const i64 t0 = (tile - C.tile_off) * VTILE;
-        VoxSlot* tab = table + C.tab_off;
+        unsigned long long* tab = tkeys + C.tab_off;
+        VoxAcc* acc = tacc + C.tab_off;
         int claimed = 0;  // voxels this thread created in this tile: one counter update per warp and tile
 #pragma unroll
         for (int r = 0; r < VROWS; ++r) {
@@ -294,7 +317,8 @@ __global__ void __launch_bounds__(256) k_vox_insert(const PointSrc src, const Vo
                 double x, y, z;
                 load_xyz(src, C.pt_off + i, x, y, z);
                 i64 kx, ky, kz;
-                bool ok = voxel_key(x, voxel, &kx) & voxel_key(y, voxel, &ky) & voxel_key(z, voxel, &kz);
+                bool ok = voxel_key_fast(x, voxel, rinv, pow2, &kx) & voxel_key_fast(y, voxel, rinv, pow2, &ky) &
+                          voxel_key_fast(z, voxel, rinv, pow2, &kz);
                 if (!ok) {
                     bad |= FLAG_NONFINITE;
                 } else if (kx < -VK_BIAS || kx >= VK_BIAS || ky < -VK_BIAS || ky >= VK_BIAS || kz < -VK_BIAS ||
@@ -307,22 +331,21 @@ __global__ void __launch_bounds__(256) k_vox_insert(const PointSrc src, const Vo
                     const unsigned long long key = ((unsigned long long)(kx + VK_BIAS) << 42) |
                                                    ((unsigned long long)(ky + VK_BIAS) << 21) |
                                                    (unsigned long long)(kz + VK_BIAS);
-                    unsigned s = (unsigned)((key * 0x9E3779B97F4A7C15ull) >> 32) & C.mask;
+                    unsigned s = vox_hash(key, C.size);
                     unsigned probes = 0;
                     while (true) {
-                        unsigned long long cur = __ldcg(&tab[s].key);
+                        unsigned long long cur = __ldcg(&tab[s]);
                         if (cur == VOX_EMPTY) {
-                            cur = atomicCAS(&tab[s].key, VOX_EMPTY, key);
+                            cur = atomicCAS(&tab[s], VOX_EMPTY, key);
                             if (cur == VOX_EMPTY) {
                                 ++claimed;
                                 cur = key;
                             }
                         }
                         if (cur == key) { slot = s; break; }
-                        s = (s + 1u) & C.mask;
-                        if (++probes > C.mask) { bad |= FLAG_TABLE_FULL; break; }
+                        s = s + 1u == C.size ? 0u : s + 1u;
+                        if (++probes >= C.size) { bad |= FLAG_TABLE_FULL; break; }
                     }
-                    slot_of_point[C.pt_off + i] = slot;
                     fx = vox_fixed(x, VF_FINE_X, &fl);
                     fy = vox_fixed(y, VF_FINE_Y, &fl);
                     fz = vox_fixed(z, VF_FINE_Z, &fl);
@@ -345,7 +368,7 @@ __global__ void __launch_bounds__(256) k_vox_insert(const PointSrc src, const Vo
             }
             const bool tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
             if (tail && slot < 0xffffffe0u) {
-                VoxSlot* S = tab + slot;
+                VoxAcc* S = acc + slot;
                 atomicAdd(reinterpret_cast<unsigned long long*>(&S->sx), (unsigned long long)fx);
                 atomicAdd(reinterpret_cast<unsigned long long*>(&S->sy), (unsigned long long)fy);
                 atomicAdd(reinterpret_cast<unsigned long long*>(&S->sz), (unsigned long long)fz);
@@ -385,27 +408,29 @@ __global__ void __launch_bounds__(256) k_vox_insert(const PointSrc src, const Vo
     }
 }
 
-// empty table: key = VOX_EMPTY, everything else 0
-__global__ void __launch_bounds__(256) k_vox_clear(VoxSlot* __restrict__ table, i64 n_slots) {
+// empty table: key = VOX_EMPTY, accumulators 0
+__global__ void __launch_bounds__(256) k_vox_clear(unsigned long long* __restrict__ tkeys, VoxAcc* __restrict__ tacc,
+                                                   i64 n_slots) {
     const i64 g = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n_slots) return;
-    uint4* w = reinterpret_cast<uint4*>(table + g);
-    w[0] = make_uint4(0xffffffffu, 0xffffffffu, 0u, 0u);
+    tkeys[g] = VOX_EMPTY;
+    uint4* w = reinterpret_cast<uint4*>(tacc + g);
+    w[0] = make_uint4(0u, 0u, 0u, 0u);
     w[1] = make_uint4(0u, 0u, 0u, 0u);
-    w[2] = make_uint4(0u, 0u, 0u, 0u);
 }
 
 // occupied slots -> per-cloud compact (relative key, slot) lists.  Tables are multiples of 256 slots, so the 256
 // slots of a block belong to one cloud: one cursor atomic per block.
 __global__ void __launch_bounds__(256) k_vox_list(const VoxCloud* __restrict__ clouds, int n_clouds, i64 n_slots,
-                                                  const VoxSlot* __restrict__ table, const i64* __restrict__ out_off,
+                                                  const unsigned long long* __restrict__ tkeys,
+                                                  const i64* __restrict__ out_off,
                                                   int* __restrict__ cursor, VoxelPack P, u64* __restrict__ lst_key,
                                                   uint32_t* __restrict__ lst_slot) {
     __shared__ int s_wcnt[8];
     __shared__ i64 s_base;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const i64 g = (i64)blockIdx.x * 256 + threadIdx.x;
-    const unsigned long long key = g < n_slots ? table[g].key : VOX_EMPTY;
+    const unsigned long long key = g < n_slots ? tkeys[g] : VOX_EMPTY;
     const bool occ = key != VOX_EMPTY;
     const unsigned bal = __ballot_sync(0xffffffffu, occ);
     if (lane == 0) s_wcnt[warp] = __popc(bal);
@@ -436,13 +461,13 @@ __global__ void __launch_bounds__(256) k_vox_list(const VoxCloud* __restrict__ c
 
 // one thread per output voxel (sorted by key): centroid from the integer sums, or a request for the ordered sum
 __global__ void __launch_bounds__(256) k_vox_finalize(const u64* __restrict__ keys, const uint32_t* __restrict__ slots,
-                                                      i64 m, double voxel, VoxelPack P, VoxSlot* __restrict__ table,
+                                                      i64 m, double voxel, VoxelPack P, VoxAcc* __restrict__ table,
                                                       double* __restrict__ out_xyz, i64* __restrict__ out_keys,
                                                       int* __restrict__ n_unproven) {
     const i64 v = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= m) return;
     const u64 k = keys[v];
-    VoxSlot* S = table + slots[v];
+    VoxAcc* S = table + slots[v];
     const i64 kk[3] = {(i64)(P.sx >= 64 ? 0ull : (k >> P.sx)) + P.minx, (i64)((k >> P.sy) & P.mask_y) + P.miny,
                        (i64)(k & P.mask_z) + P.minz};
     const unsigned cnt = S->cnt, fl = S->flags;
@@ -466,9 +491,9 @@ __global__ void __launch_bounds__(256) k_vox_finalize(const u64* __restrict__ ke
 
 // members of the voxels that asked for the ordered sum: (output row << 32 | input row)
 __global__ void __launch_bounds__(256) k_vox_collect(const VoxCloud* __restrict__ clouds,
-                                                     const int* __restrict__ tile_cloud, i64 n_tiles,
-                                                     const unsigned* __restrict__ slot_of_point,
-                                                     const VoxSlot* __restrict__ table, u64* __restrict__ list,
+                                                     const int* __restrict__ tile_cloud, i64 n_tiles, const PointSrc src,
+                                                     double voxel, const unsigned long long* __restrict__ tkeys,
+                                                     const VoxAcc* __restrict__ tacc, u64* __restrict__ list,
                                                      int* __restrict__ list_n, int* __restrict__ flags,
                                                      const int* __restrict__ n_unproven) {
     if (*n_unproven == 0) return;  // every voxel was proven exact (always, for scans born as float32)
@@ -479,7 +504,17 @@ __global__ void __launch_bounds__(256) k_vox_collect(const VoxCloud* __restrict_
         for (int r = 0; r < VROWS; ++r) {
             const i64 i = t0 + r * 256 + threadIdx.x;
             if (i >= C.n) continue;
-            const unsigned row1 = __ldg(&table[C.tab_off + slot_of_point[C.pt_off + i]].flags);
+            // the row's voxel again (this pass only runs when some voxel asked for it: never for float32-born scans)
+            double x, y, z;
+            load_xyz(src, C.pt_off + i, x, y, z);
+            i64 kx, ky, kz;
+            if (!(voxel_key(x, voxel, &kx) & voxel_key(y, voxel, &ky) & voxel_key(z, voxel, &kz))) continue;
+            const unsigned long long key = ((unsigned long long)(kx + VK_BIAS) << 42) |
+                                           ((unsigned long long)(ky + VK_BIAS) << 21) | (unsigned long long)(kz + VK_BIAS);
+            const unsigned long long* tab = tkeys + C.tab_off;
+            unsigned s = vox_hash(key, C.size);
+            for (unsigned probes = 0; probes < C.size && __ldg(&tab[s]) != key; ++probes) s = s + 1u == C.size ? 0u : s + 1u;
+            const unsigned row1 = __ldg(&tacc[C.tab_off + s].flags);
             if (row1 == 0u) continue;
             const int at = atomicAdd(list_n, 1);
             if (at < PATCH_CAP) list[at] = ((u64)(row1 - 1u) << 32) | (u64)(C.pt_off + i);
@@ -545,14 +580,13 @@ static int voxel_hashed_dev(Ctx* ctx, const PointSrc src, const i64* h_off, int 
         i64 nc = h_off[c + 1] - h_off[c];
         if (nc > 0x7fffffffLL) return SB_OK;
         i64 want = (i64)(ctx->vox_slots_per_point * (double)nc);
-        i64 sl = 256;
-        while (sl < want) sl <<= 1;
+        i64 sl = ((want > 256 ? want : 256) + 255) / 256 * 256;
         if (sl > 0x40000000LL) return SB_OK;
         C.pt_off = h_off[c];
         C.tab_off = n_slots;
         C.tile_off = n_tiles;
         C.n = (int)nc;
-        C.mask = (unsigned)(sl - 1);
+        C.size = (unsigned)sl;
         n_slots += sl;
         n_tiles += (nc + VTILE - 1) / VTILE;
     }
@@ -564,15 +598,15 @@ static int voxel_hashed_dev(Ctx* ctx, const PointSrc src, const i64* h_off, int 
     }
     VoxCloud* d_clouds;
     int* d_tile_cloud;
-    VoxSlot* d_table;
-    unsigned* d_slot_of;
+    unsigned long long* d_tkeys;
+    VoxAcc* d_table;
     int *d_nvox, *d_cursor, *d_list_n;
     i64* d_mm;
     u64* d_list;
     SB_TRY(arena_get(ctx, (size_t)n_clouds, &d_clouds));
     SB_TRY(arena_get(ctx, (size_t)(n_tiles > 0 ? n_tiles : 1), &d_tile_cloud));
+    SB_TRY(arena_get(ctx, (size_t)n_slots, &d_tkeys));
     SB_TRY(arena_get(ctx, (size_t)n_slots, &d_table));
-    SB_TRY(arena_get(ctx, (size_t)n, &d_slot_of));
     SB_TRY(arena_get(ctx, (size_t)2 * n_clouds + 2, &d_nvox));
     SB_TRY(arena_get(ctx, 6, &d_mm));
     SB_TRY(arena_get(ctx, (size_t)PATCH_CAP, &d_list));
@@ -582,7 +616,7 @@ static int voxel_hashed_dev(Ctx* ctx, const PointSrc src, const i64* h_off, int 
     SB_TRY(table_upload(ctx, d_clouds, hc.data(), sizeof(VoxCloud) * n_clouds));
     SB_TRY(table_upload(ctx, d_tile_cloud, h_tile_cloud.data(), sizeof(int) * (size_t)n_tiles));
     trace_mark(ctx, "vox:begin");
-    SB_LAUNCH(ctx, k_vox_clear, ceil_div(n_slots, 256), 256, 0, d_table, n_slots);
+    SB_LAUNCH(ctx, k_vox_clear, ceil_div(n_slots, 256), 256, 0, d_tkeys, d_table, n_slots);
     trace_mark(ctx, "vox:clear");
     SB_CUDA(ctx, cudaMemsetAsync(d_nvox, 0, sizeof(int) * (2 * (size_t)n_clouds + 2), ctx->stream));
     SB_CUDA(ctx, cudaMemsetAsync(ctx->d_flags, 0, sizeof(int), ctx->stream));
@@ -608,8 +642,10 @@ static int voxel_hashed_dev(Ctx* ctx, const PointSrc src, const i64* h_off, int 
         while (perm > 1 && gcd(perm, n_tiles) != 1) ++perm;
         if (perm <= 1 || perm >= n_tiles) perm = 0;
     }
-    SB_LAUNCH(ctx, k_vox_insert, pgrid, 256, 0, src, d_clouds, d_tile_cloud, n_tiles, voxel, d_table, d_slot_of, d_nvox,
-              d_mm, ctx->d_flags, perm);
+    int expo = 0;
+    const int pow2 = frexp(voxel, &expo) == 0.5 ? 1 : 0;   // voxel = 2^e: c * (1 / voxel) is the exact quotient
+    SB_LAUNCH(ctx, k_vox_insert, pgrid, 256, 0, src, d_clouds, d_tile_cloud, n_tiles, voxel, 1.0 / voxel, pow2, d_tkeys,
+              d_table, d_nvox, d_mm, ctx->d_flags, perm);
     trace_mark(ctx, "vox:insert");
     // ---- the only host round trip: flags, key range, voxels per cloud (into pinned memory: a pageable target would
     // make the driver stage the copies)
@@ -638,8 +674,11 @@ static int voxel_hashed_dev(Ctx* ctx, const PointSrc src, const i64* h_off, int 
     h_out_off[0] = 0;
     for (int c = 0; c < n_clouds; ++c) h_out_off[c + 1] = h_out_off[c] + nvox[c];
     const i64 m = h_out_off[n_clouds];
-    {  // size the next call's tables for 2 slots per voxel (before rounding up to a power of two) at this density
-        static const double per_voxel = getenv("SB_VOX_SLOTS") ? atof(getenv("SB_VOX_SLOTS")) : 2.0;
+    {  // Size the next call's tables for 3 slots per voxel at this batch's AVERAGE density.  The tables are sized per
+        // cloud from its row count, so a cloud that is richer than the average runs at a higher load: with 2 slots
+        // per voxel the 64 different scenes of config C5 put some clouds at 80-100 % load and the linear probe chains
+        // made the whole insert 25 % slower (9.5 vs 7.6 ms per 2048 scans; 1.5: 13.6 ms; 4: 7.7 ms).
+        static const double per_voxel = getenv("SB_VOX_SLOTS") ? atof(getenv("SB_VOX_SLOTS")) : 3.0;
         double r = per_voxel * (double)m / (double)n;
         ctx->vox_slots_per_point = r < 0.0625 ? 0.0625 : (r > 2.0 ? 2.0 : r);
     }
@@ -661,7 +700,7 @@ static int voxel_hashed_dev(Ctx* ctx, const PointSrc src, const i64* h_off, int 
     SB_TRY(arena_get(ctx, (size_t)n_clouds + 1, &d_out_off));
     SB_TRY(table_upload(ctx, d_out_off, h_out_off, sizeof(i64) * (n_clouds + 1)));
     trace_mark(ctx, "vox:after-sync1");
-    SB_LAUNCH(ctx, k_vox_list, ceil_div(n_slots, 256), 256, 0, d_clouds, n_clouds, n_slots, d_table, d_out_off, d_cursor, P,
+    SB_LAUNCH(ctx, k_vox_list, ceil_div(n_slots, 256), 256, 0, d_clouds, n_clouds, n_slots, d_tkeys, d_out_off, d_cursor, P,
               ka, va);
     trace_mark(ctx, "vox:list");
     SB_TRY(segmented_sort_pairs(ctx, ka, kb, va, vb, h_out_off, n_clouds, bx + by + bz, &ks, &vs));
@@ -669,7 +708,7 @@ static int voxel_hashed_dev(Ctx* ctx, const PointSrc src, const i64* h_off, int 
     SB_LAUNCH(ctx, k_vox_finalize, ceil_div(m, 256), 256, 0, ks, vs, m, voxel, P, d_table, d_out_xyz, d_out_keys,
               d_unproven);
     // ---- ordered re-summation of the voxels that could not be proven exact
-    SB_LAUNCH(ctx, k_vox_collect, pgrid, 256, 0, d_clouds, d_tile_cloud, n_tiles, d_slot_of, d_table, d_list, d_list_n,
+    SB_LAUNCH(ctx, k_vox_collect, pgrid, 256, 0, d_clouds, d_tile_cloud, n_tiles, src, voxel, d_tkeys, d_table, d_list, d_list_n,
               ctx->d_flags, d_unproven);
     SB_LAUNCH(ctx, k_vox_patch, 1, 1024, 0, src, d_list, d_list_n, d_out_xyz);
     trace_mark(ctx, "vox:finalize+patch");
