@@ -324,23 +324,7 @@ def sub_c4(eng, slam_b200, syn, torch, dist, rank, world_size, n_db=4000, reps=1
     del d_raw
 
     def detect():
-        cd, ce = det.candidates_local()
-        if world_size > 1:
-            md, me = sharding.all_gather_candidates(cd, ce, 16)   # top-10 of the job is inside the union of local top-16
-        else:
-            md, me = sharding.merge_candidates([cd], [ce])
-        md, me = md[:10], me[:10]
-        mine = np.array([j for j, e in enumerate(me) if sharding.owner(e, world_size) == rank], dtype=np.int64)
-        rec = np.zeros((10, 4))
-        if len(mine):
-            res, conv = det.verify_entries(me[mine], md[mine])
-            for k, j in enumerate(mine):
-                rec[j] = (1.0, float(conv[k]), res[k]["icp_fitness"], res[k]["match_frame"])
-        if world_size > 1:
-            t = torch.from_numpy(rec).cuda()
-            dist.all_reduce(t)           # every candidate is verified by exactly one rank
-            rec = t.cpu().numpy()
-        acc = sharding.accept_in_order(me, rec[:, 1] > 0.5, rec[:, 2], 0.3, 10)
+        md, me, acc, _ = sharding.sharded_detect(det, rank, world_size, top_k=10)
         return md, me, acc
 
     for _ in range(3):
@@ -358,16 +342,16 @@ def sub_c4(eng, slam_b200, syn, torch, dist, rank, world_size, n_db=4000, reps=1
     # search alone (device search + candidate copy), for the FLOP rate
     t0 = time.perf_counter()
     for _ in range(reps):
-        det.candidates_local()
+        det.candidates_local(capacity=16)
     dts = (time.perf_counter() - t0) / reps
     det.close()
     q = n_db - 1
-    true_revisits = [int(e) for e in me if abs(((q - int(e)) % int(LOOP_LEN_M))) <= 3 or abs(((q - int(e)) % int(LOOP_LEN_M)) - LOOP_LEN_M) <= 3]
+    true_revisits = [int(e) for e in me[:10] if abs(((q - int(e)) % int(LOOP_LEN_M))) <= 3 or abs(((q - int(e)) % int(LOOP_LEN_M)) - LOOP_LEN_M) <= 3]
     return {"workload": f"1 query (frame {q}) vs {n_db} keyframes of the C2 loop (20x60 descriptors, 60 column shifts), "
                         "top-10 verified by ICP (30 it), database sharded by entry id over the ranks",
             "n_gpus": world_size, "ms_per_detect": dt * 1e3, "ms_search_local": dts * 1e3,
             "descriptor_pairs_per_s": n_db / dts, "gflops_fp64_search": 2 * 60 * 1200 * n_db / dts / 1e9 / 1.0,
-            "top10_entries": [int(e) for e in me], "top10_sc_distance": [float(d) for d in md],
+            "top10_entries": [int(e) for e in me[:10]], "top10_sc_distance": [float(d) for d in md[:10]],
             "accepted_entries": acc, "top10_that_are_true_revisits": len(true_revisits),
             "db_build_s": t_build}
 
@@ -380,7 +364,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=C5_PAIRS, help="independent pairs per step (4096 = config C5)")
-    ap.add_argument("--pairs-per-call", type=int, default=1024, help="pairs handed to one sb_register_batch call")
+    ap.add_argument("--pairs-per-call", type=int, default=4096, help="pairs handed to one sb_register_batch call")
     ap.add_argument("--frames", type=int, default=1000, help="frame pairs of the C2 sub-result")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")

@@ -341,6 +341,47 @@ static int register_batch_impl(Ctx* ctx, PointSrc src, const void* h_raw, const 
     SB_TRY(forest_reserve(ctx, &F, n_index));
     std::vector<i64> off(offsets, offsets + n_clouds + 1);
     const double* d_pts = nullptr;
+    // ---- ICP of the pairs whose scans have arrived, while later chunks are still uploading (pipelined host path):
+    // a pair is ready once both of its clouds are indexed.  Ready pairs are registered in sub-batches on a stream of
+    // their own, so that the few-pairs-left tail of one sub-batch (the GPU is nearly idle then) runs beside the voxel
+    // grid / index / normals of the next chunk instead of in front of them.  Results do not depend on how the pairs
+    // are grouped (every pair's sums are added in its own fixed order).
+    bool pipelined = false;   // set on the chunked host path: index_clouds then also starts the ICP of the ready pairs
+    std::vector<char> launched((size_t)n_pairs, 0);
+    std::vector<IcpPending> pending;
+    std::vector<std::vector<int>> pending_ids;
+    static const int sub_min = getenv("SB_ICP_SUB") ? atoi(getenv("SB_ICP_SUB")) : 256;
+    auto icp_ready_pairs = [&](int c1, bool last) -> int {
+        std::vector<int> ids;
+        for (int p = 0; p < n_pairs; ++p)
+            if (!launched[p] && pair_src[p] < c1 && pair_tgt[p] < c1) ids.push_back(p);
+        if (ids.empty() || (!last && (int)ids.size() < sub_min)) return SB_OK;
+        std::vector<PairDesc> pairs(ids.size());
+        for (size_t i = 0; i < ids.size(); ++i) {
+            const int p = ids[i];
+            memset(&pairs[i], 0, sizeof(PairDesc));
+            pairs[i].tree = tree_of[pair_tgt[p]];
+            pairs[i].src_tree = tree_of[pair_src[p]];
+            pairs[i].n_src = (int)(off[pair_src[p] + 1] - off[pair_src[p]]);
+            launched[p] = 1;
+        }
+        if (!ctx->icp_stream) {
+            SB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->icp_stream, cudaStreamNonBlocking));
+            SB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->icp_ev, cudaEventDisableTiming));
+        }
+        // the ICP stream starts after everything enqueued so far (index + normals of these clouds)
+        SB_CUDA(ctx, cudaEventRecord(ctx->icp_ev, ctx->stream));
+        SB_CUDA(ctx, cudaStreamWaitEvent(ctx->icp_stream, ctx->icp_ev, 0));
+        cudaStream_t main_stream = ctx->stream;
+        ctx->stream = ctx->icp_stream;
+        IcpPending P;
+        const int s = icp_enqueue(ctx, &F, pairs, cfg, &P);
+        ctx->stream = main_stream;
+        SB_TRY(s);
+        pending.push_back(P);
+        pending_ids.push_back(std::move(ids));
+        return SB_OK;
+    };
     // index (+ normals for targets) of the clouds in [c0, c1) (their downsampled rows are final)
     auto index_clouds = [&](int c0, int c1) -> int {
         std::vector<int> ids_t, ids_s;
@@ -362,6 +403,7 @@ static int register_batch_impl(Ctx* ctx, PointSrc src, const void* h_raw, const 
             for (size_t i = 0; i < ids_s.size(); ++i) tree_of[ids_s[i]] = F.n_trees + (int)i;
             SB_TRY(forest_append(ctx, &F, d_pts, off.data(), ids_s.data(), (int)ids_s.size()));
         }
+        if (pipelined && n_pairs > 0) SB_TRY(icp_ready_pairs(c1, c1 == n_clouds));
         return SB_OK;
     };
     // 1. voxel grid (slam_node.cpp:122)
@@ -373,6 +415,8 @@ static int register_batch_impl(Ctx* ctx, PointSrc src, const void* h_raw, const 
         SB_TRY(arena_get(ctx, (size_t)3 * (n_raw > 0 ? n_raw : 1), &d_ds));
         d_pts = d_ds;
         if (h_raw) {  // upload, voxel grid, index and normals chunk by chunk: the copies overlap all of it
+            pipelined = true;
+            if (n_pairs > 0) SB_TRY(icp_reserve_results(ctx, (size_t)n_pairs));
             SB_TRY(upload_voxel_pipelined(ctx, h_raw, src.f32, src.stride, offsets, n_clouds, voxel, d_ds, off.data(),
                                           n_pairs > 0 ? std::function<int(int, int)>(index_clouds)
                                                       : std::function<int(int, int)>()));
@@ -436,8 +480,18 @@ static int register_batch_impl(Ctx* ctx, PointSrc src, const void* h_raw, const 
     if (!indexed) s = index_clouds(0, n_clouds);
     stage_mark(ctx, STAGE_ICP);
     ctx->last_counts[2] = F.n_points;
-    // 4. the ICP loop for all pairs (icp.hpp:174-255)
-    if (s == SB_OK) {
+    // 4. the ICP loop for all pairs (icp.hpp:174-255); on the pipelined host path it was enqueued chunk by chunk
+    if (s == SB_OK && indexed) {
+        s = fetch_sc();
+        std::vector<const int*> idp;
+        for (const std::vector<int>& v : pending_ids) idp.push_back(v.data());
+        if (s == SB_OK) s = icp_collect(ctx, ctx->icp_stream ? ctx->icp_stream : ctx->stream, pending, idp, results);
+        if (s == SB_OK) {
+            i64 q = 0;
+            for (int p = 0; p < n_pairs; ++p) q += (i64)(off[pair_src[p] + 1] - off[pair_src[p]]) * results[p].history_len;
+            ctx->last_counts[3] = q;
+        }
+    } else if (s == SB_OK) {
         std::vector<PairDesc> pairs((size_t)n_pairs);
         for (int p = 0; p < n_pairs; ++p) {
             memset(&pairs[p], 0, sizeof(PairDesc));
@@ -511,6 +565,10 @@ void sb_ctx_destroy(sb_ctx* ctx) {
     cudaFree(c->d_flags);
     for (int i = 0; i < c->ev_created; ++i) cudaEventDestroy(c->ev[i]);
     if (c->pinned) cudaFreeHost(c->pinned);
+    if (c->h_icp_res) cudaFreeHost(c->h_icp_res);
+    if (c->h_icp_passes) cudaFreeHost(c->h_icp_passes);
+    if (c->icp_stream) cudaStreamDestroy(c->icp_stream);
+    if (c->icp_ev) cudaEventDestroy(c->icp_ev);
     if (c->tbuf) cudaFreeHost(c->tbuf);
     for (int i = 0; i < 2; ++i)
         if (c->copy_ev[i]) cudaEventDestroy(c->copy_ev[i]);
@@ -957,6 +1015,7 @@ void sb_loop_free(sb_loop* loop) {
     cudaStreamSynchronize(loop->ctx->stream);
     cudaFree(loop->d_desc);
     cudaFree(loop->d_clouds);
+    cudaFree(loop->d_meta);
     for (double* p : loop->retired) cudaFree(p);
     delete loop;
 }
@@ -993,8 +1052,10 @@ int sb_loop_candidates_local(sb_loop* loop, double* dist, int32_t* entry, int32_
     if (!loop || !count || capacity < 0 || (capacity > 0 && (!dist || !entry))) return SB_ERR_INVALID_ARG;
     Enter g(loop->ctx);
     std::vector<std::pair<double, int>> cand;
-    SB_TRY(loop_candidates(loop, cand));
-    *count = (int32_t)cand.size();
+    int total = 0;
+    // a short list is selected on the device (k x 12 bytes come back instead of one distance per entry)
+    SB_TRY(loop_candidates(loop, cand, capacity > 0 && capacity <= SB_LOOP_SELECT_MAX ? capacity : 0, &total));
+    *count = (int32_t)total;
     for (int i = 0; i < capacity && i < (int)cand.size(); ++i) {
         dist[i] = cand[i].first;
         entry[i] = cand[i].second;
@@ -1016,12 +1077,23 @@ int sb_loop_detect(sb_loop* loop, sb_loop_result* results, int32_t capacity, int
     *count = 0;
     if (loop->world != 1) return fail(c, SB_ERR_INVALID_ARG, "sb_loop_detect needs world == 1; use candidates_local + verify_entries");
     std::vector<std::pair<double, int>> cand;
-    SB_TRY(loop_candidates(loop, cand));
+    int total = 0;
+    // the best SB_LOOP_SELECT_MAX candidates, selected on the device; the full sorted list only if the walk below
+    // gets through all of them without max_candidates acceptances (verified counts successes only)
+    SB_TRY(loop_candidates(loop, cand, SB_LOOP_SELECT_MAX, &total));
     if (cand.empty()) return SB_OK;  // loop_closure.hpp:91
     int chunk = loop->cfg.verify_chunk > 0 ? loop->cfg.verify_chunk : loop->cfg.max_candidates;
     if (chunk < 1) chunk = 1;
     int verified = 0;  // counts acceptances only (loop_closure.hpp:95-97, 121)
-    for (size_t b = 0; b < cand.size() && verified < loop->cfg.max_candidates; b += (size_t)chunk) {
+    bool have_all = (int)cand.size() >= total;
+    for (size_t b = 0; verified < loop->cfg.max_candidates; b += (size_t)chunk) {
+        if (b >= cand.size()) {
+            if (have_all) break;
+            arena_reset(c);
+            SB_TRY(loop_candidates(loop, cand, 0, &total));   // same order, now complete: continue where the short list ended
+            have_all = true;
+            if (b >= cand.size()) break;
+        }
         int m = (int)std::min(cand.size() - b, (size_t)chunk);
         std::vector<int> ent((size_t)m), conv((size_t)m);
         std::vector<double> dist((size_t)m);

@@ -92,6 +92,14 @@ struct Ctx {
     int n_ev = 0, ev_created = 0;
     // SB_PIPE_TRACE=1: named device-time marks on the main stream (trace_mark / trace_dump), a debugging aid
     std::vector<std::pair<const char*, cudaEvent_t>> trace;
+    // icp.cu: pinned staging of the results of the batches enqueued since the last icp_reserve_results
+    static constexpr int ICP_SLOTS = 256;
+    sb_icp_result* h_icp_res = nullptr;
+    size_t icp_res_cap = 0, icp_res_used = 0;
+    int* h_icp_passes = nullptr;
+    int icp_slots_used = 0;
+    cudaStream_t icp_stream = nullptr;     // api.cu: ICP of the pairs whose scans have arrived, beside the next chunk's stages
+    cudaEvent_t icp_ev = nullptr;
     unsigned knn_attr_done = 0;    // forest.cu: k_self_knn instantiations whose shared-memory limit has been raised
     i64 last_icp_iterations = 0;   // max history length of the last icp_batch (launches of k_icp_iter)
     i64 last_counts[4] = {0, 0, 0, 0};  // raw rows, downsampled rows, target rows, sum over pairs of n_src * passes
@@ -325,6 +333,17 @@ struct PairDesc {      // device-resident, one per scan pair
 // stream placed there overlap with the iterations.
 int icp_batch(Ctx* ctx, const Forest* f, const std::vector<PairDesc>& pairs, const sb_icp_config* cfg,
               sb_icp_result* results, const std::function<int()>* after_launch = nullptr);
+// The same in three steps, for callers that enqueue several batches (on ctx->stream as it is set at the time) before
+// waiting: icp_reserve_results(total pairs), icp_enqueue per batch, icp_collect.
+struct IcpPending {
+    int n_pairs;
+    size_t h_off;   // first result of the batch in Ctx::h_icp_res
+    int slot;       // index into Ctx::h_icp_passes
+};
+int icp_reserve_results(Ctx* ctx, size_t n_pairs);
+int icp_enqueue(Ctx* ctx, const Forest* f, const std::vector<PairDesc>& pairs, const sb_icp_config* cfg, IcpPending* out);
+int icp_collect(Ctx* ctx, cudaStream_t stream, const std::vector<IcpPending>& pending, const std::vector<const int*>& ids,
+                sb_icp_result* results);
 int ensure_copy_stream(Ctx* ctx);
 void icp_graph_free(Ctx* ctx);
 
@@ -371,12 +390,17 @@ struct sb_loop {
     size_t desc_cap = 0;             // in descriptors
     double* d_clouds = nullptr;      // rows x 3
     size_t cloud_cap = 0;            // in rows
+    double* d_meta = nullptr;        // slots x 8 bytes: (frame_idx, entry_id) as two int32 — the device-side search filter
+    size_t meta_cap = 0;             // in slots
     std::vector<double*> retired;    // outgrown pools, released with the detector (loop.cu: grow)
 };
 
 namespace sb {
 int loop_add(sb_loop* L, const double* xyz, i64 n, int frame_idx, const double* desc);
 int loop_reserve(sb_loop* L, i64 n_entries, i64 total_rows);
-int loop_candidates(sb_loop* L, std::vector<std::pair<double, int>>& cand);
+// limit > 0: at most `limit` (<= SB_LOOP_SELECT_MAX) best candidates, selected on the device; limit <= 0: all of them.
+// *total: number of candidates under the threshold either way.
+#define SB_LOOP_SELECT_MAX 32
+int loop_candidates(sb_loop* L, std::vector<std::pair<double, int>>& cand, int limit, int* total);
 int loop_verify(sb_loop* L, const int* entries, const double* dist, int n, sb_loop_result* results, int* converged);
 }  // namespace sb

@@ -969,9 +969,15 @@ static int icp_graph_get(Ctx* ctx, IcpGraph** out) {
     return SB_OK;
 }
 
-int icp_batch(Ctx* ctx, const Forest* f, const std::vector<PairDesc>& pairs_in, const sb_icp_config* cfg,
-              sb_icp_result* results, const std::function<int()>* after_launch) {
+// Enqueues the registration of `pairs_in` on ctx->stream and the copy of its results into the context's pinned result
+// buffer; returns without waiting.  Several batches may be enqueued back to back (they share one device-resident
+// IcpJob: stream order keeps them apart); icp_collect waits for all of them.
+int icp_enqueue(Ctx* ctx, const Forest* f, const std::vector<PairDesc>& pairs_in, const sb_icp_config* cfg,
+                IcpPending* out) {
     const int n_pairs = (int)pairs_in.size();
+    out->n_pairs = n_pairs;
+    out->h_off = ctx->icp_res_used;
+    out->slot = -1;
     if (n_pairs == 0) return SB_OK;
     if (cfg->max_iterations < 0 || cfg->max_iterations > SB_MAX_ICP_ITERATIONS)
         return fail(ctx, SB_ERR_INVALID_ARG, "icp: max_iterations %d outside [0, %d]", cfg->max_iterations,
@@ -1067,17 +1073,64 @@ int icp_batch(Ctx* ctx, const Forest* f, const std::vector<PairDesc>& pairs_in, 
         SB_LAUNCH(ctx, k_icp_accum, G->iter_grid, IWARPS * 32, 0, G->d_job);
         SB_LAUNCH(ctx, k_icp_solve, G->solve_grid, 256, 0, G->d_job, 1, none, 0);
     }
-    if (after_launch && *after_launch) SB_TRY((*after_launch)());
-    SB_CUDA(ctx, cudaMemcpyAsync(results, d_res, sizeof(sb_icp_result) * n_pairs, cudaMemcpyDeviceToHost, ctx->stream));
-    int passes = 0;
-    SB_CUDA(ctx, cudaMemcpyAsync(&passes, &G->d_job->passes, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    // results and the pass count: into pinned host memory, asynchronously
+    if (ctx->icp_res_used + (size_t)n_pairs > ctx->icp_res_cap || ctx->icp_slots_used >= Ctx::ICP_SLOTS)
+        return fail(ctx, SB_ERR_CAPACITY, "icp: result staging full (icp_reserve_results sizes it per call)");
+    out->slot = ctx->icp_slots_used++;
+    ctx->icp_res_used += (size_t)n_pairs;
+    SB_CUDA(ctx, cudaMemcpyAsync(ctx->h_icp_res + out->h_off, d_res, sizeof(sb_icp_result) * n_pairs, cudaMemcpyDeviceToHost,
+                                 ctx->stream));
+    SB_CUDA(ctx, cudaMemcpyAsync(ctx->h_icp_passes + out->slot, &G->d_job->passes, sizeof(int), cudaMemcpyDeviceToHost,
+                                 ctx->stream));
+    return SB_OK;
+}
+
+// Pinned staging for the results of all batches enqueued until the next icp_collect (n_pairs in total).
+int icp_reserve_results(Ctx* ctx, size_t n_pairs) {
+    ctx->icp_res_used = 0;
+    ctx->icp_slots_used = 0;
+    if (!ctx->h_icp_passes) SB_CUDA(ctx, cudaHostAlloc(&ctx->h_icp_passes, sizeof(int) * Ctx::ICP_SLOTS, cudaHostAllocDefault));
+    if (n_pairs > ctx->icp_res_cap) {
+        if (ctx->h_icp_res) cudaFreeHost(ctx->h_icp_res);
+        ctx->h_icp_res = nullptr;
+        ctx->icp_res_cap = 0;
+        size_t cap = n_pairs < 64 ? 64 : n_pairs;
+        SB_CUDA(ctx, cudaHostAlloc(&ctx->h_icp_res, sizeof(sb_icp_result) * cap, cudaHostAllocDefault));
+        ctx->icp_res_cap = cap;
+    }
+    return SB_OK;
+}
+
+// Waits for the stream the batches were enqueued on and hands their results out: pending[i]'s pair j goes to
+// results[ids[i][j]] (ids[i] == nullptr: results[offset so far + j]).
+int icp_collect(Ctx* ctx, cudaStream_t stream, const std::vector<IcpPending>& pending, const std::vector<const int*>& ids,
+                sb_icp_result* results) {
+    SB_CUDA(ctx, cudaStreamSynchronize(stream));
+    IcpGraph* G = static_cast<IcpGraph*>(ctx->icp_graph);
     int max_hist = 1;
-    for (int p = 0; p < n_pairs; ++p)
-        if (results[p].history_len > max_hist) max_hist = results[p].history_len;
-    if (G->exec) ctx->launches += 5 + 4 * (i64)passes;  // init + 4 per loop pass + 4 of the final pass
+    size_t seq = 0;
+    for (size_t b = 0; b < pending.size(); ++b) {
+        const IcpPending& P = pending[b];
+        for (int j = 0; j < P.n_pairs; ++j) {
+            const sb_icp_result& r = ctx->h_icp_res[P.h_off + (size_t)j];
+            results[ids[b] ? (size_t)ids[b][j] : seq + (size_t)j] = r;
+            if (r.history_len > max_hist) max_hist = r.history_len;
+        }
+        seq += (size_t)P.n_pairs;
+        if (P.slot >= 0 && G && G->exec) ctx->launches += 5 + 4 * (i64)ctx->h_icp_passes[P.slot];  // init + 4 per pass + 4 final
+    }
     ctx->last_icp_iterations = max_hist;
     return SB_OK;
+}
+
+int icp_batch(Ctx* ctx, const Forest* f, const std::vector<PairDesc>& pairs_in, const sb_icp_config* cfg,
+              sb_icp_result* results, const std::function<int()>* after_launch) {
+    if (pairs_in.empty()) return SB_OK;
+    SB_TRY(icp_reserve_results(ctx, pairs_in.size()));
+    std::vector<IcpPending> pending(1);
+    SB_TRY(icp_enqueue(ctx, f, pairs_in, cfg, &pending[0]));
+    if (after_launch && *after_launch) SB_TRY((*after_launch)());
+    return icp_collect(ctx, ctx->stream, pending, std::vector<const int*>(1, nullptr), results);
 }
 
 }  // namespace sb

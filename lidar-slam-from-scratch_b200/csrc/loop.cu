@@ -39,6 +39,7 @@ int loop_reserve(sb_loop* L, i64 n_entries, i64 total_rows) {
     size_t slots = L->entry_id.size();
     i64 rows = L->cloud_off.empty() ? 0 : L->cloud_off.back();
     if (n_entries > 0) SB_TRY(grow(L, &L->d_desc, &L->desc_cap, (size_t)n_entries, slots, SB_SC_SIZE, (size_t)n_entries));
+    if (n_entries > 0) SB_TRY(grow(L, &L->d_meta, &L->meta_cap, (size_t)n_entries, slots, 1, (size_t)n_entries));
     if (total_rows > 0) SB_TRY(grow(L, &L->d_clouds, &L->cloud_cap, (size_t)total_rows, (size_t)rows, 3, (size_t)total_rows));
     SB_CUDA(L->ctx, cudaStreamSynchronize(L->ctx->stream));
     return SB_OK;
@@ -58,6 +59,11 @@ int loop_add(sb_loop* L, const double* xyz, i64 n, int frame_idx, const double* 
     i64 rows = L->cloud_off.empty() ? 0 : L->cloud_off.back();
     if (L->cloud_off.empty()) L->cloud_off.push_back(0);
     SB_TRY(grow(L, &L->d_desc, &L->desc_cap, slots + 1, slots, SB_SC_SIZE, FIRST_DESC_SLOTS));
+    SB_TRY(grow(L, &L->d_meta, &L->meta_cap, slots + 1, slots, 1, FIRST_DESC_SLOTS));
+    {
+        const int meta[2] = {frame_idx, id};
+        SB_CUDA(ctx, cudaMemcpyAsync(L->d_meta + slots, meta, sizeof(meta), cudaMemcpyHostToDevice, ctx->stream));
+    }
     SB_TRY(grow(L, &L->d_clouds, &L->cloud_cap, (size_t)(rows + n), (size_t)rows, 3, FIRST_CLOUD_ROWS));
     if (n > 0)
         SB_CUDA(ctx, cudaMemcpyAsync(L->d_clouds + 3 * rows, xyz, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, ctx->stream));
@@ -80,10 +86,97 @@ int loop_add(sb_loop* L, const double* xyz, i64 n, int frame_idx, const double* 
     return SB_OK;
 }
 
+// -------------------------------------------------------------------------------------------------------------
+// Candidate selection on the device (loop_closure.hpp:78-92: frame-gap filter, threshold, sort by (distance, entry)):
+// one block.  Every warp keeps the KSEL best (distance, entry) pairs of its share of the database in registers, entry
+// j in lane j, ascending; warp 0 then merges the 32 lists.  The host receives KSEL x 12 bytes and the number of
+// entries under the threshold instead of one distance per database entry.
+// -------------------------------------------------------------------------------------------------------------
+static constexpr int KSEL = SB_LOOP_SELECT_MAX;
+
+struct SelList {   // lane j of a warp holds the j-th best pair
+    unsigned long long d;   // order-preserving image of the distance; ~0: empty
+    int e;
+    __device__ __forceinline__ bool less_than(unsigned long long od, int oe) const { return d < od || (d == od && e < oe); }
+    // inserts the candidates of the lanes in `m` (warp-uniform mask), each lane's own (cd, ce)
+    __device__ __forceinline__ void insert(unsigned m, unsigned long long cd, int ce, int lane) {
+        while (m) {
+            const int b = __ffs(m) - 1;
+            m &= m - 1u;
+            const unsigned long long bd = __shfl_sync(0xffffffffu, cd, b);
+            const int be = __shfl_sync(0xffffffffu, ce, b);
+            const int pos = __popc(__ballot_sync(0xffffffffu, less_than(bd, be)));   // sorted: a prefix
+            if (pos >= 32) continue;
+            const unsigned long long ud = __shfl_up_sync(0xffffffffu, d, 1);
+            const int ue = __shfl_up_sync(0xffffffffu, e, 1);
+            if (lane > pos) { d = ud; e = ue; }
+            else if (lane == pos) { d = bd; e = be; }
+        }
+    }
+};
+
+__global__ void __launch_bounds__(1024) k_loop_select(const double* __restrict__ dist, const int2* __restrict__ meta,
+                                                      int n_db, int last_frame, int frame_gap, double threshold,
+                                                      unsigned long long* __restrict__ out_d, int* __restrict__ out_e,
+                                                      int* __restrict__ out_total) {
+    __shared__ unsigned long long s_d[32][KSEL];
+    __shared__ int s_e[32][KSEL];
+    __shared__ int s_total;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_total = 0;
+    __syncthreads();
+    SelList L;
+    L.d = ~0ull; L.e = 0x7fffffff;
+    int mine = 0;
+    for (int base = warp * 32; base < n_db; base += 1024) {
+        const int i = base + lane;
+        unsigned long long cd = ~0ull;
+        int ce = 0x7fffffff;
+        bool ok = false;
+        if (i < n_db) {
+            const int2 mt = meta[i];
+            const double dv = dist[i];
+            ok = (last_frame - mt.x >= frame_gap) && (dv < threshold);   // loop_closure.hpp:79-81, 86-88 (NaN: false)
+            if (ok) {   // order-preserving image of the double (a cosine distance can round to -1e-16)
+                const unsigned long long b = (unsigned long long)__double_as_longlong(dv);
+                cd = (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+                if (cd == ~0ull) cd = ~0ull - 1ull;
+                ce = mt.y;
+                ++mine;
+            }
+        }
+        // only candidates better than the list's last entry can enter it
+        const unsigned long long ld = __shfl_sync(0xffffffffu, L.d, 31);
+        const int le = __shfl_sync(0xffffffffu, L.e, 31);
+        const unsigned m = __ballot_sync(0xffffffffu, ok && (cd < ld || (cd == ld && ce < le)));
+        L.insert(m, cd, ce, lane);
+    }
+    mine = __reduce_add_sync(0xffffffffu, mine);
+    if (lane == 0 && mine) atomicAdd(&s_total, mine);
+    s_d[warp][lane] = L.d;
+    s_e[warp][lane] = L.e;
+    __syncthreads();
+    if (warp != 0) return;
+    SelList M;
+    M.d = ~0ull; M.e = 0x7fffffff;
+    for (int w = 0; w < 32; ++w) {
+        const unsigned long long cd = s_d[w][lane];
+        const int ce = s_e[w][lane];
+        const unsigned long long ld = __shfl_sync(0xffffffffu, M.d, 31);
+        const int le = __shfl_sync(0xffffffffu, M.e, 31);
+        const unsigned m = __ballot_sync(0xffffffffu, cd != ~0ull && (cd < ld || (cd == ld && ce < le)));
+        M.insert(m, cd, ce, lane);
+    }
+    out_d[lane] = M.d;
+    out_e[lane] = M.e;
+    if (lane == 0) *out_total = s_total;
+}
+
 // loop_closure.hpp:75-92 restricted to the entries this rank owns
-int loop_candidates(sb_loop* L, std::vector<std::pair<double, int>>& cand) {
+int loop_candidates(sb_loop* L, std::vector<std::pair<double, int>>& cand, int limit, int* total) {
     Ctx* ctx = L->ctx;
     cand.clear();
+    if (total) *total = 0;
     if (L->n_global < 2) return SB_OK;  // loop_closure.hpp:69
     int slots = (int)L->entry_id.size();
     int n_db = slots - 1;  // the newest entry (the query) is always the last slot
@@ -91,6 +184,28 @@ int loop_candidates(sb_loop* L, std::vector<std::pair<double, int>>& cand) {
     double* d_out;
     SB_TRY(arena_get(ctx, (size_t)n_db, &d_out));
     SB_TRY(sc_distance_dev(ctx, L->d_desc + (size_t)(slots - 1) * SB_SC_SIZE, L->d_desc, n_db, d_out));
+    if (limit > 0 && limit <= KSEL) {
+        unsigned long long* d_sel_d;
+        int* d_sel_e;
+        SB_TRY(arena_get(ctx, (size_t)KSEL, &d_sel_d));
+        SB_TRY(arena_get(ctx, (size_t)KSEL + 1, &d_sel_e));
+        SB_LAUNCH(ctx, k_loop_select, 1, 1024, 0, d_out, reinterpret_cast<const int2*>(L->d_meta), n_db, L->last_frame,
+                  L->cfg.frame_gap, L->cfg.sc_distance_threshold, d_sel_d, d_sel_e, d_sel_e + KSEL);
+        SB_TRY(pinned_reserve(ctx, KSEL * 12 + 16));
+        unsigned long long* h_d = reinterpret_cast<unsigned long long*>(ctx->pinned);
+        int* h_e = reinterpret_cast<int*>(ctx->pinned + KSEL * 8);
+        SB_CUDA(ctx, cudaMemcpyAsync(h_d, d_sel_d, KSEL * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        SB_CUDA(ctx, cudaMemcpyAsync(h_e, d_sel_e, (KSEL + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (total) *total = h_e[KSEL];
+        for (int i = 0; i < KSEL && i < limit && h_d[i] != ~0ull; ++i) {
+            const unsigned long long b = (h_d[i] >> 63) ? (h_d[i] & 0x7fffffffffffffffull) : ~h_d[i];
+            double d;
+            memcpy(&d, &b, sizeof(d));
+            cand.push_back({d, h_e[i]});
+        }
+        return SB_OK;
+    }
     std::vector<double> dist((size_t)n_db);
     SB_CUDA(ctx, cudaMemcpyAsync(dist.data(), d_out, sizeof(double) * n_db, cudaMemcpyDeviceToHost, ctx->stream));
     SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -99,6 +214,7 @@ int loop_candidates(sb_loop* L, std::vector<std::pair<double, int>>& cand) {
         if (dist[i] < L->cfg.sc_distance_threshold) cand.push_back({dist[i], L->entry_id[i]});  // :86-88
     }
     std::sort(cand.begin(), cand.end());  // loop_closure.hpp:92: (distance, entry) ascending
+    if (total) *total = (int)cand.size();
     return SB_OK;
 }
 

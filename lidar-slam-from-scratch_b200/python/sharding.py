@@ -91,3 +91,49 @@ def accept_in_order(merged_entries, converged, fitness, fitness_threshold, max_c
         if converged[j] and fitness[j] < fitness_threshold:
             accepted.append(int(e))
     return accepted
+
+
+def sharded_detect(det, rank, world, top_k=10):
+    """One detect() of a loop-closure database sharded over `world` ranks (sb_loop_create(rank, world): entry i lives
+    on rank i % world; every rank holds the newest entry, the query).  Every rank calls this collectively:
+      1. local Scan Context search: the rank's best k candidates, selected on the device (the job's best k are
+         inside the union of the local lists);
+      2. all-gather of the local lists, the same (distance, entry) merge on every rank (loop_closure.hpp:92);
+      3. each rank verifies by ICP the candidates it owns (their clouds are local) — the whole list in parallel;
+      4. all-reduce of the verification records (each candidate is verified by exactly one rank); acceptance walks the
+         merged order until max_candidates successes (loop_closure.hpp:95-122: `verified` counts successes only).
+    The reference keeps walking down the candidate list until it has max_candidates acceptances; so if the best
+    k = top_k candidates yield fewer and more candidates exist, k doubles and only the new ones are verified.
+    Returns (merged distances, merged entries, accepted entries, records) with records[j] = [verified, converged,
+    icp_fitness, match_frame, T(16)] for candidate j of the merged list."""
+    k = max(int(top_k), 1)
+    known = {}          # entry -> record, from earlier rounds
+    while True:
+        cd, ce = det.candidates_local(capacity=k)
+        if world > 1:
+            md, me = all_gather_candidates(cd, ce, k)
+        else:
+            md, me = merge_candidates([cd], [ce])
+        md, me = md[:k], me[:k]
+        rec = np.zeros((k, 20))
+        new = [j for j, e in enumerate(me) if int(e) not in known]
+        mine = np.array([j for j in new if owner(me[j], world) == rank], dtype=np.int64)
+        if len(mine):
+            res, conv = det.verify_entries(me[mine], md[mine])
+            for i, j in enumerate(mine):
+                rec[j, :4] = (1.0, float(conv[i]), res[i]["icp_fitness"], res[i]["match_frame"])
+                rec[j, 4:] = np.asarray(res[i]["transform"]).reshape(16)
+        if world > 1:
+            t = torch.from_numpy(rec).to(_device())
+            dist.all_reduce(t)           # every new candidate is verified by exactly one rank: the sum is a gather
+            rec = t.cpu().numpy()
+        for j, e in enumerate(me):
+            if int(e) in known:
+                rec[j] = known[int(e)]
+            else:
+                known[int(e)] = rec[j].copy()
+        acc = accept_in_order(me, rec[:len(me), 1] > 0.5, rec[:len(me), 2], det.cfg.icp_fitness_threshold,
+                              det.cfg.max_candidates)
+        if len(acc) >= det.cfg.max_candidates or len(me) < k:   # enough acceptances, or no candidate left
+            return md, me, acc, rec[:len(me)]
+        k *= 2
