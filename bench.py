@@ -356,6 +356,29 @@ def sub_c4(eng, slam_b200, syn, torch, dist, rank, world_size, n_db=4000, reps=1
             "db_build_s": t_build}
 
 
+def bind_to_gpu_numa_node(torch, device):
+    """Runs this process on the CPUs next to its GPU (sysfs local_cpulist of the GPU's PCI function) so that the pinned
+    staging buffers allocated afterwards and the threads that fill them sit on that NUMA node.  Returns what it did."""
+    try:
+        pr = torch.cuda.get_device_properties(device)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        base = "/sys/bus/pci/devices/" + bdf
+        node = int(open(base + "/numa_node").read().strip())
+        cpus = set()
+        for part in open(base + "/local_cpulist").read().strip().split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return {"pci": bdf, "numa_node": node, "cpus": len(cpus)}
+    except Exception as ex:
+        return {"error": repr(ex)}
+
+
 # ---------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -383,6 +406,7 @@ def main():
     world_size = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(torch, local_rank)   # before any pinned allocation: staging memory next to the GPU
     if world_size > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     assert C5_SCENES % world_size == 0, "ranks own whole scenes: the number of GPUs must divide 64"
@@ -517,6 +541,24 @@ def main():
                     out.append(eng.register_batch(h_np[int(off[2 * c0]):int(off[2 * c1])], o, ps, pt, voxel=VOXEL, cfg=cfg))
                 return out
 
+            # the ceiling of this path: every rank of the job copying its pinned records to its GPU at the same time
+            d_sink = torch.empty((min(n_raw, 1 << 28), 3), dtype=torch.float32, device="cuda")
+            rows_c = d_sink.shape[0]
+            barrier()
+            c0_, c1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps_c = 3
+            c0_.record(stream)
+            for _ in range(reps_c):
+                for r0 in range(0, n_raw, rows_c):
+                    r1 = min(n_raw, r0 + rows_c)
+                    d_sink[:r1 - r0].copy_(h32[r0:r1], non_blocking=True)
+            c1_.record(stream)
+            barrier()
+            t_c = torch.tensor([c0_.elapsed_time(c1_) / reps_c], device="cuda", dtype=torch.float64)
+            if world_size > 1:
+                dist.all_reduce(t_c, op=dist.ReduceOp.MAX)
+            copy_ms = float(t_c.item())
+            del d_sink
             for _ in range(2):
                 gather(step_host())
             barrier()
@@ -543,6 +585,10 @@ def main():
             if world_size > 1:
                 dist.all_reduce(hb)
             e2e["h2d_bytes_per_step"], e2e["d2h_bytes_per_step"] = int(hb[0].item()), int(hb[1].item())
+            # how close the step is to doing nothing but the copies (all ranks at once, same buffers, same node)
+            e2e["h2d_ceiling"] = {"copy_only_ms_per_step": copy_ms, "aggregate_gb_per_s": hb[0].item() / copy_ms / 1e6,
+                                  "pairs_per_s_if_copy_bound": NP / (copy_ms * 1e-3),
+                                  "e2e_frac_of_ceiling": copy_ms / float(t2.item()), "numa": numa}
             del h32
 
         # ---- C4 on every rank (sharded database); the other sub-results on rank 0 at N = 1

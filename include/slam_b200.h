@@ -252,6 +252,23 @@ int sb_global_map(sb_ctx* ctx, const double* xyz, const int64_t* offsets, int32_
 int sb_odometry_poses(sb_ctx* ctx, const sb_icp_result* results, int32_t n, double max_error,
                       const double* initial_pose16, double* poses16_out);
 
+/* ---------------------------------------------------------------- multi-GPU exchanges -------- */
+/* One process per GPU; the caller owns the NCCL communicator (an ncclComm_t passed as void*; NCCL itself is looked up
+ * in the already-loaded libnccl.so.2 at first use, it is not a link dependency of this library).  The reference has no
+ * counterpart: these are the two exchanges of the sharded paths, KB-sized, once per batch / per detect().
+ *
+ * Batched independent pair ICP (config C5): unit (pair) u is registered by rank u % world as that rank's local result
+ * u / world (sb_register_batch on the rank's own pairs).  Every rank receives all n_total results in unit order.
+ * local: this rank's results (NULL allowed when it owns none); all: n_total records. */
+int sb_gather_results(sb_ctx* ctx, void* nccl_comm, int32_t rank, int32_t world, const sb_icp_result* local,
+                      int32_t n_total, sb_icp_result* all);
+/* Sharded loop-closure search (config C4): every rank contributes up to `capacity` local candidates
+ * (sb_loop_candidates_local: ascending (distance, entry)); every rank receives the `capacity` best of the job in the
+ * order of loop_closure.hpp:92.  Each rank then verifies the entries it owns (sb_loop_verify_entries) and the
+ * records go through sb_gather_results-style exchange or the caller's own. */
+int sb_gather_candidates(sb_ctx* ctx, void* nccl_comm, int32_t world, const double* dist, const int32_t* entry,
+                         int32_t n_local, int32_t capacity, double* out_dist, int32_t* out_entry, int32_t* out_count);
+
 /* ---------------------------------------------------------------- pose-graph hand-off ----- */
 /* The pose graph itself (slam::PoseGraph, GTSAM) stays on the host and is not part of this library.  These two
  * entries turn a batch of registration / loop-closure results into the factors process_frame hands to it one frame

@@ -246,7 +246,9 @@ struct GridSlot {
 struct alignas(32) TreePoint {
     double x, y, z;
     int idx;   // original row of the point, local to its cloud
-    int pad;
+    int pad;   // float bits: a lower bound of the distance to the nearest OTHER point of the cloud (entry 1 of the point's
+               // neighbour list, NbrEntry::r), written with the normals; 0 until then.  It rides in the point's own
+               // sector, so icp.cu's walk can prove "this point is the nearest neighbour" from one load.
 };
 // Unit normal of a sorted point (icp.hpp:23-67), padded to one sector.
 struct alignas(32) TreeNormal {

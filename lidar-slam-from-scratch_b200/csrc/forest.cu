@@ -585,6 +585,7 @@ __global__ void __launch_bounds__(QWARPS * 32) k_knn(ForestView F, const double*
                     e.r = have ? __fmul_rd(__fsqrt_rd(__double2float_rd(V.ld)), 0.999999f) : __int_as_float(0x7f800000);
                     nbr_sorted[(T.pt_off + I.q_off + j) * k + lane] = e;
                     if (lane == 1 && have) spacing += (unsigned long long)(fminf(e.r, 1.0e6f) * 65536.0f);
+                    if (lane == 1) const_cast<TreePoint*>(T.pts)[T.pt_off + I.q_off + j].pad = have ? __float_as_int(e.r) : 0;
                 }
                 if (lane == j) my_m = m;
             } else {
@@ -768,7 +769,7 @@ int forest_normals(Ctx* ctx, Forest* f, int k, double* d_out_normals, double* d_
 #undef SB_SELF_KNN
         SB_LAUNCH(ctx, k_knn_redo, ctx->sm_count * 8, QWARPS * 32, 0, view_of(f, B.t0), d_redo, d_redo_count, k, B.nbr);
         SB_LAUNCH(ctx, k_normals_from_graph, (unsigned)((n_items * 32 + 255) / 256), 256, 0, view_of(f, B.t0), d_tio,
-                  n_items, B.n_trees, k, B.nbr, B.normals, d_out_normals, d_out_evals, d_spacing);
+                  n_items, B.n_trees, k, B.nbr, B.pts, B.normals, d_out_normals, d_out_evals, d_spacing);
         if (d_stats) {
             unsigned long long h[PS_N];
             SB_CUDA(ctx, cudaMemcpyAsync(h, d_stats, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));

@@ -248,6 +248,11 @@ __device__ __forceinline__ void walk_lane(const TreeDesc& T, int K, const double
         bpos = -1;
         return;
     }
+    {   // One-load proof: every other point is at least r1 from the centre (TreePoint::pad), hence at least r1 - |q c|
+        // from the query; if that exceeds |q c| the centre IS the nearest neighbour — no list, no candidates.
+        const float dc = sqrt_up(bd);
+        if (__fsub_rd(__int_as_float(c.pad), dc) > dc) { cert = true; return; }
+    }
     for (int hop = 0; hop < MAX_HOPS; ++hop) {
         const float dc = sqrt_up(bd);  // |q centre|: the centre is the best point so far
         float sb = dc;

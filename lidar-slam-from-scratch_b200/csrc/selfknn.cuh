@@ -377,7 +377,7 @@ __global__ void __launch_bounds__(QWARPS * 32) k_knn_redo(ForestView F, const Re
 // like k_self_knn).  Also accumulates the mean distance to the nearest other point (sizes the seed grid).
 __global__ void __launch_bounds__(256) k_normals_from_graph(ForestView F, const i64* __restrict__ tio, i64 n_items,
                                                             int n_trees, int k, const NbrEntry* __restrict__ nbr_sorted,
-                                                            TreeNormal* __restrict__ nrm_sorted,
+                                                            TreePoint* __restrict__ pts, TreeNormal* __restrict__ nrm_sorted,
                                                             double* __restrict__ nrm_orig, double* __restrict__ evals_orig,
                                                             unsigned long long* __restrict__ spacing_acc) {
     const int lane = threadIdx.x & 31;
@@ -392,6 +392,9 @@ __global__ void __launch_bounds__(256) k_normals_from_graph(ForestView F, const 
         int m = 0;
         while (m < k && row[2 * m] >= 0) ++m;   // valid entries come first
         if (k > 1 && m > 1) spacing = (unsigned long long)(fminf(__int_as_float(row[3]), 1.0e6f) * 65536.0f);
+        // the nearest-other-point bound into the point's own sector (TreePoint::pad); with k == 1 or a single point
+        // nothing is known: 0
+        pts[T.pt_off + pos].pad = (k > 1 && m > 1) ? row[3] : 0;
         normal_of_point(T, row, 2, m, T.pt_off + pos, nrm_sorted, nrm_orig, evals_orig);
     }
 #pragma unroll

@@ -122,6 +122,8 @@ SYMBOLS = {
     "sb_loop_candidates_local": (C.c_int, [_P, _D, _I32, C.c_int32, _I32]),
     "sb_loop_verify_entries": (C.c_int, [_P, _I32, _D, C.c_int32, C.POINTER(LoopResultC), _I32]),
     "sb_odometry_poses": (C.c_int, [_P, C.POINTER(ICPResultC), C.c_int32, C.c_double, _D, _D]),
+    "sb_gather_results": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.POINTER(ICPResultC), C.c_int32, C.POINTER(ICPResultC)]),
+    "sb_gather_candidates": (C.c_int, [_P, _P, C.c_int32, _D, _I32, C.c_int32, C.c_int32, _D, _I32, _I32]),
     "sb_odometry_factors": (C.c_int, [_P, C.POINTER(ICPResultC), C.c_int32, C.c_int32, C.c_double, C.POINTER(PoseFactorC)]),
     "sb_loop_factors": (C.c_int, [_P, C.POINTER(LoopResultC), C.c_int32, C.POINTER(PoseFactorC)]),
     "sb_default_grid_config": (None, [_P]),

@@ -1,10 +1,10 @@
 #!/bin/bash
-# ICP loop variants: open lanes of an item from which the packet traversal takes over
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -q --tb=short --timeout 600 -p no:cacheprovider -x > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log
-for v in ${VARIANTS:-6}; do
-  echo "packet_min=$v"; SB_ICP_PACKET_MIN=$v timeout 600 python scripts/icp_tail_cost.py 2>&1 | tail -7
-done
-timeout 600 python scripts/stream_latency.py --frames 150 | python -c "
+timeout 600 python scripts/icp_tail_cost.py 2>&1 | tail -7
+SB_ICP_STATS=1 timeout 600 python bench.py --pairs 1024 --steps 3 --warmup 3 --no-e2e --no-sub --cpu-seconds 0.1 2>&1 | python -c "
 import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print({k:d[k] for k in ('ms_per_frame_mean','p50','p99','max','split_ms_mean','launches_per_frame')})"
+for l in sys.stdin:
+    if l.startswith('{'):
+        d=json.loads(l); print(d['ms_per_step'], d['roofline']['stages_ms'])
+    elif 'icp iterations' in l: print(l.strip())"

@@ -3,8 +3,8 @@
 N=${1:-2}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name --format=csv,noheader | head -8
-timeout 1500 python -m pytest tests/test_multi_gpu.py tests/test_gpu_parity.py -m gpu -q --tb=short --timeout 1400 -p no:cacheprovider -x -k "sharded or loop" > gpurun_out/pytest_multi.log 2>&1; tail -5 gpurun_out/pytest_multi.log
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N --pairs ${PAIRS:-1024} --steps 3 --warmup 3 > gpurun_out/bench_${N}gpu.log 2>&1; echo "bench exit $?"
+timeout 1500 python -m pytest tests/test_multi_gpu.py -m gpu -q --tb=short --timeout 1400 -p no:cacheprovider -x  > gpurun_out/pytest_multi.log 2>&1; tail -5 gpurun_out/pytest_multi.log
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N --pairs ${PAIRS:-4096} --steps 3 --warmup 3 > gpurun_out/bench_${N}gpu.log 2>&1; echo "bench exit $?"
 grep -v "^{" gpurun_out/bench_${N}gpu.log | tail -5
 python - <<PY
 import json

@@ -15,6 +15,11 @@ g++ -std=c++17 -O2 -Wall -Wno-unused-function -I$ROOT/oracle/eigen_standin -I$RO
     -L$ROOT/lidar-slam-from-scratch_b200 -lslam_b200 -L$ROOT/oracle -loracle -L$ROOT/synth -lsynth \
     -Wl,-rpath,'$ORIGIN/../../lidar-slam-from-scratch_b200' -Wl,-rpath,'$ORIGIN/../../oracle' -Wl,-rpath,'$ORIGIN/../../synth'
 echo "built tests/cpp/host_api_test and tests/cpp/host_api_test_eigenapi"
+# the multi-GPU exchanges from a C++ host program (NCCL communicator owned by the caller)
+g++ -std=c++17 -O2 -Wall -I$ROOT/include -I/usr/local/cuda/include gather_test.cpp -o gather_test \
+    -L$ROOT/lidar-slam-from-scratch_b200 -lslam_b200 -lnccl -L/usr/local/cuda/lib64 -lcudart \
+    -Wl,-rpath,'$ORIGIN/../../lidar-slam-from-scratch_b200'
+echo "built tests/cpp/gather_test"
 
 # The node's include order and call sites against the mirror, compile-only, in both branches of dense.hpp.
 REF=${SLAM_REFERENCE:-/root/reference}/slam_viz

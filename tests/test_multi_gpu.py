@@ -64,3 +64,20 @@ def test_sharded_loop_closure_matches_single_gpu(tmp_path):
             assert item["converged"] == ref["converged"]
             assert np.allclose(item["transforms"], ref["transforms"], rtol=0, atol=1e-12)
             assert np.allclose(item["fitness"], ref["fitness"], rtol=0, atol=1e-12)
+
+
+def test_c_abi_gather_from_a_cpp_host(tmp_path):
+    """sb_gather_results / sb_gather_candidates (include/slam_b200.h) called from a C++ program that owns its NCCL
+    communicator, one process per GPU (world 1 when a single GPU is visible: the plumbing, including the lookup of
+    NCCL in the already loaded library, is the same)."""
+    subprocess.check_call(["sh", os.path.join(ROOT, "tests", "cpp", "build.sh")])
+    exe = os.path.join(ROOT, "tests", "cpp", "gather_test")
+    g = n_gpus()
+    for world in sorted({1, min(2, g), min(4, g), min(8, g)}):
+        idf = tmp_path / f"nccl_id_{world}"
+        procs = [subprocess.Popen([exe, str(r), str(world), str(idf)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                                  text=True, env=dict(os.environ, NCCL_DEBUG="WARN")) for r in range(world)]
+        outs = [p.communicate(timeout=600)[0] for p in procs]
+        for r, (p, o) in enumerate(zip(procs, outs)):
+            assert p.returncode == 0, f"world {world} rank {r}:\n{o}"
+            assert "all checks passed" in o
