@@ -243,6 +243,7 @@ static constexpr int VQ_COARSE_TZ = 11;                // a coordinate is "coars
 static constexpr double VQ_LIMIT_COARSE = 524288.0;    // 2^19: sum|v| below this -> no wrap, fp64 loop exact (coarse)
 static constexpr double VQ_LIMIT_FINE = 512.0;         // 2^(53-44): sum|v| bound when some member is finer
 static constexpr int VK_BIAS = 1 << 20;                // keys are packed as (k + 2^20), 21 bits per axis
+static constexpr int VGROUP = 4;                       // lanes of one run whose sums are combined before the atomics
 static constexpr int VROWS = 4;                        // rows per thread and block iteration
 static constexpr int VTILE = 256 * VROWS;              // rows per block iteration
 static constexpr int PATCH_CAP = 4096;                 // members of unproven voxels that the patch-up pass can take
@@ -294,13 +295,17 @@ __global__ void __launch_bounds__(256) k_vox_insert(const PointSrc src, const Vo
                                                     const int* __restrict__ tile_cloud, i64 n_tiles, double voxel,
                                                     double rinv, int pow2, unsigned long long* __restrict__ tkeys,
                                                     VoxAcc* __restrict__ tacc, int* __restrict__ n_vox, i64* __restrict__ mm,
-                                                    int* __restrict__ flags, i64 perm) {
+                                                    int* __restrict__ flags, i64 win, i64 perm, i64 perm_last) {
     __shared__ i64 s_red[8][6];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     i64 lo[3] = {INT64_MAX, INT64_MAX, INT64_MAX}, hi[3] = {INT64_MIN, INT64_MIN, INT64_MIN};
     int bad = 0;
     for (i64 tile_seq = blockIdx.x; tile_seq < n_tiles; tile_seq += gridDim.x) {
-        const i64 tile = perm ? (i64)(((unsigned long long)tile_seq * (unsigned long long)perm) % (unsigned long long)n_tiles) : tile_seq;
+        // scattered inside a window of `win` consecutive tiles (see the host side)
+        const i64 w0 = (tile_seq / win) * win;
+        const i64 wn = n_tiles - w0 < win ? n_tiles - w0 : win;
+        const i64 pw = wn == win ? perm : perm_last;
+        const i64 tile = pw ? w0 + (i64)(((unsigned long long)(tile_seq - w0) * (unsigned long long)pw) % (unsigned long long)wn) : tile_seq;
         const int c = tile_cloud[tile];
         const VoxCloud C = clouds[c];
         const i64 t0 = (tile - C.tile_off) * VTILE;
@@ -352,27 +357,30 @@ __global__ void __launch_bounds__(256) k_vox_insert(const PointSrc src, const Vo
                 }
             }
             // runs of consecutive lanes in the same voxel (neighbouring rays) add up inside the warp first: a segmented
-            // inclusive scan, integers, exact in any order; the last lane of a run sends the run to the table
+            // inclusive scan, integers, exact in any order.  Runs are cut into aligned groups of VGROUP lanes — two
+            // shuffle steps instead of five (the full scan was 36 % of this kernel's instructions; most runs are
+            // short) — and the last lane of a group sends the group's sums to the table.
             const unsigned prev_slot = __shfl_up_sync(0xffffffffu, slot, 1);
             const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || slot != prev_slot);
             const int run_start = 31 - __clz(heads & (lanemask_lt() | (1u << lane)));
+            const int group_start = run_start + ((lane - run_start) & ~(VGROUP - 1));
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
+            for (int d = 1; d < VGROUP; d <<= 1) {
                 const long long ox = __shfl_up_sync(0xffffffffu, fx, d), oy = __shfl_up_sync(0xffffffffu, fy, d),
                                 oz = __shfl_up_sync(0xffffffffu, fz, d);
                 const unsigned of = __shfl_up_sync(0xffffffffu, fl, d);
-                if (lane - d >= run_start) {
+                if (lane - d >= group_start) {
                     fx += ox; fy += oy; fz += oz;
                     fl |= of;
                 }
             }
-            const bool tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
+            const bool tail = lane == 31 || ((heads >> (lane + 1)) & 1u) || ((lane - run_start) & (VGROUP - 1)) == VGROUP - 1;
             if (tail && slot < 0xffffffe0u) {
                 VoxAcc* S = acc + slot;
                 atomicAdd(reinterpret_cast<unsigned long long*>(&S->sx), (unsigned long long)fx);
                 atomicAdd(reinterpret_cast<unsigned long long*>(&S->sy), (unsigned long long)fy);
                 atomicAdd(reinterpret_cast<unsigned long long*>(&S->sz), (unsigned long long)fz);
-                atomicAdd(&S->cnt, (unsigned)(lane - run_start + 1));
+                atomicAdd(&S->cnt, (unsigned)(lane - group_start + 1));
                 if (fl) atomicOr(&S->flags, fl);
             }
         }
@@ -631,21 +639,29 @@ static int voxel_hashed_dev(Ctx* ctx, const PointSrc src, const i64* h_off, int 
     if (want_grid < (i64)ctx->sm_count * 4) want_grid = (i64)ctx->sm_count * 4;
     if (want_grid > (i64)ctx->sm_count * per_sm) want_grid = (i64)ctx->sm_count * per_sm;
     const int pgrid = (int)(n_tiles < want_grid ? n_tiles : want_grid);
-    // Tiles are visited in a scattered order (tile = seq * stride mod n_tiles, stride coprime with n_tiles): in
-    // sequence order the resident CTAs all work on the same five or six scans, whose neighbouring beams hit the
-    // same voxels, and their atomics queue up on the same slots (measured: 18-20 % faster at every batch size)
-    i64 perm = 0;
-    if (n_tiles > 2) {
+    // Tiles are visited in a scattered order: in sequence order the resident CTAs all work on the same five or six
+    // scans, whose neighbouring beams hit the same voxels, and their atomics queue up on the same slots (measured:
+    // 18-20 % faster scattered).  But scattered over the WHOLE batch every cloud's table is live at once — 1.9 GB for
+    // 2048 scans against 126 MB of L2, so every accumulator update went to DRAM (ncu: 12.3 GB moved for 5.8 GB of
+    // input).  So the scatter stays inside a window of consecutive tiles worth ~48 clouds (tile = w0 + (seq - w0) *
+    // stride mod window, stride coprime with the window): their tables (~45 MB) stay in L2.
+    auto gcd = [](i64 a, i64 b) { while (b) { i64 t = a % b; a = b; b = t; } return a; };
+    auto coprime_stride = [&](i64 n) -> i64 {
         static const i64 stride = getenv("SB_VOX_PERM") ? atoll(getenv("SB_VOX_PERM")) : 7919;
-        auto gcd = [](i64 a, i64 b) { while (b) { i64 t = a % b; a = b; b = t; } return a; };
-        perm = stride % n_tiles;
-        while (perm > 1 && gcd(perm, n_tiles) != 1) ++perm;
-        if (perm <= 1 || perm >= n_tiles) perm = 0;
-    }
+        if (n <= 2) return 0;
+        i64 p = stride % n;
+        while (p > 1 && gcd(p, n) != 1) ++p;
+        return (p <= 1 || p >= n) ? 0 : p;
+    };
+    static const int win_clouds = getenv("SB_VOX_WINDOW") ? atoi(getenv("SB_VOX_WINDOW")) : 48;
+    i64 win = n_clouds > 0 ? (n_tiles * (i64)(win_clouds > 0 ? win_clouds : 1) + n_clouds - 1) / n_clouds : n_tiles;
+    if (win < 1) win = 1;
+    if (win > n_tiles) win = n_tiles > 0 ? n_tiles : 1;
+    const i64 perm = coprime_stride(win), perm_last = coprime_stride(n_tiles % win);
     int expo = 0;
     const int pow2 = frexp(voxel, &expo) == 0.5 ? 1 : 0;   // voxel = 2^e: c * (1 / voxel) is the exact quotient
     SB_LAUNCH(ctx, k_vox_insert, pgrid, 256, 0, src, d_clouds, d_tile_cloud, n_tiles, voxel, 1.0 / voxel, pow2, d_tkeys,
-              d_table, d_nvox, d_mm, ctx->d_flags, perm);
+              d_table, d_nvox, d_mm, ctx->d_flags, win, perm, perm_last);
     trace_mark(ctx, "vox:insert");
     // ---- the only host round trip: flags, key range, voxels per cloud (into pinned memory: a pageable target would
     // make the driver stage the copies)

@@ -250,13 +250,23 @@ def test_find_correspondences(engine, oracle, small_pair):
 
 
 # ------------------------------------------------------------------ normals
-def check_normals(gn, ge, on, oe):
+def check_normals(gn, ge, on, oe, expect_excluded):
+    """Normals within 1e-4 (north_star) on the points whose two smallest eigenvalues are separated — where they are not
+    (neighbours almost on a line: one LiDAR ring) the direction is numerically arbitrary for ANY two eigen-solvers
+    (SURVEY.md H3).  The excluded fraction is reported and must be the one SURVEY.md H3 measured for this
+    configuration (about 3 % at 64 beams / 0.5 m / k = 20, about 13 % at 128 beams / 0.2 m / k = 10; this scene:
+    4.5 % and 14.9 %), so that the filter cannot quietly swallow a broken kernel.  Eigenvalues, unit length and the
+    z >= 0 orientation (icp.hpp:59-63) are checked on ALL points."""
     assert np.allclose(ge, oe, rtol=1e-9, atol=1e-12)
     ok = (oe[:, 1] - oe[:, 0]) / np.maximum(oe[:, 2], 1e-300) > 1e-2  # SURVEY.md H3 eigen-gap filter
-    assert ok.mean() > 0.7
+    excluded = 1.0 - float(ok.mean())
+    exact = float(np.mean(np.all(gn == on, axis=1)))
+    print(f"normals: {len(gn)} points, excluded by the eigen-gap filter {excluded:.4f} (expected ~{expect_excluded}), "
+          f"bit-identical to the oracle {exact:.4f}, max |diff| on the rest {np.max(np.abs(gn[ok] - on[ok])):.2e}")
+    assert abs(excluded - expect_excluded) < 0.02, excluded
     assert np.max(np.abs(gn[ok] - on[ok])) < 1e-4
     assert np.allclose(np.linalg.norm(gn, axis=1), 1.0, atol=1e-12) and np.all(gn[:, 2] >= 0)
-    return float(np.mean(np.all(gn == on, axis=1)))
+    return exact
 
 
 def test_normals_k20_voxel05(engine, oracle, synth, scene):
@@ -265,7 +275,7 @@ def test_normals_k20_voxel05(engine, oracle, synth, scene):
     pts = engine.voxel_downsample(raw, 0.5)
     gn, ge = slam_b200.KDTree(engine, pts).estimate_normals(20, return_evals=True)
     on, oe = oracle.tree(pts).estimate_normals(20)
-    exact = check_normals(gn, ge, on, oe)
+    exact = check_normals(gn, ge, on, oe, expect_excluded=0.045)
     assert exact > 0.99, f"only {exact:.4f} of the normals are bit-identical to the oracle"
 
 
@@ -275,7 +285,8 @@ def test_normals_k10_voxel02(engine, oracle, synth, scene):
     pts = engine.voxel_downsample(raw, 0.2)
     gn, ge = slam_b200.KDTree(engine, pts).estimate_normals(10, return_evals=True)
     on, oe = oracle.tree(pts).estimate_normals(10)
-    check_normals(gn, ge, on, oe)
+    exact = check_normals(gn, ge, on, oe, expect_excluded=0.149)
+    assert exact > 0.99, f"only {exact:.4f} of the normals are bit-identical to the oracle"
 
 
 def test_normals_degenerate(engine):
