@@ -733,7 +733,10 @@ int forest_normals(Ctx* ctx, Forest* f, int k, double* d_out_normals, double* d_
     SB_CUDA(ctx, cudaMemsetAsync(B.grid, 0xff, sizeof(GridSlot) * (size_t)B.n_slots, ctx->stream));
     // one lane per query (k_self_knn) for the k the pipelines use; SB_KNN_PACKET=0 or any other k: one warp per query
     static const bool packet = !(getenv("SB_KNN_PACKET") && atoi(getenv("SB_KNN_PACKET")) == 0);
-    if (packet && (k == 20 || k == 10)) {
+    // k = 10 (config C3: 44 k-point clouds at voxel 0.2) stays with one warp per query unless SB_KNN_PACKET_K10=1: there
+    // the packet kernel measured 4.70 ms against 4.37 ms per 47 clouds (4 % of its queries end in the redo list)
+    static const bool packet10 = getenv("SB_KNN_PACKET_K10") && atoi(getenv("SB_KNN_PACKET_K10")) != 0;
+    if (packet && (k == 20 || (k == 10 && packet10))) {
         static const bool want_stats = getenv("SB_KNN_STATS") != nullptr;
         static const int pcap = getenv("SB_KNN_PCAP") ? atoi(getenv("SB_KNN_PCAP")) : 48;
         unsigned long long* d_stats = nullptr;
@@ -750,11 +753,12 @@ int forest_normals(Ctx* ctx, Forest* f, int k, double* d_out_normals, double* d_
         SB_TRY(arena_get(ctx, (size_t)B.n_points, &d_redo));
         SB_TRY(arena_get(ctx, (size_t)1, &d_redo_count));
         SB_CUDA(ctx, cudaMemsetAsync(d_redo_count, 0, sizeof(int), ctx->stream));
+        static const int tot10 = getenv("SB_KNN_TOT10") ? atoi(getenv("SB_KNN_TOT10")) : 16;
         auto launch = [&](auto kern, int cap_entries) -> int {
             const int row = k | 1;
             const size_t entries = (size_t)(32 * row > cap_entries * 32 ? 32 * row : cap_entries * 32);
             const size_t smem = (size_t)PWARPS * entries * sizeof(int2);
-            const unsigned bit = 1u << ((k == 20 ? 1 : 0) | (cap_entries >= 64 ? 2 : 0) | (want_stats ? 4 : 0));
+            const unsigned bit = 1u << ((k == 20 ? 1 : 0) | (cap_entries >= 64 ? 2 : 0) | (want_stats ? 4 : 0) | (k == 10 && tot10 == 16 ? 8 : 0));
             if (!(ctx->knn_attr_done & bit)) {   // once per kernel instantiation and context (device)
                 SB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 ctx->knn_attr_done |= bit;
@@ -763,9 +767,11 @@ int forest_normals(Ctx* ctx, Forest* f, int k, double* d_out_normals, double* d_
                       d_redo_count, d_stats);
             return SB_OK;
         };
-#define SB_SELF_KNN(KK, CAP) (want_stats ? launch(k_self_knn<KK, 32, CAP, true>, CAP) : launch(k_self_knn<KK, 32, CAP, false>, CAP))
-        if (k == 20) SB_TRY(pcap >= 64 ? SB_SELF_KNN(20, 64) : SB_SELF_KNN(20, 48));
-        else SB_TRY(pcap >= 64 ? SB_SELF_KNN(10, 64) : SB_SELF_KNN(10, 48));
+#define SB_SELF_KNN(KK, TT, CAP) (want_stats ? launch(k_self_knn<KK, TT, CAP, true>, CAP) : launch(k_self_knn<KK, TT, CAP, false>, CAP))
+        // list + batch = 32 registers pairs for k = 20 (batches of 11); for k = 10 either 16 (batches of 5) or 32 (21)
+        if (k == 20) SB_TRY(pcap >= 64 ? SB_SELF_KNN(20, 32, 64) : SB_SELF_KNN(20, 32, 48));
+        else if (tot10 == 16) SB_TRY(SB_SELF_KNN(10, 16, 48));
+        else SB_TRY(SB_SELF_KNN(10, 32, 48));
 #undef SB_SELF_KNN
         SB_LAUNCH(ctx, k_knn_redo, ctx->sm_count * 8, QWARPS * 32, 0, view_of(f, B.t0), d_redo, d_redo_count, k, B.nbr);
         SB_LAUNCH(ctx, k_normals_from_graph, (unsigned)((n_items * 32 + 255) / 256), 256, 0, view_of(f, B.t0), d_tio,
