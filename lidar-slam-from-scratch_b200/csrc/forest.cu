@@ -231,10 +231,15 @@ __global__ void __launch_bounds__(256) k_boxes_up(const TreeDesc* __restrict__ t
 void forest_free(Forest* f) {
     if (!f) return;
     if (!f->in_arena) {
+        // cudaFree only fails on a context that is already broken (a sticky error of an earlier kernel): it is recorded
+        // for sb_last_error, there is nothing else to do with it while tearing down
+        cudaError_t e = cudaSuccess;
+        auto rel = [&](void* p) { const cudaError_t r = cudaFree(p); if (r != cudaSuccess) e = r; };
         for (ForestBatch& B : f->batches) {
-            cudaFree(B.pts); cudaFree(B.pts32); cudaFree(B.boxes); cudaFree(B.normals); cudaFree(B.nbr); cudaFree(B.grid);
+            rel(B.pts); rel(B.pts32); rel(B.boxes); rel(B.normals); rel(B.nbr); rel(B.grid);
         }
-        cudaFree(f->d_trees);
+        rel(f->d_trees);
+        if (e != cudaSuccess && f->ctx) fail(f->ctx, SB_ERR_CUDA, "index: cudaFree failed: %s", cudaGetErrorString(e));
     }
     f->batches.clear();
     f->d_trees = nullptr;

@@ -259,9 +259,10 @@ int loop_verify(sb_loop* L, const int* entries, const double* dist, int n, sb_lo
         }
         s = icp_batch(ctx, &F, pairs, &cfg, res.data());
     }
-    cudaStreamSynchronize(ctx->stream);
+    const cudaError_t sync_err = cudaStreamSynchronize(ctx->stream);
     forest_free(&F);
     if (s != SB_OK) return s;
+    if (sync_err != cudaSuccess) return fail(ctx, SB_ERR_CUDA, "loop: verification failed on the device: %s", cudaGetErrorString(sync_err));
     for (int i = 0; i < n; ++i) {
         sb_loop_result& R = results[i];
         R.query_frame = L->last_frame;

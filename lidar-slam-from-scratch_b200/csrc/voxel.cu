@@ -19,6 +19,7 @@
 // if there are too many of them, or keys do not fit 21 bits per axis, the call falls back to the sort.
 #include "common.cuh"
 
+#include <climits>
 #include <cmath>
 #include <cstdlib>
 
@@ -44,16 +45,28 @@ __device__ __forceinline__ bool voxel_key(double c, double voxel, i64* k) {
 // a power of two (pow2) c * rinv IS c / voxel.  Otherwise q~ = fl(c * rinv) is within 2^-51 |q~| of the exact quotient
 // and fl(c / voxel) within 2^-53: unless q~ lies within 2^-49 |q~| of an integer all three have the same floor; the
 // rare rest (and huge quotients) takes the IEEE division the reference performs (file_utils.cpp:177-179).
-__device__ __forceinline__ bool voxel_key_fast(double c, double voxel, double rinv, bool pow2, i64* k) {
+// the rare exact path, out of line: inlined, its twelve copies (three axes x four rows) made k_vox_insert 64 KB of code
+__device__ __noinline__ bool voxel_key_slow(double c, double voxel, i64* k) { return voxel_key(c, voxel, k); }
+
+// -> 0 and the key as a 32-bit integer inside the 21-bit window of the packed table keys, or the flag that makes the
+// call fail (non-finite) / fall back to the sort (key outside the window)
+__device__ __forceinline__ int voxel_key_fast(double c, double voxel, double rinv, bool pow2, int* k) {
     const double q = c * rinv;
-    if (!(fabs(q) < 1.0e15)) return voxel_key(c, voxel, k);   // also NaN / inf
     const double f = floor(q);
-    if (!pow2) {
+    bool exact = !(fabs(q) < 1048575.0);   // outside the window, NaN, inf: the exact path classifies it
+    if (!pow2 && !exact) {
         const double r = q - f, tol = fabs(q) * 1.7763568394002505e-15 + 1.0e-300;   // 2^-49
-        if (!(r > tol && (1.0 - r) > tol)) return voxel_key(c, voxel, k);
+        exact = !(r > tol && (1.0 - r) > tol);
     }
-    *k = (i64)f;
-    return true;
+    if (exact) {
+        i64 kk;
+        if (!voxel_key_slow(c, voxel, &kk)) return FLAG_NONFINITE;
+        if (kk < -(i64)(1 << 20) || kk >= (i64)(1 << 20)) return FLAG_KEY_RANGE;
+        *k = (int)kk;
+        return 0;
+    }
+    *k = (int)f;   // |f| < 2^20
+    return 0;
 }
 
 // slot of `key` in a cloud's table (it is there: k_vox_insert put it)
@@ -298,7 +311,7 @@ __global__ void __launch_bounds__(256) k_vox_insert(const PointSrc src, const Vo
                                                     int* __restrict__ flags, i64 win, i64 perm, i64 perm_last) {
     __shared__ i64 s_red[8][6];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    i64 lo[3] = {INT64_MAX, INT64_MAX, INT64_MAX}, hi[3] = {INT64_MIN, INT64_MIN, INT64_MIN};
+    int lo[3] = {INT_MAX, INT_MAX, INT_MAX}, hi[3] = {INT_MIN, INT_MIN, INT_MIN};
     int bad = 0;
     for (i64 tile_seq = blockIdx.x; tile_seq < n_tiles; tile_seq += gridDim.x) {
         // scattered inside a window of `win` consecutive tiles (see the host side)
@@ -321,14 +334,11 @@ __global__ void __launch_bounds__(256) k_vox_insert(const PointSrc src, const Vo
             if (i < C.n) {
                 double x, y, z;
                 load_xyz(src, C.pt_off + i, x, y, z);
-                i64 kx, ky, kz;
-                bool ok = voxel_key_fast(x, voxel, rinv, pow2, &kx) & voxel_key_fast(y, voxel, rinv, pow2, &ky) &
-                          voxel_key_fast(z, voxel, rinv, pow2, &kz);
-                if (!ok) {
-                    bad |= FLAG_NONFINITE;
-                } else if (kx < -VK_BIAS || kx >= VK_BIAS || ky < -VK_BIAS || ky >= VK_BIAS || kz < -VK_BIAS ||
-                           kz >= VK_BIAS) {
-                    bad |= FLAG_KEY_RANGE;
+                int kx = 0, ky = 0, kz = 0;
+                const int st = voxel_key_fast(x, voxel, rinv, pow2, &kx) | voxel_key_fast(y, voxel, rinv, pow2, &ky) |
+                               voxel_key_fast(z, voxel, rinv, pow2, &kz);
+                if (st) {
+                    bad |= st;
                 } else {
                     lo[0] = min(lo[0], kx); hi[0] = max(hi[0], kx);
                     lo[1] = min(lo[1], ky); hi[1] = max(hi[1], ky);
@@ -390,17 +400,16 @@ __global__ void __launch_bounds__(256) k_vox_insert(const PointSrc src, const Vo
     // key range + flags of this block
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            lo[a] = min(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
-            hi[a] = max(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
-        }
+        lo[a] = __reduce_min_sync(0xffffffffu, lo[a]);
+        hi[a] = __reduce_max_sync(0xffffffffu, hi[a]);
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+    bad = (int)__reduce_or_sync(0xffffffffu, (unsigned)bad);
     if (lane == 0) {
 #pragma unroll
-        for (int a = 0; a < 3; ++a) { s_red[warp][a] = lo[a]; s_red[warp][3 + a] = hi[a]; }
+        for (int a = 0; a < 3; ++a) {
+            s_red[warp][a] = lo[a] == INT_MAX ? INT64_MAX : (i64)lo[a];
+            s_red[warp][3 + a] = hi[a] == INT_MIN ? INT64_MIN : (i64)hi[a];
+        }
         if (bad) atomicOr(flags, bad);
     }
     __syncthreads();

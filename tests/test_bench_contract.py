@@ -1,5 +1,7 @@
-"""The stored bench lines (profiles/r01_bench_*.json, written by bench.py on the GPU box) carry every key of the bench
-contract; a guard against a bench.py edit that silently drops one."""
+"""The stored bench lines (profiles/r0N_bench_*.json, written by bench.py on the GPU box) carry every key of the bench
+contract; a guard against a bench.py edit that silently drops one.  Round 1 lines: config C2 as a batch, one sequence
+per GPU (weak scaling).  Round 2 lines: config C5, the same 4096 pairs split over the GPUs (strong scaling), with the
+other configurations as named sub-results."""
 import glob
 import json
 import os
@@ -14,7 +16,7 @@ BASE = ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "
 
 def lines():
     out = []
-    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "r01_bench_*.json"))):
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "r0[12]_bench_*.json"))):
         for ln in open(f):
             if ln.startswith("{"):
                 out.append((os.path.basename(f), json.loads(ln)))
@@ -37,8 +39,21 @@ def test_bench_line_has_the_contract_keys(name, d):
     assert d["gpu_launches"] > 0
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
     assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
-    pairs = int(re.search(r"C2: (\d+)-pair", d["config"]["workload"]).group(1))   # per GPU (weak scaling)
-    assert abs(d["value"] - d["n_gpus"] * pairs / (d["ms_per_step"] * 1e-3)) / d["value"] < 1e-6  # whole-job aggregate
+    if name.startswith("r01"):
+        pairs = int(re.search(r"C2: (\d+)-pair", d["config"]["workload"]).group(1))   # per GPU (weak scaling)
+        assert abs(d["value"] - d["n_gpus"] * pairs / (d["ms_per_step"] * 1e-3)) / d["value"] < 1e-6  # whole-job aggregate
+    else:
+        pairs = int(re.search(r"C5: batched ICP of (\d+) independent", d["config"]["workload"]).group(1))
+        assert d["scaling"] == "strong" and d["workload_stats"]["pairs"] == pairs
+        assert abs(d["value"] - pairs / (d["ms_per_step"] * 1e-3)) / d["value"] < 1e-6   # the job is always the same pairs
+        assert d["workload_stats"]["status_ok_frac"] == 1.0
+        assert 0 < d["e2e"]["h2d_ceiling"]["e2e_frac_of_ceiling"] <= 1.05
+        c4 = d["c4_loop_closure"]
+        assert c4["n_gpus"] == d["n_gpus"] and c4["ms_per_detect"] > 0 and c4["top10_that_are_true_revisits"] >= 3
+        if d["n_gpus"] == 1:
+            assert d["c2_streaming"]["ms_per_frame_mean"] > 0 and d["c2_batch"]["pairs_per_s"] > 0
+            assert d["c3_knn_normals"]["knn_plus_normals_queries_per_s"] > 0
+            assert d["roofline"]["issue"] is None or 0 < d["roofline"]["issue"]["frac"] < 1
     if d["n_gpus"] == 1:
         r = d["roofline"]
         assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(r) and r["bound"] in ("hbm", "tensor")

@@ -289,6 +289,33 @@ def test_normals_k10_voxel02(engine, oracle, synth, scene):
     assert exact > 0.99, f"only {exact:.4f} of the normals are bit-identical to the oracle"
 
 
+def test_normals_packet_kernel_k10_in_a_subprocess():
+    """k = 10 uses the warp-per-query kernel by default (faster on config C3); the packet kernel's k = 10 instantiation is
+    selected with SB_KNN_PACKET_K10=1, read once per process — so it is checked in a process of its own: bit-identical
+    normals and eigenvalues to the default kernel's on the same cloud (both equal the oracle's neighbour sets)."""
+    import subprocess
+    import sys
+    code = r"""
+import sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import oracle_lib, slam_b200
+syn = oracle_lib.Synth(); orc = oracle_lib.Oracle()
+raw = syn.scan(oracle_lib.small_sensor(64, 900), syn.scene(1, n_boxes=400), (0.0, 0.0, 0.0), 7)
+eng = slam_b200.Engine(0)
+pts = eng.voxel_downsample(raw, 0.2)
+gn, ge = slam_b200.KDTree(eng, pts).estimate_normals(10, return_evals=True)
+on, oe = orc.tree(pts).estimate_normals(10)
+assert np.allclose(ge, oe, rtol=1e-9, atol=1e-12)
+print("IDENTICAL", float(np.mean(np.all(gn == on, axis=1))), len(pts))
+""" % (os.path.dirname(os.path.abspath(__file__)), os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                                              "lidar-slam-from-scratch_b200", "python"))
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, SB_KNN_PACKET_K10="1"))
+    assert p.returncode == 0, p.stdout + p.stderr
+    frac = float(p.stdout.split("IDENTICAL")[1].split()[0])
+    assert frac > 0.99, p.stdout
+
+
 def test_normals_degenerate(engine):
     import slam_b200
     n = slam_b200.KDTree(engine, np.array([[0, 0, 0], [1, 1, 1.0]])).estimate_normals(20)
