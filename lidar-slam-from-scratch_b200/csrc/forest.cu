@@ -537,7 +537,7 @@ __global__ void __launch_bounds__(QWARPS * 32) k_knn(ForestView F, const double*
                                                      TreeNormal* __restrict__ nrm_sorted,
                                                      NbrEntry* __restrict__ nbr_sorted, double* __restrict__ nrm_orig,
                                                      double* __restrict__ evals_orig, int n_trees_or_zero,
-                                                     unsigned long long* __restrict__ spacing_acc) {
+                                                     unsigned long long* __restrict__ spacing_acc, int qpi) {
     __shared__ WarpStack stacks[QWARPS];
     __shared__ TreeDesc s_tree[QWARPS];
     __shared__ int s_nbr[MODE == 1 ? QWARPS : 1][32][33];  // neighbour positions (cloud-local sorted), padded
@@ -550,9 +550,11 @@ __global__ void __launch_bounds__(QWARPS * 32) k_knn(ForestView F, const double*
             const i64* tio = reinterpret_cast<const i64*>(items);
             int t = find_segment(tio, n_trees_or_zero, it);
             I.tree = t;
-            I.q_off = (it - tio[t]) * 32;
+            // qpi consecutive points per work item: 32 for batches; a single small cloud (the streaming path) is cut
+            // finer so that it still fills the chip (see forest_normals)
+            I.q_off = (it - tio[t]) * qpi;
             int rem = F.trees[t].n - (int)I.q_off;
-            I.count = rem < 32 ? rem : 32;
+            I.count = rem < qpi ? rem : qpi;
         } else {
             I = items[it];
         }
@@ -688,7 +690,7 @@ int forest_knn(Ctx* ctx, const Forest* f, const double* d_q, const QueryItem* d_
                int* d_out_idx, double* d_out_d2) {
     if (n_items <= 0) return SB_OK;
     SB_LAUNCH(ctx, k_knn<0>, query_grid(ctx, n_items), QWARPS * 32, 0, view_of(f), d_q, d_items, n_items, k, d_out_idx,
-              d_out_d2, nullptr, nullptr, nullptr, nullptr, 0, nullptr);
+              d_out_d2, nullptr, nullptr, nullptr, nullptr, 0, nullptr, 32);
     return SB_OK;
 }
 
@@ -741,7 +743,22 @@ int forest_normals(Ctx* ctx, Forest* f, int k, double* d_out_normals, double* d_
     // k = 10 (config C3: 44 k-point clouds at voxel 0.2) stays with one warp per query unless SB_KNN_PACKET_K10=1: there
     // the packet kernel measured 4.70 ms against 4.37 ms per 47 clouds (4 % of its queries end in the redo list)
     static const bool packet10 = getenv("SB_KNN_PACKET_K10") && atoi(getenv("SB_KNN_PACKET_K10")) != 0;
-    if (packet && (k == 20 || (k == 10 && packet10))) {
+    // A batch too small to fill the chip with one warp per 32 queries (a single scan: 266 packets on 148 SMs, where a
+    // packet's 17 k dependent instructions took 0.44 ms): one warp per `qpi` queries with the warp-per-query kernel
+    // instead — it executes 3x the instructions, but 16-32 warps per SM hide each other's latencies.
+    int qpi = 32;
+    while (qpi > 1 && B.n_points / qpi < (i64)ctx->sm_count * 24) qpi >>= 1;
+    static const bool allow_small = !(getenv("SB_KNN_SMALL") && atoi(getenv("SB_KNN_SMALL")) == 0);
+    if (qpi < 32 && allow_small) {
+        std::vector<i64> tq((size_t)B.n_trees + 1, 0);
+        for (int t = 0; t < B.n_trees; ++t) tq[t + 1] = tq[t] + (f->h_trees[(size_t)(B.t0 + t)].n + qpi - 1) / qpi;
+        i64* d_tq;
+        SB_TRY(arena_get(ctx, tq.size(), &d_tq));
+        SB_TRY(table_upload(ctx, d_tq, tq.data(), sizeof(i64) * tq.size()));
+        SB_LAUNCH(ctx, k_knn<1>, query_grid(ctx, tq[B.n_trees]), QWARPS * 32, 0, view_of(f, B.t0), nullptr,
+                  reinterpret_cast<const QueryItem*>(d_tq), tq[B.n_trees], k, nullptr, nullptr, B.normals, B.nbr,
+                  d_out_normals, d_out_evals, B.n_trees, d_spacing, qpi);
+    } else if (packet && (k == 20 || (k == 10 && packet10))) {
         static const bool want_stats = getenv("SB_KNN_STATS") != nullptr;
         static const int pcap = getenv("SB_KNN_PCAP") ? atoi(getenv("SB_KNN_PCAP")) : 48;
         unsigned long long* d_stats = nullptr;
@@ -794,7 +811,7 @@ int forest_normals(Ctx* ctx, Forest* f, int k, double* d_out_normals, double* d_
     } else {
         SB_LAUNCH(ctx, k_knn<1>, query_grid(ctx, n_items), QWARPS * 32, 0, view_of(f, B.t0), nullptr,
                   reinterpret_cast<const QueryItem*>(d_tio), n_items, k, nullptr, nullptr, B.normals, B.nbr, d_out_normals,
-                  d_out_evals, B.n_trees, d_spacing);
+                  d_out_evals, B.n_trees, d_spacing, 32);
     }
     // seed grid for icp.cu (cell size from the measured point spacing)
     SB_LAUNCH(ctx, k_grid_params, ceil_div(B.n_trees, 128), 128, 0, d_bt, d_spacing, B.n_trees);
