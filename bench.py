@@ -621,7 +621,7 @@ def main():
         kern = {"voxel": "k_vox_insert (+ clear/list/sort/finalize/collect/patch)",
                 "index_build": "k_morton/k_sort_*/k_gather_leaves",
                 "normals": "k_self_knn (+ k_knn_redo + k_normals_from_graph)",
-                "icp_loop": "k_icp_match/k_icp_fallback/k_icp_accum/k_icp_solve in the WHILE graph + k_icp_tail"}
+                "icp_loop": "k_icp_match/k_icp_fallback/k_icp_accum/k_icp_solve in the CUDA-graph WHILE loop"}
         traffic = {}
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))

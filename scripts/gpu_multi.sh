@@ -1,16 +1,17 @@
 #!/bin/bash
-# multi-GPU checks: sharded loop-closure test + the strong-scaling bench on N GPUs (N = $1)
+# multi-GPU evidence on N GPUs of one box (gpurun --gpus N): the multi-GPU tests (TESTS=1), then the strong-scaling bench
 N=${1:-2}
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=name --format=csv,noheader | head -8
-timeout 1500 python -m pytest tests/test_multi_gpu.py -m gpu -q --tb=short --timeout 1400 -p no:cacheprovider -x  > gpurun_out/pytest_multi.log 2>&1; tail -5 gpurun_out/pytest_multi.log
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N --pairs ${PAIRS:-4096} --steps 3 --warmup 3 > gpurun_out/bench_${N}gpu.log 2>&1; echo "bench exit $?"
-grep -v "^{" gpurun_out/bench_${N}gpu.log | tail -5
+nvidia-smi --query-gpu=name --format=csv,noheader | head -8 | sort | uniq -c
+if [ "${TESTS:-1}" = "1" ]; then
+  timeout 1500 python -m pytest tests/test_multi_gpu.py -m gpu -q --tb=short --timeout 1400 -p no:cacheprovider > gpurun_out/pytest_multi_${N}gpu.log 2>&1; tail -3 gpurun_out/pytest_multi_${N}gpu.log
+fi
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N > gpurun_out/bench_${N}gpu.log 2>&1; echo "bench exit $?"
+grep "^{" gpurun_out/bench_${N}gpu.log > gpurun_out/r02_bench_${N}gpu.json
 python - <<PY
 import json
-for l in open("gpurun_out/bench_${N}gpu.log"):
-    if l.startswith("{"):
-        d = json.loads(l)
-        print("value", d["value"], "ms", d["ms_per_step"], "e2e", d["e2e"], "per_rank", d["per_rank"], "scaling", d["scaling"])
-        print("c4", {k: v for k, v in d.get("c4_loop_closure", {}).items() if k != "workload"})
+for l in open("gpurun_out/r02_bench_${N}gpu.json"):
+    d = json.loads(l)
+    print("value", d["value"], "ms", d["ms_per_step"], "e2e", d["e2e"]["value"], d["e2e"]["ms_per_step"], d["e2e"]["h2d_ceiling"], "per_rank", d["per_rank"])
+    print("c4", {k: v for k, v in d.get("c4_loop_closure", {}).items() if k not in ("workload", "top10_sc_distance")})
 PY
