@@ -244,6 +244,15 @@ int sb_occupancy_cells(sb_ctx* ctx, const double* xyz, const int64_t* offsets, i
 int sb_global_map(sb_ctx* ctx, const double* xyz, const int64_t* offsets, int32_t n_clouds, const double* poses16,
                   double voxel, double* out_xyz, int64_t* out_m);
 
+/* The same two results as the payload of the sensor_msgs/PointCloud2 the node publishes — eigen_to_pointcloud2
+ * (slam_node.cpp:299-322): x, y, z as float32 (static_cast<float>, round to nearest), point_step 12, row after row —
+ * converted on the device so that half the bytes cross PCIe.  publish_current_scan (slam_node.cpp:147, 231-233) /
+ * publish_global_map (slam_node.cpp:235-238).  out_xyz: offsets[n_clouds]*3 floats. */
+int sb_transform_clouds_f32(sb_ctx* ctx, const double* xyz, const int64_t* offsets, int32_t n_clouds,
+                            const double* poses16, float* out_xyz);
+int sb_global_map_f32(sb_ctx* ctx, const double* xyz, const int64_t* offsets, int32_t n_clouds, const double* poses16,
+                      double voxel, float* out_xyz, int64_t* out_m);
+
 /* The pose chain of process_frame (slam_node.cpp:139-145), for a sequence registered as one batch: results[i] is the
  * registration of frame i+1 against frame i; delta_i = identity if !converged or final_error > max_error (the node
  * uses 1.0), else the result's transformation; poses16_out[0] = initial_pose16 (NULL: identity) and

@@ -1157,6 +1157,28 @@ int sb_transform_clouds(sb_ctx* ctx, const double* xyz, const int64_t* offsets, 
     return SB_OK;
 }
 
+// publish_current_scan (slam_node.cpp:147, 231-233, 299-322): the world-frame cloud as the float32 records of a
+// PointCloud2 message — converted on the device, so half the bytes come back
+int sb_transform_clouds_f32(sb_ctx* ctx, const double* xyz, const int64_t* offsets, int32_t n_clouds,
+                            const double* poses16, float* out_xyz) {
+    if (!ctx || !offsets || n_clouds < 0) return SB_ERR_INVALID_ARG;
+    Ctx* c = &ctx->c;
+    Enter g(c);
+    SB_TRY(check_clouds(c, xyz, offsets, n_clouds, poses16));
+    const i64 n = offsets[n_clouds];
+    if (n == 0) return SB_OK;
+    if (!out_xyz) return fail(c, SB_ERR_INVALID_ARG, "null output buffer");
+    double *d_world, *d_poses;
+    i64* d_off;
+    float* d_f32;
+    SB_TRY(world_clouds(c, xyz, offsets, n_clouds, poses16, &d_world, &d_off, &d_poses));
+    SB_TRY(arena_get(c, (size_t)3 * n, &d_f32));
+    SB_TRY(pack_f32_dev(c, d_world, n, d_f32));
+    SB_TRY(download(c, out_xyz, d_f32, sizeof(float) * 3 * n));
+    SB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return SB_OK;
+}
+
 int sb_occupancy_cells(sb_ctx* ctx, const double* xyz, const int64_t* offsets, int32_t n_clouds, const double* poses16,
                        const sb_grid_config* cfg, int32_t* out_cells, int64_t capacity, int64_t* out_count) {
     if (!ctx || !offsets || n_clouds < 0 || !cfg || !out_count || capacity < 0 || (capacity > 0 && !out_cells))
@@ -1259,6 +1281,32 @@ int sb_global_map(sb_ctx* ctx, const double* xyz, const int64_t* offsets, int32_
     SB_TRY(voxel_downsample_dev(c, d_world, one, 1, voxel, d_out, out_off, nullptr));
     *out_m = out_off[1];
     SB_TRY(download(c, out_xyz, d_out, sizeof(double) * 3 * (size_t)out_off[1]));
+    SB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return SB_OK;
+}
+
+// publish_global_map (slam_node.cpp:235-238, 299-322): the downsampled global map as PointCloud2 float32 records
+int sb_global_map_f32(sb_ctx* ctx, const double* xyz, const int64_t* offsets, int32_t n_clouds, const double* poses16,
+                      double voxel, float* out_xyz, int64_t* out_m) {
+    if (!ctx || !offsets || n_clouds < 0 || !out_m) return SB_ERR_INVALID_ARG;
+    Ctx* c = &ctx->c;
+    Enter g(c);
+    *out_m = 0;
+    SB_TRY(check_clouds(c, xyz, offsets, n_clouds, poses16));
+    const i64 n = offsets[n_clouds];
+    if (n == 0) return SB_OK;
+    if (!out_xyz) return fail(c, SB_ERR_INVALID_ARG, "null output buffer");
+    double *d_world, *d_poses, *d_out;
+    i64* d_off;
+    float* d_f32;
+    SB_TRY(world_clouds(c, xyz, offsets, n_clouds, poses16, &d_world, &d_off, &d_poses));
+    SB_TRY(arena_get(c, (size_t)3 * n, &d_out));
+    SB_TRY(arena_get(c, (size_t)3 * n, &d_f32));
+    i64 one[2] = {0, n}, out_off[2] = {0, 0};
+    SB_TRY(voxel_downsample_dev(c, d_world, one, 1, voxel, d_out, out_off, nullptr));
+    *out_m = out_off[1];
+    SB_TRY(pack_f32_dev(c, d_out, out_off[1], d_f32));
+    SB_TRY(download(c, out_xyz, d_f32, sizeof(float) * 3 * (size_t)out_off[1]));
     SB_CUDA(c, cudaStreamSynchronize(c->stream));
     return SB_OK;
 }

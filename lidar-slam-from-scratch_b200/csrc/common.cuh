@@ -363,6 +363,7 @@ int solve_point_to_plane_dev(Ctx* ctx, const double* d_src, const double* d_tgt,
 // mapping.cu
 int transform_clouds_dev(Ctx* ctx, const double* d_xyz, const i64* d_off, int n_clouds, const double* d_poses, i64 n,
                          double* d_out);
+int pack_f32_dev(Ctx* ctx, const double* d_in, i64 n_rows, float* d_out);
 int occupancy_cells_dev(Ctx* ctx, const double* d_world, const i64* d_off, int n_clouds, const double* d_poses, i64 n,
                         const sb_grid_config* cfg, int* d_cells, i64 capacity, i64* count);
 // synth.cu

@@ -35,8 +35,8 @@ struct PairState {
 
 struct FallbackEntry {   // a source point whose walk did not end with a proof
     i64 q;               // item * ITEM_Q + lane
-    int seed;            // best target position the walk found (-1: none)
-    int pad;
+    int seed;            // best target position the walk found (-1: none); item entries: mask of the open lanes
+    int pad;             // pair << 1 | (1: item entry)
 };
 
 struct IcpJob {
@@ -77,7 +77,7 @@ static constexpr int MAX_HOPS = 6;  // re-centrings of the neighbour-graph walk 
 // Block-wide (256 threads): the list of pairs in state `want` and the prefix sums of their work items.  The passes
 // iterate over this list only, so an iteration costs what its ACTIVE pairs cost — the batch keeps running until
 // the slowest pair stops (icp.hpp:181, max_iterations), long after most pairs have converged.
-__device__ void build_active(IcpJob* __restrict__ job, int want) {
+__device__ void build_active(IcpJob* __restrict__ job, int want, bool from_list) {
     __shared__ int s_wc[8];
     __shared__ i64 s_wi[8];
     __shared__ int s_bc;
@@ -85,10 +85,16 @@ __device__ void build_active(IcpJob* __restrict__ job, int want) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) { s_bc = 0; s_bi = 0; }
     __syncthreads();
-    const int n = job->n_pairs;
+    // from_list: a pair only ever leaves ST_ACTIVE, so the next active list is a filter of the current one — compacted
+    // in place (round r reads entries [256 r, 256 r + 256) before its first barrier and writes below 256 r + 256 after
+    // it).  With 4096 pairs the scan over all of them was 16 rounds of three barriers in EVERY pass, run by one block
+    // while the rest of the chip waits.
+    const int n = from_list ? job->n_act : job->n_pairs;
     for (int base = 0; base < n; base += 256) {
-        const int p = base + tid;
-        const bool flag = p < n && __ldcg(&job->state[p].state) == want;
+        const int e = base + tid;
+        int p = e;
+        if (from_list && e < n) p = job->act_pair[e];
+        const bool flag = e < n && __ldcg(&job->state[p].state) == want;
         const i64 items = flag ? (i64)job->pairs[p].n_items : 0;
         const unsigned bal = __ballot_sync(0xffffffffu, flag);
         i64 inc = items;  // inclusive warp scan of the item counts
@@ -141,29 +147,35 @@ __global__ void __launch_bounds__(256) k_icp_init(IcpJob* __restrict__ job, cuda
     }
     __syncthreads();
     const bool loop = job->n_active > 0 && job->max_it > 0;
-    build_active(job, loop ? ST_ACTIVE : ST_EXHAUSTED);
+    build_active(job, loop ? ST_ACTIVE : ST_EXHAUSTED, false);
     if (threadIdx.x == 0) {
         job->q_count = 0;
         if (use_cond) cudaGraphSetConditional(cond, loop ? 1u : 0u);
     }
 }
 
-// largest s in [0, n) with pairs[s].item_off <= x
-__device__ __forceinline__ int find_pair(const PairDesc* __restrict__ pairs, int n, i64 x) {
-    int lo = 0, hi = n;
-    while (hi - lo > 1) {
-        int mid = (lo + hi) >> 1;
-        if (pairs[mid].item_off <= x) lo = mid; else hi = mid;
+// largest a in [0, n) with off[a] <= x (off[0] = 0 <= x), called by the whole (converged) warp.  These loads head the
+// dependency chain of every work item, and a pass with few pairs left costs what its longest chain costs: up to 256
+// active pairs the warp tests 32 evenly spaced entries per step — two dependent loads instead of eight.  Above that
+// (a pass that is throughput-bound anyway) the plain binary search: one broadcast load per step.
+__device__ __forceinline__ int find_active(const i64* __restrict__ off, int n, i64 x, int lane) {
+    int lo = 0, len = n;
+    if (n > 256) {
+        int hi = n;
+        while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if (off[mid] <= x) lo = mid; else hi = mid;
+        }
+        return lo;
     }
-    return lo;
-}
-
-// largest a in [0, n) with off[a] <= x
-__device__ __forceinline__ int find_active(const i64* __restrict__ off, int n, i64 x) {
-    int lo = 0, hi = n;
-    while (hi - lo > 1) {
-        int mid = (lo + hi) >> 1;
-        if (off[mid] <= x) lo = mid; else hi = mid;
+    while (len > 1) {
+        const int step = (len + 31) >> 5;
+        const int idx = lo + lane * step;
+        const bool le = idx < lo + len && off[idx] <= x;   // true for a prefix of the lanes, lane 0 included
+        const int j = 31 - __clz(__ballot_sync(0xffffffffu, le) | 1u);
+        const int end = lo + len;
+        lo += j * step;
+        len = end - lo < step ? end - lo : step;
     }
     return lo;
 }
@@ -323,7 +335,7 @@ __global__ void __launch_bounds__(IWARPS * 32) k_icp_match(IcpJob* __restrict__ 
     const int K = job->nbr_k;
     const int packet_min = job->packet_min;
     for (i64 ai = (i64)blockIdx.x * IWARPS + warp; ai < n_act_items; ai += (i64)gridDim.x * IWARPS) {
-        const int a = find_active(job->act_off, n_act, ai);
+        const int a = find_active(job->act_off, n_act, ai, lane);
         const int pair = job->act_pair[a];
         const PairDesc P = job->pairs[pair];
         const i64 it = P.item_off + (ai - job->act_off[a]);
@@ -352,10 +364,10 @@ __global__ void __launch_bounds__(IWARPS * 32) k_icp_match(IcpJob* __restrict__ 
             base = __shfl_sync(0xffffffffu, base, 0);
             FallbackEntry e;
             if (as_item) {
-                e.q = it * ITEM_Q; e.seed = (int)todo; e.pad = 1;
+                e.q = it * ITEM_Q; e.seed = (int)todo; e.pad = (pair << 1) | 1;
                 if (lane == 0) job->queue[base] = e;
             } else if ((todo >> lane) & 1u) {
-                e.q = it * ITEM_Q + lane; e.seed = bpos; e.pad = 0;
+                e.q = it * ITEM_Q + lane; e.seed = bpos; e.pad = pair << 1;
                 job->queue[base + __popc(todo & lanemask_lt())] = e;
             }
         }
@@ -380,11 +392,11 @@ __global__ void __launch_bounds__(IWARPS * 32) k_icp_fallback(IcpJob* __restrict
     WarpStack& S = stacks[warp];
     const ForestView F = job->F;
     const int n = job->q_count;
-    const int n_pairs = job->n_pairs;
     for (int e = blockIdx.x * IWARPS + warp; e < n; e += gridDim.x * IWARPS) {
         const FallbackEntry E = job->queue[e];
         const i64 it = E.q / ITEM_Q;
-        const int pair = find_pair(job->pairs, n_pairs, it);
+        const int pair = E.pad >> 1;   // (a binary search over all pairs' item offsets — ten dependent loads — until round 2)
+        const bool item_entry = (E.pad & 1) != 0;
         const PairDesc P = job->pairs[pair];
         __syncwarp();
         {
@@ -395,7 +407,7 @@ __global__ void __launch_bounds__(IWARPS * 32) k_icp_fallback(IcpJob* __restrict
         }
         const TreeDesc& T = s_tree[warp];
         const double* Tm = job->results[pair].transformation;
-        if (E.pad == 1 && T.gext < 1.0e15) {
+        if (item_entry && T.gext < 1.0e15) {
             const int s0 = (int)(it - P.item_off) * ITEM_Q;
             const int count = P.n_src - s0 < ITEM_Q ? P.n_src - s0 : ITEM_Q;
             const unsigned todo = (unsigned)E.seed;
@@ -408,15 +420,15 @@ __global__ void __launch_bounds__(IWARPS * 32) k_icp_fallback(IcpJob* __restrict
             packet_nearest(F, T, S, lane, todo, cx, cy, cz, bpos);
             if ((todo >> lane) & 1u) job->match[E.q + lane] = bpos;
         } else {
-            unsigned todo = E.pad == 1 ? (unsigned)E.seed : 1u;   // (an item entry of a tree of extreme extent: lane by lane)
+            unsigned todo = item_entry ? (unsigned)E.seed : 1u;   // (an item entry of a tree of extreme extent: lane by lane)
             while (todo) {
                 const int j = __ffs(todo) - 1;
                 todo &= todo - 1u;
-                const i64 q = E.pad == 1 ? E.q + j : E.q;
+                const i64 q = item_entry ? E.q + j : E.q;
                 double qx, qy, qz;
                 transform_point(Tm, reinterpret_cast<const double*>(P.src_pts + (q - P.item_off * ITEM_Q)), qx, qy, qz);
                 NearestVisitor V(F, T, qx, qy, qz, lane);
-                V.seed(E.pad == 1 ? job->match[q] : E.seed);
+                V.seed(item_entry ? job->match[q] : E.seed);
                 traverse(F, T, qx, qy, qz, S, V, lane);
                 if (lane == 0) job->match[q] = V.best_pos;
             }
@@ -488,7 +500,7 @@ __global__ void __launch_bounds__(IWARPS * 32) k_icp_accum(const IcpJob* __restr
     const i64 n_act_items = job->n_act_items;
     const int n_act = job->n_act;
     for (i64 ai = (i64)blockIdx.x * IWARPS + warp; ai < n_act_items; ai += (i64)gridDim.x * IWARPS) {
-        const int a = find_active(job->act_off, n_act, ai);
+        const int a = find_active(job->act_off, n_act, ai, lane);
         const int pair = job->act_pair[a];
         const PairDesc P = job->pairs[pair];
         const i64 it = P.item_off + (ai - job->act_off[a]);
@@ -518,6 +530,48 @@ __device__ __forceinline__ void cswap(bool c, double& x, double& y) {
     x = c ? y : x;
     y = c ? t : y;
 }
+// (one step of the elimination per template instance: written as one `for k` loop, the compiler left the swap loop of
+// some k rolled — `.pragma "nounroll"` in the PTX — which made every index of it dynamic, put the matrix in local
+// memory after all and cost k_icp_solve 683 local loads/stores on its one solving thread)
+template <int K, int R>
+__device__ __forceinline__ void ldlt_swap(int p, double (&a)[6][6], double (&y)[6], int (&perm)[6]) {
+    if constexpr (R < 6) {
+        const bool c = p == R;   // swap rows and columns K <-> R
+#pragma unroll
+        for (int j = 0; j < 6; ++j) cswap(c, a[K][j], a[R][j]);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) cswap(c, a[i][K], a[i][R]);
+        cswap(c, y[K], y[R]);
+        const int t = perm[K];
+        perm[K] = c ? perm[R] : perm[K];
+        perm[R] = c ? t : perm[R];
+        ldlt_swap<K, R + 1>(p, a, y, perm);
+    }
+}
+template <int K>
+__device__ __forceinline__ void ldlt_step(double (&a)[6][6], double (&y)[6], int (&perm)[6]) {
+    if constexpr (K < 6) {
+        int p = K;
+        double best = fabs(a[K][K]);
+#pragma unroll
+        for (int i = K + 1; i < 6; ++i)
+            if (fabs(a[i][i]) > best) { best = fabs(a[i][i]); p = i; }
+        ldlt_swap<K, K + 1>(p, a, y, perm);
+        const double d = a[K][K];
+        if (d != 0.0) {
+#pragma unroll
+            for (int i = K + 1; i < 6; ++i) a[i][K] /= d;  // column K of L
+#pragma unroll
+            for (int i = K + 1; i < 6; ++i)
+#pragma unroll
+                for (int j = K + 1; j <= i; ++j) {
+                    a[i][j] -= a[i][K] * d * a[j][K];
+                    a[j][i] = a[i][j];
+                }
+        }
+        ldlt_step<K + 1>(a, y, perm);
+    }
+}
 __device__ __forceinline__ void ldlt6_solve(const double (&Ain)[6][6], const double (&bin)[6], double (&x)[6]) {
     double a[6][6], y[6];
 #pragma unroll
@@ -527,38 +581,7 @@ __device__ __forceinline__ void ldlt6_solve(const double (&Ain)[6][6], const dou
         for (int j = 0; j < 6; ++j) a[i][j] = Ain[i][j];
     }
     int perm[6] = {0, 1, 2, 3, 4, 5};
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-        int p = k;
-        double best = fabs(a[k][k]);
-#pragma unroll
-        for (int i = k + 1; i < 6; ++i)
-            if (fabs(a[i][i]) > best) { best = fabs(a[i][i]); p = i; }
-#pragma unroll
-        for (int r = k + 1; r < 6; ++r) {   // p == r: swap rows and columns k <-> r
-            const bool c = p == r;
-#pragma unroll
-            for (int j = 0; j < 6; ++j) cswap(c, a[k][j], a[r][j]);
-#pragma unroll
-            for (int i = 0; i < 6; ++i) cswap(c, a[i][k], a[i][r]);
-            cswap(c, y[k], y[r]);
-            const int t = perm[k];
-            perm[k] = c ? perm[r] : perm[k];
-            perm[r] = c ? t : perm[r];
-        }
-        const double d = a[k][k];
-        if (d != 0.0) {
-#pragma unroll
-            for (int i = k + 1; i < 6; ++i) a[i][k] /= d;  // column k of L
-#pragma unroll
-            for (int i = k + 1; i < 6; ++i)
-#pragma unroll
-                for (int j = k + 1; j <= i; ++j) {
-                    a[i][j] -= a[i][k] * d * a[j][k];
-                    a[j][i] = a[i][j];
-                }
-        }
-    }
+    ldlt_step<0>(a, y, perm);
 #pragma unroll
     for (int i = 0; i < 6; ++i)  // L y' = P b
 #pragma unroll
@@ -570,10 +593,11 @@ __device__ __forceinline__ void ldlt6_solve(const double (&Ain)[6][6], const dou
 #pragma unroll
         for (int j = i + 1; j < 6; ++j) y[i] -= a[j][i] * y[j];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) {   // x = P^T w
+    for (int o = 0; o < 6; ++o) {   // x = P^T w: x[perm[i]] = y[i], as selects (a scatter would put x in local memory)
+        double v = y[0];
 #pragma unroll
-        for (int o = 0; o < 6; ++o)
-            if (perm[i] == o) x[o] = y[i];
+        for (int i = 1; i < 6; ++i) v = perm[i] == o ? y[i] : v;
+        x[o] = v;
     }
 }
 
@@ -656,7 +680,14 @@ __device__ __forceinline__ void solve_pair(IcpJob* __restrict__ job, int p, int 
         if (lane < NSUM) {
             const double* base = job->partials + P.item_off * NSUM + lane;
             int i = warp;
-            for (; i + 24 < P.n_items; i += 32) {  // four loads in flight, additions in item order
+            for (; i + 56 < P.n_items; i += 64) {  // eight loads in flight, additions in item order
+                double v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = __ldcg(base + (i64)(i + 8 * u) * NSUM);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) s += v[u];
+            }
+            for (; i + 24 < P.n_items; i += 32) {  // four
                 const double v0 = __ldcg(base + (i64)i * NSUM), v1 = __ldcg(base + (i64)(i + 8) * NSUM),
                              v2 = __ldcg(base + (i64)(i + 16) * NSUM), v3 = __ldcg(base + (i64)(i + 24) * NSUM);
                 s += v0; s += v1; s += v2; s += v3;
@@ -775,7 +806,7 @@ __global__ void __launch_bounds__(256) k_icp_solve(IcpJob* __restrict__ job, int
             const int active = *reinterpret_cast<volatile int*>(&job->n_active);
             // next pass: the pairs still iterating, or — once none is left — the final error pass of the pairs that
             // ran out of iterations (icp.hpp:235-252)
-            build_active(job, active > 0 ? ST_ACTIVE : ST_EXHAUSTED);
+            build_active(job, active > 0 ? ST_ACTIVE : ST_EXHAUSTED, active > 0);
             if (threadIdx.x == 0) {
                 job->ticket = 0;
                 job->q_count = 0;

@@ -2,6 +2,7 @@
 //   world-frame clouds      world = cloud * R^T + t           slam_viz/src/ros/slam_node.cpp:147, 189, 201-203
 //   occupancy cells         height / range filter + floor(x / resolution) cell set   slam_node.cpp:211-229
 //   global map              all clouds in the world frame, voxel grid at 2 * voxel_size     slam_node.cpp:196-209, 235-238
+//   PointCloud2 payload     float32 x, y, z records of what is published                      slam_node.cpp:299-322
 // The cell set is an unordered_set in the reference; here it comes out sorted by (x, y).  The global map reuses the
 // voxel grid of voxel.cu (world coordinates are arbitrary doubles: the sort-based path answers, bit-exact).
 #include "common.cuh"
@@ -70,6 +71,18 @@ __global__ void __launch_bounds__(256) k_occ_emit(const u64* __restrict__ keys, 
     const u64 k = keys[i];
     cells[2 * (i64)pos[i]] = (int)((uint32_t)(k >> 32) ^ 0x80000000u);
     cells[2 * (i64)pos[i] + 1] = (int)((uint32_t)k ^ 0x80000000u);
+}
+
+// eigen_to_pointcloud2 (slam_node.cpp:299-322): the PointCloud2 payload is x, y, z as float32, point_step 12 —
+// static_cast<float> of every coordinate (round to nearest even)
+__global__ void __launch_bounds__(256) k_pack_f32(const double* __restrict__ in, i64 n3, float* __restrict__ out) {
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n3) out[i] = __double2float_rn(in[i]);
+}
+
+int pack_f32_dev(Ctx* ctx, const double* d_in, i64 n_rows, float* d_out) {
+    if (n_rows > 0) SB_LAUNCH(ctx, k_pack_f32, ceil_div(3 * n_rows, 256), 256, 0, d_in, 3 * n_rows, d_out);
+    return SB_OK;
 }
 
 int transform_clouds_dev(Ctx* ctx, const double* d_xyz, const i64* d_off, int n_clouds, const double* d_poses, i64 n,

@@ -20,7 +20,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(os.path.dirname(_HERE), "libslam_b200.so")
+# SB_LIB_PATH: another build of the same library (A/B measurements of two builds in one job)
+_LIB_PATH = os.environ.get("SB_LIB_PATH") or os.path.join(os.path.dirname(_HERE), "libslam_b200.so")
 
 SB_SC_SIZE = 1200
 SB_MAX_K = 32
@@ -130,6 +131,8 @@ SYMBOLS = {
     "sb_transform_clouds": (C.c_int, [_P, _D, _I64, C.c_int32, _D, _D]),
     "sb_occupancy_cells": (C.c_int, [_P, _D, _I64, C.c_int32, _D, _P, _I32, C.c_int64, _I64]),
     "sb_global_map": (C.c_int, [_P, _D, _I64, C.c_int32, _D, C.c_double, _D, _I64]),
+    "sb_transform_clouds_f32": (C.c_int, [_P, _D, _I64, C.c_int32, _D, C.POINTER(C.c_float)]),
+    "sb_global_map_f32": (C.c_int, [_P, _D, _I64, C.c_int32, _D, C.c_double, C.POINTER(C.c_float), _I64]),
     "sb_synth_scans_dev": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                                      C.POINTER(C.c_float), C.c_int32, _D, C.c_int32, C.c_uint64, _P, _I64]),
 }
@@ -394,6 +397,25 @@ class Engine:
         m = C.c_int64(0)
         self._check(self.lib.sb_global_map(self.h, _dp(pts), off.ctypes.data_as(_I64), off.shape[0] - 1, _dp(T),
                                            float(voxel), _dp(out), C.byref(m)))
+        return out[:m.value].copy()
+
+    def transform_clouds_f32(self, points, offsets, poses):
+        """World-frame clouds as PointCloud2 float32 xyz records (slam_node.cpp:147, 299-322)."""
+        pts, off = _f64(points, 3), np.ascontiguousarray(offsets, dtype=np.int64)
+        T = np.ascontiguousarray(poses, dtype=np.float64).reshape(-1, 16)
+        out = np.empty(pts.shape, dtype=np.float32)
+        self._check(self.lib.sb_transform_clouds_f32(self.h, _dp(pts), off.ctypes.data_as(_I64), off.shape[0] - 1,
+                                                     _dp(T), out.ctypes.data_as(C.POINTER(C.c_float))))
+        return out
+
+    def global_map_f32(self, points, offsets, poses, voxel):
+        """Global map as PointCloud2 float32 xyz records (slam_node.cpp:235-238, 299-322)."""
+        pts, off = _f64(points, 3), np.ascontiguousarray(offsets, dtype=np.int64)
+        T = np.ascontiguousarray(poses, dtype=np.float64).reshape(-1, 16)
+        out = np.empty((max(pts.shape[0], 1), 3), dtype=np.float32)
+        m = C.c_int64(0)
+        self._check(self.lib.sb_global_map_f32(self.h, _dp(pts), off.ctypes.data_as(_I64), off.shape[0] - 1, _dp(T),
+                                               float(voxel), out.ctypes.data_as(C.POINTER(C.c_float)), C.byref(m)))
         return out[:m.value].copy()
 
     # ---- Scan Context (scan_context.hpp)

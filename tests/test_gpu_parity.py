@@ -665,6 +665,12 @@ def test_world_frame_occupancy_and_global_map(engine, oracle, synth, scene):
     assert np.array_equal(gm, ref_gm)
     assert np.array_equal(engine.global_map(allpts, off, Ts, 0.0), ref_world)
     assert engine.occupancy_cells(np.zeros((0, 3)), [0], np.zeros((0, 16)))[1] == 0
+    # the PointCloud2 payload of what the node publishes (eigen_to_pointcloud2, slam_node.cpp:299-322): static_cast<float>
+    w32 = engine.transform_clouds_f32(allpts, off, Ts)
+    assert w32.dtype == np.float32 and np.array_equal(w32, ref_world.astype(np.float32))
+    g32 = engine.global_map_f32(allpts, off, Ts, 1.0)
+    assert g32.dtype == np.float32 and np.array_equal(g32, ref_gm.astype(np.float32))
+    assert len(engine.global_map_f32(np.zeros((0, 3)), [0], np.zeros((0, 16)), 1.0)) == 0
     # the whole offline-mapping chain through the ABI: register the sequence as one batch, chain the poses the way
     # process_frame does (slam_node.cpp:139-145), build the map from them
     res = engine.register_batch(allpts, off, np.arange(1, 6), np.arange(0, 5), voxel=0.0)
