@@ -327,7 +327,7 @@ __device__ __forceinline__ void accumulate_item(const IcpJob* __restrict__ job, 
 // Works on the pairs listed in job->act_pair: the ST_ACTIVE ones inside the loop, the ST_EXHAUSTED ones in the final
 // error pass (icp.hpp:235-252).  Work item = ITEM_Q consecutive source points of one pair (implicit: binary search
 // over the prefix sums act_off), one source point per lane.  Replaces KDTree::nearest_batch (kdtree.hpp:43-59), exact.
-__global__ void __launch_bounds__(IWARPS * 32) k_icp_match(IcpJob* __restrict__ job) {
+__global__ void __launch_bounds__(IWARPS * 32, 5) k_icp_match(IcpJob* __restrict__ job) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const ForestView F = job->F;
     const i64 n_act_items = job->n_act_items;
@@ -494,7 +494,7 @@ __device__ __forceinline__ void accumulate_item(const IcpJob* __restrict__ job, 
 }
 
 // Residuals and sums of the work items that k_icp_match could not finish itself (some point was queued).
-__global__ void __launch_bounds__(IWARPS * 32) k_icp_accum(const IcpJob* __restrict__ job) {
+__global__ void __launch_bounds__(IWARPS * 32, 5) k_icp_accum(const IcpJob* __restrict__ job) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const ForestView F = job->F;
     const i64 n_act_items = job->n_act_items;

@@ -219,7 +219,14 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(const u64* __rest
 static constexpr int SEG_CAP = 12288;
 static constexpr int SEG_THREADS = 1024;
 static constexpr int SEG_EPT = SEG_CAP / SEG_THREADS;   // batches of 32 rows per warp, at most
-static constexpr size_t SEG_SMEM = (size_t)SEG_CAP * 4 + (size_t)SEG_CAP * 2 * 2 + (size_t)RADIX * 32 * 2;
+// counters: [warp][digit] with a row stride of 258 shorts = 129 words — odd, so that neither the ranking (one warp,
+// 32 different digits) nor the scan (eight warps' counters of one digit per thread) piles onto a few banks; as
+// [digit][warp] the 32 lanes of a ranking step hit two banks.
+#ifndef SB_SORT_CSTR
+#define SB_SORT_CSTR 258
+#endif
+static constexpr int SEG_CSTR = SB_SORT_CSTR;
+static constexpr size_t SEG_SMEM = (size_t)SEG_CAP * 4 + (size_t)SEG_CAP * 2 * 2 + (size_t)SEG_CSTR * 32 * 2;
 
 __global__ void __launch_bounds__(SEG_THREADS) k_seg_sort_smem(const u64* __restrict__ kin, const uint32_t* __restrict__ vin,
                                                                u64* __restrict__ kout, uint32_t* __restrict__ vout,
@@ -228,7 +235,7 @@ __global__ void __launch_bounds__(SEG_THREADS) k_seg_sort_smem(const u64* __rest
     uint32_t* keys = reinterpret_cast<uint32_t*>(seg_sm);
     unsigned short* pin = reinterpret_cast<unsigned short*>(keys + SEG_CAP);
     unsigned short* pout = pin + SEG_CAP;
-    unsigned short* cnt = pout + SEG_CAP;  // [digit][warp]: rows of this digit in this warp's block, then their base
+    unsigned short* cnt = pout + SEG_CAP;  // [warp][digit]: rows of this digit in this warp's block, then their base
     __shared__ uint32_t s_scan[33];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const i64 base = seg_off[blockIdx.x];
@@ -241,7 +248,7 @@ __global__ void __launch_bounds__(SEG_THREADS) k_seg_sort_smem(const u64* __rest
     const int per = (((n + 31) / 32) + 31) & ~31;  // rows per warp: a multiple of 32, 32 * per >= n
     const int w0 = warp * per, w1 = min(n, w0 + per);
     for (int shift = 0; shift < key_bits; shift += 8) {
-        for (int i = tid; i < RADIX * 32; i += SEG_THREADS) cnt[i] = 0;
+        for (int i = tid; i < SEG_CSTR * 32; i += SEG_THREADS) cnt[i] = 0;
         __syncthreads();
         unsigned short rank[SEG_EPT];
 #pragma unroll
@@ -253,25 +260,25 @@ __global__ void __launch_bounds__(SEG_THREADS) k_seg_sort_smem(const u64* __rest
                 const unsigned d = act ? ((keys[pin[i]] >> shift) & (RADIX - 1)) : (unsigned)RADIX + lane;
                 const unsigned m = __match_any_sync(0xffffffffu, d);
                 unsigned short old = 0;
-                if (act) old = cnt[d * 32 + warp];
+                if (act) old = cnt[warp * SEG_CSTR + d];
                 __syncwarp();
                 if (act) {
                     rank[j] = (unsigned short)(old + __popc(m & lanemask_lt()));
-                    if ((int)(__ffs(m) - 1) == lane) cnt[d * 32 + warp] = (unsigned short)(old + __popc(m));
+                    if ((int)(__ffs(m) - 1) == lane) cnt[warp * SEG_CSTR + d] = (unsigned short)(old + __popc(m));
                 }
                 __syncwarp();
             }
         }
         __syncthreads();
-        {   // exclusive scan over the 8192 counters in [digit][warp] order: 8 consecutive counters per thread
-            unsigned short* c8 = cnt + tid * 8;
+        {   // exclusive scan over the 8192 counters in (digit, warp) order: thread t takes digit t / 4, warps 8 (t % 4) ..
+            unsigned short* c8 = cnt + (tid & 3) * 8 * SEG_CSTR + (tid >> 2);
             uint32_t loc[8], sum = 0;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) { loc[q] = sum; sum += c8[q]; }
+            for (int q = 0; q < 8; ++q) { loc[q] = sum; sum += c8[q * SEG_CSTR]; }
             uint32_t total;
             const uint32_t off = block_exclusive_scan_1024(sum, s_scan, &total);
 #pragma unroll
-            for (int q = 0; q < 8; ++q) c8[q] = (unsigned short)(off + loc[q]);
+            for (int q = 0; q < 8; ++q) c8[q * SEG_CSTR] = (unsigned short)(off + loc[q]);
         }
         __syncthreads();
 #pragma unroll
@@ -281,7 +288,7 @@ __global__ void __launch_bounds__(SEG_THREADS) k_seg_sort_smem(const u64* __rest
                 if (i < w1) {
                     const unsigned short idx = pin[i];
                     const unsigned d = (keys[idx] >> shift) & (RADIX - 1);
-                    pout[cnt[d * 32 + warp] + rank[j]] = idx;
+                    pout[cnt[warp * SEG_CSTR + d] + rank[j]] = idx;
                 }
             }
         }
