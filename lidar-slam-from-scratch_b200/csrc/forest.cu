@@ -479,8 +479,6 @@ __device__ __forceinline__ void normal_of_point(const TreeDesc& T, const int* nb
     double n0 = 0.0, n1 = 0.0, n2 = 1.0, e0 = 0.0, e1 = 0.0, e2 = 0.0;
     if (m >= 3) {  // icp.hpp:34-37
         double c0 = 0.0, c1 = 0.0, c2 = 0.0;
-        // (both loops: four gathers in flight, the additions still in list order)
-#pragma unroll 4
         for (int j = 0; j < m; ++j) {  // icp.hpp:40-44, neighbours ascending by (d2, idx)
             TreePoint P = load_point(T.pts + T.pt_off + nb[j * stride]);
             c0 += P.x; c1 += P.y; c2 += P.z;
@@ -488,7 +486,6 @@ __device__ __forceinline__ void normal_of_point(const TreeDesc& T, const int* nb
         double md = (double)m;
         c0 /= md; c1 /= md; c2 /= md;
         double C00 = 0, C01 = 0, C02 = 0, C11 = 0, C12 = 0, C22 = 0;
-#pragma unroll 4
         for (int j = 0; j < m; ++j) {  // icp.hpp:47-52
             TreePoint P = load_point(T.pts + T.pt_off + nb[j * stride]);
             double d0 = P.x - c0, d1 = P.y - c1, d2 = P.z - c2;
