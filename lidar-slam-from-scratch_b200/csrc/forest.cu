@@ -395,6 +395,15 @@ __device__ __forceinline__ void load_tree(TreeDesc* dst, const TreeDesc* src, in
     __syncwarp();
 }
 
+// Next work item of a warp: from a device-wide counter (work != nullptr: a grid of resident CTAs whose warps finish
+// at different times keeps all of them busy to the end), else a fixed share (item = warp id + r * warps of the grid).
+__device__ __forceinline__ i64 next_work(int* __restrict__ work, i64 prev, int lane, int warp, int wpb) {
+    if (!work) return prev < 0 ? (i64)blockIdx.x * wpb + warp : prev + (i64)gridDim.x * wpb;
+    int v = 0;
+    if (lane == 0) v = atomicAdd(work, 1);
+    return (i64)__shfl_sync(0xffffffffu, v, 0);
+}
+
 __global__ void __launch_bounds__(QWARPS * 32) k_nearest(ForestView F, const double* __restrict__ q,
                                                          const QueryItem* __restrict__ items, i64 n_items,
                                                          int* __restrict__ out_idx, double* __restrict__ out_d2,
@@ -531,19 +540,20 @@ __device__ __forceinline__ int find_segment(const i64* __restrict__ off, int n, 
 // MODE 0: k-NN of external queries -> out_idx/out_d2 (row-major nq x k)
 // MODE 1: normals of the trees' own points (queries are the sorted points; item.q_off is cloud-local sorted start)
 template <int MODE>
-__global__ void __launch_bounds__(QWARPS * 32) k_knn(ForestView F, const double* __restrict__ q,
+__global__ void __launch_bounds__(QWARPS * 32, 4) k_knn(ForestView F, const double* __restrict__ q,
                                                      const QueryItem* __restrict__ items, i64 n_items, int k,
                                                      int* __restrict__ out_idx, double* __restrict__ out_d2,
                                                      TreeNormal* __restrict__ nrm_sorted,
                                                      NbrEntry* __restrict__ nbr_sorted, double* __restrict__ nrm_orig,
                                                      double* __restrict__ evals_orig, int n_trees_or_zero,
-                                                     unsigned long long* __restrict__ spacing_acc, int qpi) {
+                                                     unsigned long long* __restrict__ spacing_acc, int qpi,
+                                                     int* __restrict__ work) {
     __shared__ WarpStack stacks[QWARPS];
     __shared__ TreeDesc s_tree[QWARPS];
     __shared__ int s_nbr[MODE == 1 ? QWARPS : 1][32][33];  // neighbour positions (cloud-local sorted), padded
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpStack& S = stacks[warp];
-    for (i64 it = (i64)blockIdx.x * QWARPS + warp; it < n_items; it += (i64)gridDim.x * QWARPS) {
+    for (i64 it = next_work(work, -1, lane, warp, QWARPS); it < n_items; it = next_work(work, it, lane, warp, QWARPS)) {
         QueryItem I;
         if (MODE == 1) {
             // implicit items: tree_item_off (passed in `items`' place as i64 prefix sums) -> (tree, 32-point chunk)
@@ -690,7 +700,7 @@ int forest_knn(Ctx* ctx, const Forest* f, const double* d_q, const QueryItem* d_
                int* d_out_idx, double* d_out_d2) {
     if (n_items <= 0) return SB_OK;
     SB_LAUNCH(ctx, k_knn<0>, query_grid(ctx, n_items), QWARPS * 32, 0, view_of(f), d_q, d_items, n_items, k, d_out_idx,
-              d_out_d2, nullptr, nullptr, nullptr, nullptr, 0, nullptr, 32);
+              d_out_d2, nullptr, nullptr, nullptr, nullptr, 0, nullptr, 32, nullptr);
     return SB_OK;
 }
 
@@ -734,9 +744,17 @@ int forest_normals(Ctx* ctx, Forest* f, int k, double* d_out_normals, double* d_
     i64* d_tio;
     unsigned long long* d_spacing;
     SB_TRY(arena_get(ctx, tio.size(), &d_tio));
-    SB_TRY(arena_get(ctx, (size_t)B.n_trees, &d_spacing));
+    SB_TRY(arena_get(ctx, (size_t)B.n_trees + 1, &d_spacing));   // + the work counter of k_knn<1>
     SB_TRY(table_upload(ctx, d_tio, tio.data(), sizeof(i64) * tio.size()));
-    SB_CUDA(ctx, cudaMemsetAsync(d_spacing, 0, sizeof(unsigned long long) * (size_t)B.n_trees, ctx->stream));
+    SB_CUDA(ctx, cudaMemsetAsync(d_spacing, 0, sizeof(unsigned long long) * ((size_t)B.n_trees + 1), ctx->stream));
+    // work items handed out by a counter to a grid of resident CTAs (SB_KNN_DYN = CTAs per SM, 0: fixed shares)
+    static const int dyn = getenv("SB_KNN_DYN") ? atoi(getenv("SB_KNN_DYN")) : 4;
+    int* d_work_knn = dyn > 0 ? reinterpret_cast<int*>(d_spacing + B.n_trees) : nullptr;
+    auto knn_grid = [&](i64 items) -> int {
+        if (!d_work_knn || items >= 0x7fff0000LL) return query_grid(ctx, items);
+        const i64 blocks = (items + QWARPS - 1) / QWARPS, cap = (i64)ctx->sm_count * dyn;
+        return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+    };
     SB_CUDA(ctx, cudaMemsetAsync(B.grid, 0xff, sizeof(GridSlot) * (size_t)B.n_slots, ctx->stream));
     // one lane per query (k_self_knn) for the k the pipelines use; SB_KNN_PACKET=0 or any other k: one warp per query
     static const bool packet = !(getenv("SB_KNN_PACKET") && atoi(getenv("SB_KNN_PACKET")) == 0);
@@ -755,9 +773,9 @@ int forest_normals(Ctx* ctx, Forest* f, int k, double* d_out_normals, double* d_
         i64* d_tq;
         SB_TRY(arena_get(ctx, tq.size(), &d_tq));
         SB_TRY(table_upload(ctx, d_tq, tq.data(), sizeof(i64) * tq.size()));
-        SB_LAUNCH(ctx, k_knn<1>, query_grid(ctx, tq[B.n_trees]), QWARPS * 32, 0, view_of(f, B.t0), nullptr,
+        SB_LAUNCH(ctx, k_knn<1>, knn_grid(tq[B.n_trees]), QWARPS * 32, 0, view_of(f, B.t0), nullptr,
                   reinterpret_cast<const QueryItem*>(d_tq), tq[B.n_trees], k, nullptr, nullptr, B.normals, B.nbr,
-                  d_out_normals, d_out_evals, B.n_trees, d_spacing, qpi);
+                  d_out_normals, d_out_evals, B.n_trees, d_spacing, qpi, tq[B.n_trees] < 0x7fff0000LL ? d_work_knn : nullptr);
     } else if (packet && (k == 20 || (k == 10 && packet10))) {
         static const bool want_stats = getenv("SB_KNN_STATS") != nullptr;
         static const int pcap = getenv("SB_KNN_PCAP") ? atoi(getenv("SB_KNN_PCAP")) : 48;
@@ -773,8 +791,9 @@ int forest_normals(Ctx* ctx, Forest* f, int k, double* d_out_normals, double* d_
         RedoEntry* d_redo;
         int* d_redo_count;
         SB_TRY(arena_get(ctx, (size_t)B.n_points, &d_redo));
-        SB_TRY(arena_get(ctx, (size_t)1, &d_redo_count));
-        SB_CUDA(ctx, cudaMemsetAsync(d_redo_count, 0, sizeof(int), ctx->stream));
+        SB_TRY(arena_get(ctx, (size_t)4, &d_redo_count));   // [1], [2]: the work counters of k_self_knn and k_knn_redo
+        SB_CUDA(ctx, cudaMemsetAsync(d_redo_count, 0, 4 * sizeof(int), ctx->stream));
+        int* d_work = (dyn > 0 && n_items < 0x7fff0000LL) ? d_redo_count + 1 : nullptr;
         static const int tot10 = getenv("SB_KNN_TOT10") ? atoi(getenv("SB_KNN_TOT10")) : 16;
         auto launch = [&](auto kern, int cap_entries) -> int {
             const int row = k | 1;
@@ -785,8 +804,9 @@ int forest_normals(Ctx* ctx, Forest* f, int k, double* d_out_normals, double* d_
                 SB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 ctx->knn_attr_done |= bit;
             }
-            SB_LAUNCH(ctx, kern, grid, PWARPS * 32, smem, view_of(f, B.t0), d_tio, n_items, B.n_trees, B.nbr, d_redo,
-                      d_redo_count, d_stats);
+            const int g = d_work ? (int)std::min<i64>(blocks, (i64)ctx->sm_count * dyn) : grid;
+            SB_LAUNCH(ctx, kern, g, PWARPS * 32, smem, view_of(f, B.t0), d_tio, n_items, B.n_trees, B.nbr, d_redo,
+                      d_redo_count, d_stats, d_work);
             return SB_OK;
         };
 #define SB_SELF_KNN(KK, TT, CAP) (want_stats ? launch(k_self_knn<KK, TT, CAP, true>, CAP) : launch(k_self_knn<KK, TT, CAP, false>, CAP))
@@ -795,7 +815,8 @@ int forest_normals(Ctx* ctx, Forest* f, int k, double* d_out_normals, double* d_
         else if (tot10 == 16) SB_TRY(SB_SELF_KNN(10, 16, 48));
         else SB_TRY(SB_SELF_KNN(10, 32, 48));
 #undef SB_SELF_KNN
-        SB_LAUNCH(ctx, k_knn_redo, ctx->sm_count * 8, QWARPS * 32, 0, view_of(f, B.t0), d_redo, d_redo_count, k, B.nbr);
+        SB_LAUNCH(ctx, k_knn_redo, ctx->sm_count * 8, QWARPS * 32, 0, view_of(f, B.t0), d_redo, d_redo_count, k, B.nbr,
+                  d_work ? d_redo_count + 2 : nullptr);
         SB_LAUNCH(ctx, k_normals_from_graph, (unsigned)((n_items * 32 + 255) / 256), 256, 0, view_of(f, B.t0), d_tio,
                   n_items, B.n_trees, k, B.nbr, B.pts, B.normals, d_out_normals, d_out_evals, d_spacing);
         if (d_stats) {
@@ -809,9 +830,9 @@ int forest_normals(Ctx* ctx, Forest* f, int k, double* d_out_normals, double* d_
                     h[PS_ROUNDS] / np, h[PS_MERGES] / np, h[PS_REDO] / np);
         }
     } else {
-        SB_LAUNCH(ctx, k_knn<1>, query_grid(ctx, n_items), QWARPS * 32, 0, view_of(f, B.t0), nullptr,
+        SB_LAUNCH(ctx, k_knn<1>, knn_grid(n_items), QWARPS * 32, 0, view_of(f, B.t0), nullptr,
                   reinterpret_cast<const QueryItem*>(d_tio), n_items, k, nullptr, nullptr, B.normals, B.nbr, d_out_normals,
-                  d_out_evals, B.n_trees, d_spacing, 32);
+                  d_out_evals, B.n_trees, d_spacing, 32, n_items < 0x7fff0000LL ? d_work_knn : nullptr);
     }
     // seed grid for icp.cu (cell size from the measured point spacing)
     SB_LAUNCH(ctx, k_grid_params, ceil_div(B.n_trees, 128), 128, 0, d_bt, d_spacing, B.n_trees);

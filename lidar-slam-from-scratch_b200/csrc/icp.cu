@@ -64,6 +64,7 @@ struct IcpJob {
     int packet_min;             // open lanes of a work item from which the packet traversal takes over (SB_ICP_PACKET_MIN)
     int passes;                 // batch passes run so far (launch accounting)
     int pad2;
+    int work[4];                // next work item of k_icp_match / k_icp_fallback / k_icp_accum in this pass (reset with q_count)
     i64 n_act_items;            // = act_off[n_act]
 };
 
@@ -71,7 +72,10 @@ static constexpr int IWARPS = 8;
 static constexpr int NSUM = 29;      // 21 of J^T J, 6 of J^T r, sum r^2, and the number of points with a correspondence
 static constexpr int ITEM_Q = 32;   // source points per warp work item: one per lane
 static constexpr int PACKET_MIN_ITEMS = 32768;  // work items of a pass (32 source points each) from which packets are used
-static constexpr int MAX_HOPS = 6;  // re-centrings of the neighbour-graph walk before the tree takes over
+#ifndef SB_MAX_HOPS
+#define SB_MAX_HOPS 6
+#endif
+static constexpr int MAX_HOPS = SB_MAX_HOPS;  // re-centrings of the neighbour-graph walk before the tree takes over
 
 // -------------------------------------------------------------------------------------------------------------
 // Block-wide (256 threads): the list of pairs in state `want` and the prefix sums of their work items.  The passes
@@ -150,6 +154,7 @@ __global__ void __launch_bounds__(256) k_icp_init(IcpJob* __restrict__ job, cuda
     build_active(job, loop ? ST_ACTIVE : ST_EXHAUSTED, false);
     if (threadIdx.x == 0) {
         job->q_count = 0;
+        job->work[0] = job->work[1] = job->work[2] = 0;
         if (use_cond) cudaGraphSetConditional(cond, loop ? 1u : 0u);
     }
 }
@@ -179,6 +184,39 @@ __device__ __forceinline__ int find_active(const i64* __restrict__ off, int n, i
     }
     return lo;
 }
+
+// Work distribution of the three per-pass kernels: the warps of a grid of resident CTAs take their work items from a
+// device-wide counter, `chunk` consecutive items per fetch.  With fixed shares (item = warp id + r * warps of the
+// grid, until round 2) the CTA slots of the early finishers idled while one warp of the CTA still walked its last
+// items — a work item costs anything between 32 one-load proofs and a packet traversal of the tree.  A pass with no
+// more items than the grid has warps (few pairs left, a single pair) costs what its longest chain costs: there warp w
+// takes item w, without the round trip to the counter.
+struct WorkIter {   // (item counts are below 2^31 / 32: icp_enqueue checks)
+    int* counter;
+    int n, cur, end, chunk, lane;
+    __device__ __forceinline__ WorkIter(int* c, i64 n_, int lane_, int gwarp, int gwarps, int chunk_)
+        : counter(c), n((int)n_), cur(-1), end(0), chunk(chunk_), lane(lane_) {
+        if (n <= gwarps) { chunk = 0; cur = gwarp; }
+    }
+    __device__ __forceinline__ bool next(i64& it) {
+        if (chunk == 0) {            // one item per warp
+            it = cur;
+            const bool have = cur < n;
+            cur = n;
+            return have;
+        }
+        if (cur + 1 >= end) {        // cur: the item handed out last; end: the end of the chunk in hand
+            int v = 0;
+            if (lane == 0) v = atomicAdd(counter, chunk);
+            cur = __shfl_sync(0xffffffffu, v, 0);
+            end = cur + chunk;
+        } else {
+            ++cur;
+        }
+        it = cur;
+        return cur < n;
+    }
+};
 
 // upper bound of sqrt(d2), with 1e-6 of slack for the rounding of d2 itself
 __device__ __forceinline__ float sqrt_up(double d2) {
@@ -334,7 +372,9 @@ __global__ void __launch_bounds__(IWARPS * 32, 5) k_icp_match(IcpJob* __restrict
     const int n_act = job->n_act;
     const int K = job->nbr_k;
     const int packet_min = job->packet_min;
-    for (i64 ai = (i64)blockIdx.x * IWARPS + warp; ai < n_act_items; ai += (i64)gridDim.x * IWARPS) {
+    WorkIter W(&job->work[0], n_act_items, lane, (int)(blockIdx.x * IWARPS + warp), (int)(gridDim.x * IWARPS), n_act_items >= 262144 ? 4 : 1);
+    i64 ai;
+    while (W.next(ai)) {
         const int a = find_active(job->act_off, n_act, ai, lane);
         const int pair = job->act_pair[a];
         const PairDesc P = job->pairs[pair];
@@ -392,7 +432,11 @@ __global__ void __launch_bounds__(IWARPS * 32) k_icp_fallback(IcpJob* __restrict
     WarpStack& S = stacks[warp];
     const ForestView F = job->F;
     const int n = job->q_count;
-    for (int e = blockIdx.x * IWARPS + warp; e < n; e += gridDim.x * IWARPS) {
+    // (one entry per fetch: a point and a whole item by packet traversal differ too much to be taken in groups)
+    WorkIter W(&job->work[1], (i64)n, lane, (int)(blockIdx.x * IWARPS + warp), (int)(gridDim.x * IWARPS), 1);
+    i64 e64;
+    while (W.next(e64)) {
+        const int e = (int)e64;
         const FallbackEntry E = job->queue[e];
         const i64 it = E.q / ITEM_Q;
         const int pair = E.pad >> 1;   // (a binary search over all pairs' item offsets — ten dependent loads — until round 2)
@@ -499,7 +543,11 @@ __global__ void __launch_bounds__(IWARPS * 32, 5) k_icp_accum(const IcpJob* __re
     const ForestView F = job->F;
     const i64 n_act_items = job->n_act_items;
     const int n_act = job->n_act;
-    for (i64 ai = (i64)blockIdx.x * IWARPS + warp; ai < n_act_items; ai += (i64)gridDim.x * IWARPS) {
+    // (most items were finished by k_icp_match — a look at a flag: sixteen per fetch)
+    WorkIter W(const_cast<int*>(&job->work[2]), n_act_items, lane, (int)(blockIdx.x * IWARPS + warp), (int)(gridDim.x * IWARPS),
+               n_act_items >= 262144 ? 16 : 1);
+    i64 ai;
+    while (W.next(ai)) {
         const int a = find_active(job->act_off, n_act, ai, lane);
         const int pair = job->act_pair[a];
         const PairDesc P = job->pairs[pair];
@@ -810,6 +858,7 @@ __global__ void __launch_bounds__(256) k_icp_solve(IcpJob* __restrict__ job, int
             if (threadIdx.x == 0) {
                 job->ticket = 0;
                 job->q_count = 0;
+                job->work[0] = job->work[1] = job->work[2] = 0;
                 job->passes += 1;
                 if (use_cond) cudaGraphSetConditional(cond, active > 0 ? 1u : 0u);
             }
@@ -957,7 +1006,9 @@ static void icp_graph_destroy(IcpGraph* G) {
 
 static int icp_graph_build(Ctx* ctx, IcpGraph* G) {
     SB_CUDA(ctx, cudaMalloc(&G->d_job, sizeof(IcpJob)));
-    G->iter_grid = ctx->sm_count * (getenv("SB_ICP_GRID") ? atoi(getenv("SB_ICP_GRID")) : 32);
+    // resident CTAs that take their work items from a counter (WorkIter): 8 per SM (SB_ICP_GRID; measured: 5 or 8
+    // alike, 4 and 16 slower)
+    G->iter_grid = ctx->sm_count * (getenv("SB_ICP_GRID") ? atoi(getenv("SB_ICP_GRID")) : 8);
     G->solve_grid = ctx->sm_count * 4;
     if (getenv("SB_ICP_STATS")) {
         SB_CUDA(ctx, cudaMalloc(&G->d_stats, 8 * sizeof(unsigned long long)));

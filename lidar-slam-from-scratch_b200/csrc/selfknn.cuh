@@ -248,7 +248,7 @@ template <int K, int TOT, int PCAP, bool STATS>
 __global__ void __launch_bounds__(PWARPS * 32, 4) k_self_knn(ForestView F, const i64* __restrict__ tio, i64 n_items,
                                                           int n_trees, NbrEntry* __restrict__ nbr_sorted,
                                                           RedoEntry* __restrict__ redo_list, int* __restrict__ redo_count,
-                                                          unsigned long long* __restrict__ stats) {
+                                                          unsigned long long* __restrict__ stats, int* __restrict__ work) {
     constexpr int ROW = K | 1;   // int2 entries per row of the output staging: odd, so that rows start on different banks
     constexpr int ENTRIES = (32 * ROW > PCAP * 32) ? 32 * ROW : PCAP * 32;
     extern __shared__ __align__(16) unsigned char s_dyn[];
@@ -259,7 +259,16 @@ __global__ void __launch_bounds__(PWARPS * 32, 4) k_self_knn(ForestView F, const
     // rows (entry j of query l at + (l * ROW + j) * 8); always addressed through the shared window (sts64 / lds64)
     const unsigned rows = (unsigned)__cvta_generic_to_shared(s_dyn) + (unsigned)warp * (unsigned)(ENTRIES * 8);
     WarpStack& S = stacks[warp];
-    for (i64 it = (i64)blockIdx.x * PWARPS + warp; it < n_items; it += (i64)gridDim.x * PWARPS) {
+    // Packets are handed out by a device-wide counter (work != nullptr) to a grid of resident CTAs: a packet costs
+    // anything between a few and a few dozen leaves, and with a fixed share per warp the CTA slots of the early
+    // finishers idled (ncu: 13 of 16 warps per SM active on average).
+    auto next_item = [&](i64 prev) -> i64 {
+        if (!work) return prev < 0 ? (i64)blockIdx.x * PWARPS + warp : prev + (i64)gridDim.x * PWARPS;
+        int v = 0;
+        if (lane == 0) v = atomicAdd(work, 1);
+        return (i64)__shfl_sync(0xffffffffu, v, 0);
+    };
+    for (i64 it = next_item(-1); it < n_items; it = next_item(it)) {
         const int t = find_segment(tio, n_trees, it);
         const int q_off = (int)(it - tio[t]) * 32;
         __syncwarp();
@@ -349,13 +358,13 @@ __global__ void __launch_bounds__(PWARPS * 32, 4) k_self_knn(ForestView F, const
 // order; rewrites the query's row of the neighbour graph.
 __global__ void __launch_bounds__(QWARPS * 32) k_knn_redo(ForestView F, const RedoEntry* __restrict__ redo_list,
                                                           const int* __restrict__ redo_count, int k,
-                                                          NbrEntry* __restrict__ nbr_sorted) {
+                                                          NbrEntry* __restrict__ nbr_sorted, int* __restrict__ work) {
     __shared__ WarpStack stacks[QWARPS];
     __shared__ TreeDesc s_tree[QWARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpStack& S = stacks[warp];
     const int n = *redo_count;
-    for (int e = blockIdx.x * QWARPS + warp; e < n; e += gridDim.x * QWARPS) {
+    for (i64 e = next_work(work, -1, lane, warp, QWARPS); e < n; e = next_work(work, e, lane, warp, QWARPS)) {
         const RedoEntry E = redo_list[e];
         __syncwarp();
         load_tree(&s_tree[warp], &F.trees[E.tree], lane);

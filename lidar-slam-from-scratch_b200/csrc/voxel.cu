@@ -256,7 +256,10 @@ static constexpr int VQ_COARSE_TZ = 11;                // a coordinate is "coars
 static constexpr double VQ_LIMIT_COARSE = 524288.0;    // 2^19: sum|v| below this -> no wrap, fp64 loop exact (coarse)
 static constexpr double VQ_LIMIT_FINE = 512.0;         // 2^(53-44): sum|v| bound when some member is finer
 static constexpr int VK_BIAS = 1 << 20;                // keys are packed as (k + 2^20), 21 bits per axis
-static constexpr int VGROUP = 4;                       // lanes of one run whose sums are combined before the atomics
+#ifndef SB_VGROUP
+#define SB_VGROUP 8
+#endif
+static constexpr int VGROUP = SB_VGROUP;                       // lanes of one run whose sums are combined before the atomics
 static constexpr int VROWS = 4;                        // rows per thread and block iteration
 static constexpr int VTILE = 256 * VROWS;              // rows per block iteration
 static constexpr int PATCH_CAP = 4096;                 // members of unproven voxels that the patch-up pass can take

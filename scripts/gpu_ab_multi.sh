@@ -1,13 +1,15 @@
 #!/bin/bash
 # A/B/C... of several builds of the library in one gpurun call: bench.py (device-resident C5 step only) on every
-# lidar-slam-from-scratch_b200/libslam_b200_<name>.so named in LIBS, ROUNDS times in alternation.
+# lidar-slam-from-scratch_b200/libslam_b200_<name>.so named in LIBS (or the current build with the environment
+# ENV_<name>), ROUNDS times in alternation.
 mkdir -p gpurun_out
 P=lidar-slam-from-scratch_b200
 for r in $(seq 1 ${ROUNDS:-2}); do
 for v in $LIBS; do
   lib=$P/libslam_b200_$v.so
-  [ -f $lib ] || { echo "no $lib"; continue; }
-  SB_LIB_PATH=$PWD/$lib timeout 900 python bench.py --steps ${STEPS:-3} --warmup 3 --no-e2e --cpu-seconds 0.1 ${BENCH_ARGS:---no-sub} \
+  [ -f $lib ] || lib=$P/libslam_b200.so      # a name without a build of its own: the current build + ENV_<name>="A=1 B=2"
+  envs=$(eval echo \$ENV_$v)
+  env $envs SB_LIB_PATH=$PWD/$lib timeout 900 python bench.py --steps ${STEPS:-3} --warmup 3 --no-e2e --cpu-seconds 0.1 ${BENCH_ARGS:---no-sub} \
       >> gpurun_out/abm_$v.json 2>> gpurun_out/abm_$v.err
   rc=$?
   tail -1 gpurun_out/abm_$v.json | python -c "
