@@ -471,8 +471,9 @@ __device__ __forceinline__ void jacobi3(double (&A)[3][3], double (&w)[3], doubl
 #pragma unroll
         for (int j = 0; j < 3; ++j) V[i][j] = (i == j) ? 1.0 : 0.0;
     for (int sweep = 0; sweep < 12; ++sweep) {
+        // converged: the rotations left are the identity in fp64 (same test, same expression as the oracle's jacobi3)
         double off = fabs(A[0][1]) + fabs(A[0][2]) + fabs(A[1][2]);
-        if (off == 0.0) break;
+        if (off <= 1.0e-25 * ((fabs(A[0][0]) + fabs(A[1][1])) + fabs(A[2][2]))) break;
         jacobi_rotate<0, 1, 2>(A, V);
         jacobi_rotate<0, 2, 1>(A, V);
         jacobi_rotate<1, 2, 0>(A, V);

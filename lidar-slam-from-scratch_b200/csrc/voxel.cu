@@ -501,7 +501,8 @@ __global__ void __launch_bounds__(256) k_vox_finalize(const u64* __restrict__ ke
         const double B = dc * ((double)(kk[a] < 0 ? -kk[a] : kk[a]) + 1.0) * voxel * 1.0001;
         proven = proven && B < ((fl >> a) & 1u ? VQ_LIMIT_FINE : VQ_LIMIT_COARSE);
     }
-    S->flags = proven ? 0u : (unsigned)(v + 1);
+    const unsigned want = proven ? 0u : (unsigned)(v + 1);
+    if (fl != want) S->flags = want;   // (almost never: an unconditional store dirtied every accumulator sector)
     if (!proven) atomicAdd(n_unproven, 1);  // rare; lets the member collection skip its pass over all rows
     out_xyz[3 * v + 0] = __ddiv_rn((double)S->sx / VQ_SCALE, dc);  // file_utils.cpp:191
     out_xyz[3 * v + 1] = __ddiv_rn((double)S->sy / VQ_SCALE, dc);
