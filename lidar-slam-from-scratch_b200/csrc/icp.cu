@@ -425,7 +425,7 @@ __global__ void __launch_bounds__(IWARPS * 32, 5) k_icp_match(IcpJob* __restrict
 
 // One warp per queue entry.  A point entry: the exact warp-cooperative tree traversal, started from the best point of
 // the walk.  An item entry (pad == 1, seed = mask of the item's open lanes): one packet traversal for all of them.
-__global__ void __launch_bounds__(IWARPS * 32) k_icp_fallback(IcpJob* __restrict__ job) {
+__global__ void __launch_bounds__(IWARPS * 32, 5) k_icp_fallback(IcpJob* __restrict__ job) {
     __shared__ WarpStack stacks[IWARPS];
     __shared__ TreeDesc s_tree[IWARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
