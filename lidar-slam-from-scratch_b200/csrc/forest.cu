@@ -600,7 +600,7 @@ __global__ void __launch_bounds__(QWARPS * 32, 4) k_knn(ForestView F, const doub
                     // the neighbour graph of icp.cu: position + a lower bound of the distance (padding: -1, +inf)
                     NbrEntry e;
                     e.pos = have ? V.lpos : -1;
-                    e.r = have ? __fmul_rd(__fsqrt_rd(__double2float_rd(V.ld)), 0.999999f) : __int_as_float(0x7f800000);
+                    e.r = have ? sqrt_lower(V.ld) : __int_as_float(0x7f800000);
                     nbr_sorted[(T.pt_off + I.q_off + j) * k + lane] = e;
                     if (lane == 1 && have) spacing += (unsigned long long)(fminf(e.r, 1.0e6f) * 65536.0f);
                     if (lane == 1) const_cast<TreePoint*>(T.pts)[T.pt_off + I.q_off + j].pad = have ? __float_as_int(e.r) : 0;

@@ -220,7 +220,7 @@ struct WorkIter {   // (item counts are below 2^31 / 32: icp_enqueue checks)
 
 // upper bound of sqrt(d2), with 1e-6 of slack for the rounding of d2 itself
 __device__ __forceinline__ float sqrt_up(double d2) {
-    return __fmul_ru(__fsqrt_ru(__double2float_ru(d2)), 1.000001f);
+    return sqrt_upper(d2);
 }
 
 // cur = src * R^T + t with the oracle's association (types.hpp:110-115)
@@ -362,6 +362,39 @@ __device__ __forceinline__ void packet_nearest(const ForestView& F, const TreeDe
 __device__ __forceinline__ void accumulate_item(const IcpJob* __restrict__ job, const TreeDesc& T, i64 it, int lane,
                                                 int my_pos, double cx, double cy, double cz);
 
+// Term T of a source point's contribution to its work item's 29 sums: 0..20 the upper triangle of J^T J row by row,
+// 21..26 J^T r, 27 r^2, 28 the point counts; 29..31 unused.
+template <int T>
+__device__ __forceinline__ double item_term(const double (&J)[6], double b, double cnt) {
+    if constexpr (T < 21) {
+        constexpr int A = T < 6 ? 0 : T < 11 ? 1 : T < 15 ? 2 : T < 18 ? 3 : T < 20 ? 4 : 5;
+        constexpr int first = A == 0 ? 0 : A == 1 ? 6 : A == 2 ? 11 : A == 3 ? 15 : A == 4 ? 18 : 20;
+        return J[A] * J[A + (T - first)];
+    } else if constexpr (T < 27) {
+        return J[T - 21] * b;
+    } else if constexpr (T == 27) {
+        return b * b;
+    } else if constexpr (T == 28) {
+        return cnt;
+    } else {
+        return 0.0;
+    }
+}
+// Slot T (0 <= T < M) after the reduction step with partner lane ^ M: the lane's own bit M decides which of the two
+// slots T, T + M of the step before it keeps; the other goes to the partner.  item_sum<1, 0> = sum `lane` over the warp.
+template <int M, int T>
+__device__ __forceinline__ double item_sum(const double (&J)[6], double b, double cnt, int lane) {
+    if constexpr (M == 32) {
+        return item_term<T>(J, b, cnt);
+    } else {
+        const double lo = item_sum<2 * M, T>(J, b, cnt, lane);
+        const double hi = item_sum<2 * M, T + M>(J, b, cnt, lane);
+        const bool up = (lane & M) != 0;
+        const double keep = up ? hi : lo, send = up ? lo : hi;
+        return keep + shfl_d_xor(send, M);
+    }
+}
+
 // Works on the pairs listed in job->act_pair: the ST_ACTIVE ones inside the loop, the ST_EXHAUSTED ones in the final
 // error pass (icp.hpp:235-252).  Work item = ITEM_Q consecutive source points of one pair (implicit: binary search
 // over the prefix sums act_off), one source point per lane.  Replaces KDTree::nearest_batch (kdtree.hpp:43-59), exact.
@@ -501,39 +534,12 @@ __device__ __forceinline__ void accumulate_item(const IcpJob* __restrict__ job, 
     J[2] = cx * ny - cy * nx;
     J[3] = nx; J[4] = ny; J[5] = nz;
     const double b = ((tx - cx) * nx + (ty - cy) * ny) + (tz - cz) * nz;  // icp.hpp:116
-    // 28 sums over the item points: term i is kept by lane i
-    double mine = 0.0;
-    int t = 0;
-#pragma unroll
-    for (int a = 0; a < 6; ++a) {
-#pragma unroll
-        for (int c = a; c < 6; ++c) {
-            double v = J[a] * J[c];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += shfl_d_xor(v, o);
-            if (lane == t) mine = v;
-            ++t;
-        }
-    }
-#pragma unroll
-    for (int a = 0; a < 6; ++a) {
-        double v = J[a] * b;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += shfl_d_xor(v, o);
-        if (lane == 21 + a) mine = v;
-    }
-    {
-        double v = b * b;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += shfl_d_xor(v, o);
-        if (lane == 27) mine = v;
-    }
-    {
-        double v = my_pos >= 0 ? 1.0 : 0.0;   // points with a correspondence (exact in any order)
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += shfl_d_xor(v, o);
-        if (lane == 28) mine = v;
-    }
+    // 29 sums over the item's 32 points, sum t ending in lane t.  Every sum is the butterfly tree ((v_i + v_{i^16}) +
+    // (v_{i^8} + v_{i^24})) + ..., but instead of 29 separate butterflies (145 shuffle steps) the lanes split the sums
+    // between them as they go: at the step with partner lane ^ m a lane keeps the sums whose index has its own bit m and
+    // sends the others — 16 + 8 + 4 + 2 + 1 = 31 shuffle steps, the same additions on the same operands, the same bits
+    // (item_sum below, evaluated depth first so that five partial sums are live at a time, not thirty-two).
+    const double mine = item_sum<1, 0>(J, b, my_pos >= 0 ? 1.0 : 0.0, lane);
     if (lane < NSUM) job->partials[it * NSUM + lane] = mine;
 }
 

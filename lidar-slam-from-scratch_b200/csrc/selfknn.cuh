@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(PWARPS * 32, 4) k_self_knn(ForestView F, const
                     const double D = dist2_rn(P.x, P.y, P.z, V.qx, V.qy, V.qz);
                     ok = ok && (D > prev);
                     prev = D;
-                    sts32(my_row + 8u * j + 4u, __float_as_int(__fmul_rd(__fsqrt_rd(__double2float_rd(D)), 0.999999f)));
+                    sts32(my_row + 8u * j + 4u, __float_as_int(sqrt_lower(D)));
                     ++m;
                 }
             }
@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(QWARPS * 32) k_knn_redo(ForestView F, const Re
             const bool have = V.lidx != 0x7fffffff;
             NbrEntry o;
             o.pos = have ? V.lpos : -1;
-            o.r = have ? __fmul_rd(__fsqrt_rd(__double2float_rd(V.ld)), 0.999999f) : __int_as_float(0x7f800000);
+            o.r = have ? sqrt_lower(V.ld) : __int_as_float(0x7f800000);
             nbr_sorted[(T.pt_off + E.pos) * (i64)k + lane] = o;
         }
     }
