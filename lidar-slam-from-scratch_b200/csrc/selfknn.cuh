@@ -49,6 +49,14 @@ __device__ __forceinline__ int2 lds64(unsigned addr) {
     asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
     return v;
 }
+__device__ __forceinline__ void sts128(unsigned addr, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
+}
+__device__ __forceinline__ float4 lds128(unsigned addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
 __device__ __forceinline__ int lds32(unsigned addr) {
     int v;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
@@ -98,6 +106,7 @@ struct PacketVisitor {
     const int lane;
     const int own_p0;
     const unsigned buf;        // shared-window address of this lane's column: entry `slot` at buf + slot * 256 = (key bits, position)
+    const unsigned stage;      // shared-window address of the warp's 32 x float4 staging row (SB_LEAF_STAGE)
     double qx, qy, qz;         // this lane's query (NaN for lanes without one: nothing is ever kept)
     float xk[TOT];             // [0, KL): the list's keys, ascending; [KL, TOT): the batch being merged
     int xp[TOT];               // positions (cloud-local, sorted order)
@@ -106,7 +115,8 @@ struct PacketVisitor {
     float beta_max;            // largest beta of any leaf this lane KEPT a candidate of
     int cnt;                   // buffered candidates of this lane
     unsigned st[STATS ? PS_N : 1];
-    __device__ __forceinline__ PacketVisitor(const TreeDesc& t, int l, int p0, unsigned b) : T(t), lane(l), own_p0(p0), buf(b) {}
+    __device__ __forceinline__ PacketVisitor(const TreeDesc& t, int l, int p0, unsigned b, unsigned st_)
+        : T(t), lane(l), own_p0(p0), buf(b), stage(st_) {}
     __device__ __forceinline__ double tau() const { return (double)U_warp; }
     __device__ __forceinline__ void refresh_bounds() {
         U = xk[K - 1];
@@ -135,9 +145,21 @@ struct PacketVisitor {
         unsigned w = buf + (unsigned)cnt * 256u;
         const unsigned w0 = w;
         const float thr = U;
+#if defined(SB_LEAF_STAGE) && SB_LEAF_STAGE
+        // the leaf's 32 candidates: ONE coalesced 512-byte load, lane i fetching candidate i, handed round through
+        // shared memory — as 32 broadcast loads the four lines of a leaf missed one after the other (14 % of the
+        // kernel's stall samples sat on the first use of a candidate)
+        __syncwarp();
+        if (lane < n) sts128(stage + 16u * lane, __ldg(c + lane));
+        __syncwarp();
+#endif
 #pragma unroll 8
         for (int i = 0; i < n; ++i) {
+#if defined(SB_LEAF_STAGE) && SB_LEAF_STAGE
+            const float4 P = lds128(stage + 16u * i);
+#else
             const float4 P = __ldg(c + i);  // same address in every lane: one broadcast load
+#endif
             const float dx = P.x - ox, dy = P.y - oy, dz = P.z - oz;
             const float d = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx));
             const float lo = __fmaf_rd(d, SB_RHO_DN, -beta);
@@ -254,6 +276,9 @@ __global__ void __launch_bounds__(PWARPS * 32, 4) k_self_knn(ForestView F, const
     extern __shared__ __align__(16) unsigned char s_dyn[];
     __shared__ WarpStack stacks[PWARPS];
     __shared__ TreeDesc s_tree[PWARPS];
+#if defined(SB_LEAF_STAGE) && SB_LEAF_STAGE
+    __shared__ __align__(16) float4 s_stage[PWARPS][32];
+#endif
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // candidate buffer during the search (entry `slot` of lane l at + (slot * 32 + l) * 8), then the packet's result
     // rows (entry j of query l at + (l * ROW + j) * 8); always addressed through the shared window (sts64 / lds64)
@@ -282,7 +307,12 @@ __global__ void __launch_bounds__(PWARPS * 32, 4) k_self_knn(ForestView F, const
         }
         bool ok = false;
         if (T.gext < 1.0e15) {   // finite, moderate extent (false for NaN too): the float32 error bounds cannot overflow
-            PacketVisitor<K, TOT, PCAP, STATS> V(T, lane, q_off, rows + (unsigned)lane * 8u);
+#if defined(SB_LEAF_STAGE) && SB_LEAF_STAGE
+            const unsigned stage_addr = (unsigned)__cvta_generic_to_shared(&s_stage[warp][0]);
+#else
+            const unsigned stage_addr = 0u;
+#endif
+            PacketVisitor<K, TOT, PCAP, STATS> V(T, lane, q_off, rows + (unsigned)lane * 8u, stage_addr);
             V.init(lane < count, mx, my, mz);
             V.scan_own(count);
             const float2* b = reinterpret_cast<const float2*>(T.boxes + 6 * (T.box_off[0] + (q_off >> 5)));
@@ -398,8 +428,11 @@ __global__ void __launch_bounds__(256) k_normals_from_graph(ForestView F, const 
     unsigned long long spacing = 0ull;
     if (pos < T.n) {
         const int* row = reinterpret_cast<const int*>(nbr_sorted + (T.pt_off + pos) * (i64)k);
-        int m = 0;
-        while (m < k && row[2 * m] >= 0) ++m;   // valid entries come first
+        int m = k;   // valid entries come first: all k of them unless the cloud has fewer points (one look at the last)
+        if (row[2 * (k - 1)] < 0) {
+            m = 0;
+            while (m < k && row[2 * m] >= 0) ++m;
+        }
         if (k > 1 && m > 1) spacing = (unsigned long long)(fminf(__int_as_float(row[3]), 1.0e6f) * 65536.0f);
         // the nearest-other-point bound into the point's own sector (TreePoint::pad); with k == 1 or a single point
         // nothing is known: 0

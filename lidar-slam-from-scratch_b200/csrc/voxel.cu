@@ -354,11 +354,26 @@ __global__ void __launch_bounds__(256) k_vox_insert(const PointSrc src, const Vo
                     while (true) {
                         unsigned long long cur = __ldcg(&tab[s]);
                         if (cur == VOX_EMPTY) {
+#if !defined(SB_CAS_DEDUPE) || SB_CAS_DEDUPE
+                            // The rows of a run (neighbouring rays, neighbouring lanes) find their voxel's slot empty
+                            // together, and their compare-and-swaps on the one address queue up in L2 (18 % of the
+                            // kernel's stall samples for 1 % of its instructions): one lane per key claims, the
+                            // others take its answer.  Same key = same probe sequence = same slot.
+                            const unsigned peers = __match_any_sync(__activemask(), key);
+                            const int leader = __ffs(peers) - 1;
+                            if (lane == leader) cur = atomicCAS(&tab[s], VOX_EMPTY, key);
+                            cur = __shfl_sync(peers, cur, leader);
+                            if (cur == VOX_EMPTY) {
+                                if (lane == leader) ++claimed;
+                                cur = key;
+                            }
+#else
                             cur = atomicCAS(&tab[s], VOX_EMPTY, key);
                             if (cur == VOX_EMPTY) {
                                 ++claimed;
                                 cur = key;
                             }
+#endif
                         }
                         if (cur == key) { slot = s; break; }
                         s = s + 1u == C.size ? 0u : s + 1u;
