@@ -338,9 +338,9 @@ __device__ __forceinline__ float float_from_ordered_u32(unsigned u) {
 // Exact nearest neighbours of the lanes in `todo` (queries (cx, cy, cz), starting points bpos): one packet traversal
 // for all of them (NearestPacketVisitor, traverse.cuh).  The caller checks T.gext < 1e15 (float32 bounds).
 __device__ __forceinline__ void packet_nearest(const ForestView& F, const TreeDesc& T, WarpStack& S, int lane,
-                                               unsigned todo, double cx, double cy, double cz, int& bpos) {
+                                               unsigned todo, double cx, double cy, double cz, int& bpos, unsigned stage) {
     const bool mine = (todo >> lane) & 1u;
-    NearestPacketVisitor V(T, lane);
+    NearestPacketVisitor V(T, lane, stage);
     V.init(mine, cx, cy, cz, bpos);
     // bounding box of the packet's queries (float32, rounded outwards)
     const float inf = __int_as_float(0x7f800000);
@@ -461,6 +461,7 @@ __global__ void __launch_bounds__(IWARPS * 32, 5) k_icp_match(IcpJob* __restrict
 __global__ void __launch_bounds__(IWARPS * 32, 5) k_icp_fallback(IcpJob* __restrict__ job) {
     __shared__ WarpStack stacks[IWARPS];
     __shared__ TreeDesc s_tree[IWARPS];
+    __shared__ __align__(16) float4 s_stage[IWARPS][32];   // NearestPacketVisitor's staging rows
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpStack& S = stacks[warp];
     const ForestView F = job->F;
@@ -494,7 +495,7 @@ __global__ void __launch_bounds__(IWARPS * 32, 5) k_icp_fallback(IcpJob* __restr
                 transform_point(Tm, reinterpret_cast<const double*>(P.src_pts + s0 + lane), cx, cy, cz);
                 bpos = job->match[E.q + lane];
             }
-            packet_nearest(F, T, S, lane, todo, cx, cy, cz, bpos);
+            packet_nearest(F, T, S, lane, todo, cx, cy, cz, bpos, (unsigned)__cvta_generic_to_shared(&s_stage[warp][0]));
             if ((todo >> lane) & 1u) job->match[E.q + lane] = bpos;
         } else {
             unsigned todo = item_entry ? (unsigned)E.seed : 1u;   // (an item entry of a tree of extreme extent: lane by lane)

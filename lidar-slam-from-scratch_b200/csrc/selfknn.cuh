@@ -49,14 +49,6 @@ __device__ __forceinline__ int2 lds64(unsigned addr) {
     asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
     return v;
 }
-__device__ __forceinline__ void sts128(unsigned addr, float4 v) {
-    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
-}
-__device__ __forceinline__ float4 lds128(unsigned addr) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-    return v;
-}
 __device__ __forceinline__ int lds32(unsigned addr) {
     int v;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
@@ -145,7 +137,7 @@ struct PacketVisitor {
         unsigned w = buf + (unsigned)cnt * 256u;
         const unsigned w0 = w;
         const float thr = U;
-#if defined(SB_LEAF_STAGE) && SB_LEAF_STAGE
+#if SB_LEAF_STAGE
         // the leaf's 32 candidates: ONE coalesced 512-byte load, lane i fetching candidate i, handed round through
         // shared memory — as 32 broadcast loads the four lines of a leaf missed one after the other (14 % of the
         // kernel's stall samples sat on the first use of a candidate)
@@ -155,7 +147,7 @@ struct PacketVisitor {
 #endif
 #pragma unroll 8
         for (int i = 0; i < n; ++i) {
-#if defined(SB_LEAF_STAGE) && SB_LEAF_STAGE
+#if SB_LEAF_STAGE
             const float4 P = lds128(stage + 16u * i);
 #else
             const float4 P = __ldg(c + i);  // same address in every lane: one broadcast load
@@ -276,7 +268,7 @@ __global__ void __launch_bounds__(PWARPS * 32, 4) k_self_knn(ForestView F, const
     extern __shared__ __align__(16) unsigned char s_dyn[];
     __shared__ WarpStack stacks[PWARPS];
     __shared__ TreeDesc s_tree[PWARPS];
-#if defined(SB_LEAF_STAGE) && SB_LEAF_STAGE
+#if SB_LEAF_STAGE
     __shared__ __align__(16) float4 s_stage[PWARPS][32];
 #endif
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -307,7 +299,7 @@ __global__ void __launch_bounds__(PWARPS * 32, 4) k_self_knn(ForestView F, const
         }
         bool ok = false;
         if (T.gext < 1.0e15) {   // finite, moderate extent (false for NaN too): the float32 error bounds cannot overflow
-#if defined(SB_LEAF_STAGE) && SB_LEAF_STAGE
+#if SB_LEAF_STAGE
             const unsigned stage_addr = (unsigned)__cvta_generic_to_shared(&s_stage[warp][0]);
 #else
             const unsigned stage_addr = 0u;

@@ -323,6 +323,22 @@ __device__ __forceinline__ void leaf_local_frame(double qx, double qy, double qz
     beta = __fmul_ru(__fmul_ru(a, a), 1572868.0f);           // 3 * 2^19 + 4
 }
 
+// SB_LEAF_STAGE (default 1): the packet visitors fetch a leaf's 32 float32 candidates with ONE coalesced 512-byte load,
+// lane i taking candidate i, and hand them round through a 512-byte row of shared memory per warp; as 32 broadcast
+// loads the four lines of a leaf missed one after the other (14 % of k_self_knn's and 31 % of the first fallback pass's
+// stall samples sat on the first use of a candidate).
+#ifndef SB_LEAF_STAGE
+#define SB_LEAF_STAGE 1
+#endif
+__device__ __forceinline__ void sts128(unsigned addr, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
+}
+__device__ __forceinline__ float4 lds128(unsigned addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
 // -------------------------------------------------------------------------------------------------------------
 // 1-NN of a PACKET of up to 32 nearby queries, one per lane (icp.cu): the packet shares one traversal (the query is
 // the packet's bounding box); a visited leaf's points are read as leaf-local float32 (one broadcast load per
@@ -339,7 +355,8 @@ struct NearestPacketVisitor {
     int bidx, bpos;  // its original row and sorted position
     float U;         // >= bd (0 for lanes that do not search)
     float U_warp;    // max over lanes
-    __device__ __forceinline__ NearestPacketVisitor(const TreeDesc& t, int l) : T(t), lane(l) {}
+    const unsigned stage;   // shared-window address of the warp's 32 x float4 staging row (SB_LEAF_STAGE)
+    __device__ __forceinline__ NearestPacketVisitor(const TreeDesc& t, int l, unsigned st_) : T(t), lane(l), stage(st_) {}
     __device__ __forceinline__ double tau() const { return (double)U_warp; }
     __device__ __forceinline__ void refresh() {
         U = need ? __double2float_ru(bd) : 0.f;
@@ -369,9 +386,18 @@ struct NearestPacketVisitor {
         const float4* __restrict__ c = T.pts32 + T.pt_off + p0;
         const TreePoint* __restrict__ TP = T.pts + T.pt_off + p0;
         float thr = want ? U : -1.f;   // lanes that do not want this leaf pass nothing
+#if SB_LEAF_STAGE
+        __syncwarp();
+        if (lane < n) sts128(stage + 16u * lane, __ldg(c + lane));
+        __syncwarp();
+#endif
 #pragma unroll 4
         for (int i = 0; i < n; ++i) {
+#if SB_LEAF_STAGE
+            const float4 P32 = lds128(stage + 16u * i);
+#else
             const float4 P32 = __ldg(c + i);  // same address in every lane: one broadcast load
+#endif
             const float dx = P32.x - ox, dy = P32.y - oy, dz = P32.z - oz;
             const float dd = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx));
             const float lo = __fmaf_rd(dd, SB_RHO_DN, -beta);
