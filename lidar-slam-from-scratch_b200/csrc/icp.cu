@@ -49,7 +49,7 @@ struct IcpJob {
     double* partials;           // n_items x 28
     int* act_pair;              // pairs the next pass works on (ascending), rebuilt after every solve
     i64* act_off;               // n_act + 1 prefix sums of their work items
-    unsigned char* item_done;   // n_items: 1 if k_icp_match already wrote the item's partial in this pass
+    int2* open_items;           // (work item, pair) of the items k_icp_match could not finish in this pass: k_icp_accum's list
     FallbackEntry* queue;       // capacity n_items x ITEM_Q
     unsigned long long* stats;  // optional (SB_ICP_STATS): per iteration bucket [queries, answered by the tree]
     double T0[16];
@@ -63,7 +63,7 @@ struct IcpJob {
     int n_act;                  // entries of act_pair
     int packet_min;             // open lanes of a work item from which the packet traversal takes over (SB_ICP_PACKET_MIN)
     int passes;                 // batch passes run so far (launch accounting)
-    int pad2;
+    int n_open;                 // entries of open_items (reset with q_count)
     int work[4];                // next work item of k_icp_match / k_icp_fallback / k_icp_accum in this pass (reset with q_count)
     i64 n_act_items;            // = act_off[n_act]
 };
@@ -154,6 +154,7 @@ __global__ void __launch_bounds__(256) k_icp_init(IcpJob* __restrict__ job, cuda
     build_active(job, loop ? ST_ACTIVE : ST_EXHAUSTED, false);
     if (threadIdx.x == 0) {
         job->q_count = 0;
+        job->n_open = 0;
         job->work[0] = job->work[1] = job->work[2] = 0;
         if (use_cond) cudaGraphSetConditional(cond, loop ? 1u : 0u);
     }
@@ -433,7 +434,12 @@ __global__ void __launch_bounds__(IWARPS * 32, 5) k_icp_match(IcpJob* __restrict
             // what its longest dependency chain costs — measured: 149 vs 79 us per pass with 34 pairs iterating)
             const bool as_item = __popc(todo) >= packet_min && n_act_items >= PACKET_MIN_ITEMS;
             int base = 0;
-            if (lane == 0) base = atomicAdd(&job->q_count, as_item ? 1 : __popc(todo));
+            if (lane == 0) {
+                base = atomicAdd(&job->q_count, as_item ? 1 : __popc(todo));
+                // ... and the item itself goes on k_icp_accum's list (it scanned a done-flag per item before: with three
+                // quarters of the items finished here, most of that kernel was waiting for flags and its work counter)
+                job->open_items[atomicAdd(&job->n_open, 1)] = make_int2((int)it, pair);
+            }
             base = __shfl_sync(0xffffffffu, base, 0);
             FallbackEntry e;
             if (as_item) {
@@ -446,7 +452,6 @@ __global__ void __launch_bounds__(IWARPS * 32, 5) k_icp_match(IcpJob* __restrict
         }
         // every point of the item has its proven correspondence: finish the item here (k_icp_accum skips it)
         if (!todo) accumulate_item(job, T, it, lane, lane < count ? bpos : -1, cx, cy, cz);
-        if (lane == 0) job->item_done[it] = todo ? 0 : 1;
         if (job->stats && lane == 0) {  // SB_ICP_STATS: buckets by iteration: 0, 1, 2..11, >= 12
             int bkt = job->state[pair].iter;
             bkt = bkt >= 12 ? 3 : (bkt >= 2 ? 2 : bkt);
@@ -544,22 +549,19 @@ __device__ __forceinline__ void accumulate_item(const IcpJob* __restrict__ job, 
     if (lane < NSUM) job->partials[it * NSUM + lane] = mine;
 }
 
-// Residuals and sums of the work items that k_icp_match could not finish itself (some point was queued).
+// Residuals and sums of the work items that k_icp_match could not finish itself (some point was queued): the items of
+// job->open_items, one warp each.
 __global__ void __launch_bounds__(IWARPS * 32, 5) k_icp_accum(const IcpJob* __restrict__ job) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const ForestView F = job->F;
-    const i64 n_act_items = job->n_act_items;
-    const int n_act = job->n_act;
-    // (most items were finished by k_icp_match — a look at a flag: sixteen per fetch)
-    WorkIter W(const_cast<int*>(&job->work[2]), n_act_items, lane, (int)(blockIdx.x * IWARPS + warp), (int)(gridDim.x * IWARPS),
-               n_act_items >= 262144 ? 16 : 1);
-    i64 ai;
-    while (W.next(ai)) {
-        const int a = find_active(job->act_off, n_act, ai, lane);
-        const int pair = job->act_pair[a];
+    WorkIter W(const_cast<int*>(&job->work[2]), (i64)job->n_open, lane, (int)(blockIdx.x * IWARPS + warp),
+               (int)(gridDim.x * IWARPS), 1);
+    i64 e;
+    while (W.next(e)) {
+        const int2 E = job->open_items[e];
+        const i64 it = E.x;
+        const int pair = E.y;
         const PairDesc P = job->pairs[pair];
-        const i64 it = P.item_off + (ai - job->act_off[a]);
-        if (job->item_done[it]) continue;  // k_icp_match wrote this item's partial already
         const int s0 = (int)(it - P.item_off) * ITEM_Q;
         const int count = P.n_src - s0 < ITEM_Q ? P.n_src - s0 : ITEM_Q;
         const TreeDesc& T = F.trees[P.tree];
@@ -865,6 +867,7 @@ __global__ void __launch_bounds__(256) k_icp_solve(IcpJob* __restrict__ job, int
             if (threadIdx.x == 0) {
                 job->ticket = 0;
                 job->q_count = 0;
+                job->n_open = 0;
                 job->work[0] = job->work[1] = job->work[2] = 0;
                 job->passes += 1;
                 if (use_cond) cudaGraphSetConditional(cond, active > 0 ? 1u : 0u);
@@ -1112,9 +1115,9 @@ int icp_enqueue(Ctx* ctx, const Forest* f, const std::vector<PairDesc>& pairs_in
     SB_TRY(arena_get(ctx, (size_t)n_pairs, &d_state));
     SB_TRY(arena_get(ctx, ni * NSUM, &d_part));
     FallbackEntry* d_queue;
-    unsigned char* d_item_done;
+    int2* d_open;
     SB_TRY(arena_get(ctx, ni * ITEM_Q, &d_queue));
-    SB_TRY(arena_get(ctx, ni, &d_item_done));
+    SB_TRY(arena_get(ctx, ni, &d_open));
     SB_TRY(arena_get(ctx, (size_t)n_pairs, &d_act_pair));
     SB_TRY(arena_get(ctx, (size_t)n_pairs + 1, &d_act_off));
     SB_CUDA(ctx, cudaMemcpyAsync(d_pairs, pairs.data(), sizeof(PairDesc) * n_pairs, cudaMemcpyHostToDevice, ctx->stream));
@@ -1131,7 +1134,8 @@ int icp_enqueue(Ctx* ctx, const Forest* f, const std::vector<PairDesc>& pairs_in
     job.state = d_state;
     job.partials = d_part;
     job.queue = d_queue;
-    job.item_done = d_item_done;
+    job.open_items = d_open;
+    job.n_open = 0;
     job.q_count = 0;
     job.act_pair = d_act_pair;
     job.act_off = d_act_off;
