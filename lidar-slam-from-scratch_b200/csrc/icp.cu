@@ -13,7 +13,8 @@
 //   k_icp_fallback  one WARP per queued point: the exact warp-cooperative tree traversal of traverse.cuh;
 //   k_icp_accum     one warp per 32 source points: residual + the 29 sums (21 of J^T J, 6 of J^T r, sum r^2, matched
 //                   points), fixed-order shuffle tree, one 232-byte partial per work item (items whose points were
-//                   all settled in k_icp_match are finished there, same device function, same bits);
+//                   all settled in k_icp_match are finished there, same device function, same bits; the others are
+//                   listed in IcpJob::open_items, which is what this kernel works off);
 //   k_icp_solve     one block per pair: adds the pair's partials in item order (run-to-run deterministic), RMS error,
 //                   convergence test (icp.hpp:210-217), 6x6 pivoted LDL^T, Rodrigues (icp.hpp:127-142), T <- delta * T.
 // The loop is a CUDA-graph WHILE node whose condition k_icp_solve's last block sets from the device-side count of
