@@ -7,18 +7,19 @@
 //   k_icp_match     one warp per 32 consecutive source points (in the source's own curve order), one point per lane:
 //                   cur = T * src (never stored); a walk over the target's k-nearest-neighbour graph from the previous
 //                   correspondence that ends with a PROOF that the best point seen is the exact nearest neighbour.
-//                   If many lanes of the item are left without a proof (the first pass: no previous correspondences)
-//                   they are answered together, in place, by ONE packet traversal of the tree
-//                   (NearestPacketVisitor, traverse.cuh); a few open lanes go to a device-wide queue;
-//   k_icp_fallback  one WARP per queued point: the exact warp-cooperative tree traversal of traverse.cuh;
+//                   Lanes left without a proof go to a device-wide queue: one entry per point, or — when an item has
+//                   many of them (the first pass: no previous correspondences) — ONE entry for the item;
+//   k_icp_fallback  one WARP per queue entry: a point by the exact warp-cooperative tree traversal of traverse.cuh, an
+//                   item's open points together by ONE packet traversal (NearestPacketVisitor, traverse.cuh);
 //   k_icp_accum     one warp per 32 source points: residual + the 29 sums (21 of J^T J, 6 of J^T r, sum r^2, matched
 //                   points), fixed-order shuffle tree, one 232-byte partial per work item (items whose points were
 //                   all settled in k_icp_match are finished there, same device function, same bits; the others are
 //                   listed in IcpJob::open_items, which is what this kernel works off);
 //   k_icp_solve     one block per pair: adds the pair's partials in item order (run-to-run deterministic), RMS error,
 //                   convergence test (icp.hpp:210-217), 6x6 pivoted LDL^T, Rodrigues (icp.hpp:127-142), T <- delta * T.
-// The loop is a CUDA-graph WHILE node whose condition k_icp_solve's last block sets from the device-side count of
-// still-active pairs: no host round trip per iteration.  All kernels read their arguments from one device-resident
+// The three per-item kernels run as grids of resident CTAs whose warps take their work from device-wide counters
+// (WorkIter).  The loop is a CUDA-graph WHILE node whose condition k_icp_solve's last block sets from the device-side
+// count of still-active pairs: no host round trip per iteration.  All kernels read their arguments from one device-resident
 // IcpJob, so the instantiated graph is reused by every call on the context.
 #include "traverse.cuh"
 
