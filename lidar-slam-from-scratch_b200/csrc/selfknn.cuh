@@ -329,6 +329,30 @@ __global__ void __launch_bounds__(PWARPS * 32, 4) k_self_knn(ForestView F, const
             const unsigned my_row = rows + (unsigned)(lane * ROW) * 8u;
 #pragma unroll
             for (int j = 0; j < K; ++j) sts64(my_row + 8u * j, V.xp[j], 0x7f800000);
+#ifndef SB_VERIFY_PIPE
+#define SB_VERIFY_PIPE 1
+#endif
+#if SB_VERIFY_PIPE
+            // rolled (code size), software-pipelined by one: the gather of entry j + 1 is in flight while entry j is checked
+            int p_nx = lds32(my_row);
+            TreePoint P_nx = load_point(TP + (p_nx >= 0 ? p_nx : 0));
+#pragma unroll 1
+            for (int j = 0; j < K; ++j) {
+                const int p = p_nx;
+                const TreePoint P = P_nx;
+                if (j + 1 < K) {
+                    p_nx = lds32(my_row + 8u * (j + 1));
+                    P_nx = load_point(TP + (p_nx >= 0 ? p_nx : 0));
+                }
+                if (p >= 0) {
+                    const double D = dist2_rn(P.x, P.y, P.z, V.qx, V.qy, V.qz);
+                    ok = ok && (D > prev);
+                    prev = D;
+                    sts32(my_row + 8u * j + 4u, __float_as_int(sqrt_lower(D)));
+                    ++m;
+                }
+            }
+#else
 #pragma unroll 1
             for (int j = 0; j < K; ++j) {   // rolled on purpose (code size): the positions come back from shared memory
                 const int p = lds32(my_row + 8u * j);
@@ -341,6 +365,7 @@ __global__ void __launch_bounds__(PWARPS * 32, 4) k_self_knn(ForestView F, const
                     ++m;
                 }
             }
+#endif
             // (ii): the best candidate left out is provably farther than the list's last point
             const float v_lo = __fmaf_rd(V.xk[K], SB_RHO2_DN, -2.0f * V.beta_max);
             ok = ok && (m < K || __double2float_ru(prev) < v_lo * 0.99999988f);
